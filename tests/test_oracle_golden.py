@@ -1,0 +1,142 @@
+"""CPU: pin the oracle (oracle/yolo2_oracle.py) against fixtures produced by executing the
+reference's own code (tests/golden/make_golden.py) and against the reference's embedded IoU
+known-answer tests (utils/iou/torch.py:79-113,179-213)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import yolo2_oracle as O
+
+
+def load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def test_topology_matches_reference_keys():
+    sd = O.make_state_dict(0)
+    layers = O.darknet19_layers()
+    assert len(layers) == 23
+    assert sum(v.numel() for k, v in sd.items() if 'running' not in k) == 50655389 - 0
+    assert layers[-1]['cout'] == 125 and layers[-2]['cin'] == 1280
+
+
+def test_backbone_64_every_layer(golden_dir):
+    g = load(golden_dir, 'darknet_64.npz')
+    sd = O.make_state_dict(0)
+    x = O.synth_images(1, 64, 64, seed=10)
+    collect = {}
+    with torch.no_grad():
+        f = O.darknet_forward(sd, x, collect=collect)
+    for key, act in collect.items():
+        ref = g['act_' + key]
+        np.testing.assert_allclose(act.numpy(), ref, rtol=0, atol=2e-5 * max(1.0, np.abs(ref).max()), err_msg=key)
+    np.testing.assert_allclose(f.numpy(), g['feature'], rtol=0, atol=2e-5 * np.abs(g['feature']).max())
+
+
+def test_backbone_416_feature(golden_dir):
+    g = load(golden_dir, 'darknet_416.npz')
+    sd = O.make_state_dict(0)
+    x = O.synth_images(1, 416, 416, seed=0)
+    collect = {}
+    with torch.no_grad():
+        f = O.darknet_forward(sd, x, collect=collect)
+    ref = g['feature']
+    assert np.abs(f.numpy() - ref).max() <= 2e-5 * np.abs(ref).max()
+    for key, act in collect.items():
+        assert abs(act.double().abs().mean().item() - float(g['absmean_' + key])) <= 1e-5 * float(g['absmean_' + key]), key
+        np.testing.assert_allclose(act.flatten()[:64].numpy(), g['head_' + key], rtol=1e-4, atol=1e-5)
+
+
+def test_reorg_bit_exact(golden_dir):
+    g = load(golden_dir, 'reorg.npz')
+    assert np.array_equal(O.reorg(torch.from_numpy(g['x'])).numpy(), g['y'])
+
+
+def test_decode_and_softmax(golden_dir):
+    g = load(golden_dir, 'decode.npz')
+    pred = O.decode(torch.from_numpy(g['feature']), torch.from_numpy(g['anchors']))
+    for k in ('iou', 'center_offset', 'size_norm', 'yx_min', 'yx_max', 'logits'):
+        np.testing.assert_allclose(pred[k].numpy(), g[k], rtol=1e-6, atol=1e-6, err_msg=k)
+    np.testing.assert_allclose(O.class_prob(pred).numpy(), g['prob'], rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize('tag', list('abcdef'))
+def test_nms_indices_exact(golden_dir, tag):
+    g = load(golden_dir, 'nms.npz')
+    keep = O.nms(g['score_' + tag], g['yx_min_' + tag], g['yx_max_' + tag], float(g['overlap_' + tag]))
+    assert keep == g['keep_' + tag].tolist()
+
+
+def test_nms_empty():
+    assert O.nms(np.zeros(0), np.zeros((0, 2)), np.zeros((0, 2))) == []
+
+
+@pytest.mark.parametrize('fix', [1, 0])
+@pytest.mark.parametrize('img', [0, 1])
+def test_postprocess(golden_dir, fix, img):
+    g = load(golden_dir, 'postprocess.npz')
+    d = load(golden_dir, 'decode.npz')
+    iou = torch.from_numpy(d['iou'][img]).reshape(-1)
+    yx_min = torch.from_numpy(d['yx_min'][img]).reshape(-1, 2)
+    yx_max = torch.from_numpy(d['yx_max'][img]).reshape(-1, 2)
+    prob = torch.from_numpy(d['prob'][img]).reshape(-1, 20)
+    tag = 'fix%d_img%d_' % (fix, img)
+    fv = O.filter_visible(iou, yx_min, yx_max, prob, fix, 0.3, 0.005)
+    for name, t in zip(('iou', 'yx_min', 'yx_max', 'prob', 'prob_cls', 'cls'), fv):
+        assert np.array_equal(t.numpy(), g[tag + 'fv_' + name]), name
+    res = O.postprocess(iou, yx_min, yx_max, prob, fix, 0.3, 0.005, 0.45)
+    assert (res is None) == bool(g[tag + 'none'])
+    if res is not None:
+        for name, t in zip(('iou', 'yx_min', 'yx_max', 'cls', 'score'), res):
+            np.testing.assert_allclose(t.numpy(), g[tag + name], rtol=1e-6, atol=0, err_msg=name)
+
+
+def test_postprocess_none(golden_dir):
+    g = load(golden_dir, 'postprocess.npz')
+    assert bool(g['empty_none'])
+    res = O.postprocess(torch.full((845,), 0.1), torch.zeros(845, 2), torch.ones(845, 2), torch.full((845, 20), 0.05), 0, 0.3, 0.005, 0.45)
+    assert res is None
+
+
+def test_iou_known_answers(golden_dir):
+    g = load(golden_dir, 'iou.npz')
+    t = lambda k: torch.from_numpy(g[k])
+    m0 = O.iou_matrix(t('c_min'), t('c_max'), t('d_min'), t('d_max'))
+    np.testing.assert_almost_equal(m0.numpy(), np.zeros((1, 8), np.float32))      # utils/iou/torch.py:79-95 (test0)
+    np.testing.assert_almost_equal(m0.numpy(), g['m0'])
+    m1 = O.iou_matrix(t('a_min'), t('a_max'), t('b_min'), t('b_max'))
+    np.testing.assert_almost_equal(m1.numpy(), np.array([[1 / 7] * 4, [4 / 16] * 4], np.float32))  # :97-113 (test1)
+    assert np.array_equal(m1.numpy(), g['m1'])
+    mb = O.batch_iou_matrix(t('r_min'), t('r_max'), t('s_min'), t('s_max'))
+    assert np.array_equal(mb.numpy(), g['mb'])
+
+
+def test_loss_restatement_self_consistency():
+    """The loss is parity-unpinned by execution (see oracle header); check its closed-form gradient
+    (SURVEY 8a derived spec) against autograd and basic invariants."""
+    torch.manual_seed(0)
+    anchors = O.anchors_yolo_voc()
+    B, S, G = 3, 13, 6
+    feature = (torch.randn(B, 125, S, S) * 0.5).requires_grad_(True)
+    data = O.norm_data(O.synth_targets(B, 416, 416, slots=G), 416, 416, S, S)
+    pred = O.decode(feature, anchors)
+    losses, dbg = O.loss(anchors, data, pred, 0.6)
+    total = O.loss_total(losses)
+    total.backward()
+    pos, neg = dbg['positive'], dbg['negative']
+    assert pos.sum() > 0 and not (pos & neg).any()
+    cnt = B * S * S * 5
+    f = feature.detach().permute(0, 2, 3, 1).reshape(B, S * S, 5, 25)
+    sig = torch.sigmoid(f[..., :3])
+    t_c, t_s = O.fill_norm(dbg['data']['yx_min'], dbg['data']['yx_max'], anchors)
+    gexp = torch.zeros_like(f)
+    p = pos.float(); n = neg.float()
+    gexp[..., 0] = (5 * 2 * (sig[..., 0] - dbg['iou']) * p + 2 * sig[..., 0] * n) * sig[..., 0] * (1 - sig[..., 0]) / cnt
+    gexp[..., 1:3] = 2 * (sig[..., 1:3] - t_c) * sig[..., 1:3] * (1 - sig[..., 1:3]) * p[..., None] / cnt
+    gexp[..., 3:5] = torch.where(pos[..., None], 2 * (f[..., 3:5] - t_s) / cnt, torch.zeros(()))
+    onehot = torch.nn.functional.one_hot(dbg['data']['cls'], 20).float()
+    gexp[..., 5:] = (torch.softmax(f[..., 5:], -1) - onehot) * p[..., None] / (pos.sum() * cnt)
+    gexp = gexp.reshape(B, S, S, 125).permute(0, 3, 1, 2)
+    np.testing.assert_allclose(feature.grad.numpy(), gexp.numpy(), rtol=1e-4, atol=1e-9)
