@@ -1,0 +1,112 @@
+/* libyolo2_b200.so -- C ABI of the B200-native YOLOv2 hot path.
+ *
+ * Drop-in boundary for the Darknet-19 detection path of ruiminshen/yolo2-pytorch.  The reference
+ * has no FFI of its own (it is pure Python over torch); each entry point below
+ * names the reference Python interface it replaces (file:line under /root/reference) -- these
+ * are the calls a maintainer would bind with ctypes (INTEGRATION.md shows the stubs).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer owned by the caller
+ *     (PyTorch owns all storage); the library never allocates or frees device memory that
+ *     outlives the call and never touches the default stream unless `stream` is NULL;
+ *   - `stream` is a cudaStream_t passed as void*; all work is asynchronous on it;
+ *   - return value: 0 = success, >0 = cudaError_t, <0 = library error (YB_ERR_*); a human
+ *     readable message for the calling thread is returned by yb_last_error();
+ *   - there is NO CPU fallback and no silent dispatch: unsupported shapes are errors.
+ *   - activations inside the backbone are fp16 NHWC ("x_ld" = elements between consecutive
+ *     pixels, so a tensor may be a channel slice of a wider buffer); the tensors the reference's
+ *     callers see (input image batch, head feature map, decode outputs) are fp32 in the
+ *     reference's own layouts.
+ */
+#ifndef YOLO2_B200_H_
+#define YOLO2_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* yb_stream_t; /* cudaStream_t */
+
+#define YB_ERR_BAD_ARG (-1)
+#define YB_ERR_UNSUPPORTED (-2)
+#define YB_ERR_DRIVER (-3)
+
+/* yb_conv_bn_act_fwd out_mode */
+#define YB_OUT_F16_NHWC 0
+#define YB_OUT_F32_NCHW 1
+/* yb_conv_bn_act_fwd flags */
+#define YB_CONV_A_TILED 1      /* 1x1 only: fetch A with a plain 2-D tiled TMA instead of im2col mode */
+#define YB_CONV_WIDE_N 2       /* allow the 128x256 tile when Cout % 256 == 0 */
+#define YB_CONV_FORCE_BN(bn) ((bn) << 8) /* testing: force BLOCK_N in {64,128,256} */
+/* yb_filter_nms mode */
+#define YB_FILTER_THRESHOLD 0  /* detect/fix = 0: iou > detect/threshold            (detect.py:56) */
+#define YB_FILTER_FIX 1        /* detect/fix = 1: iou * max prob > threshold_cls    (detect.py:54) */
+#define YB_FILTER_NONE 2       /* plain utils.postprocess.nms over all n boxes */
+
+int yb_version(void);
+const char* yb_last_error(void);
+/* Reads (and clears) the host-mapped debug word a kernel writes before it traps on a pipeline
+ * time-out: out[0] = 0x0BADxxxx code, out[1] = block, out[2] = thread, out[3] = parity. */
+int yb_debug_read(int out[4]);
+
+/* ---- parameter preparation ---------------------------------------------------------------- */
+/* nn.Conv2d weight [Cout,Cin,k,k] fp32 (model/yolo2.py:57) -> fp16 [Cout][k][k][Cin] (mode 0), or
+ * the rotated/transposed data-gradient operand [Cin][k][k][Cout] (mode 1). */
+int yb_pack_weight_f16(const float* w_oihw, void* w_f16, int cout, int cin, int ksize, int mode, yb_stream_t stream);
+/* nn.BatchNorm2d in eval mode (model/yolo2.py:58): scale = gamma / sqrt(var + eps), shift = beta - mean * scale. */
+int yb_bn_fold(const float* gamma, const float* beta, const float* running_mean, const float* running_var, float eps, float* scale,
+               float* shift, int channels, yb_stream_t stream);
+
+/* ---- backbone: model.yolo2.Conv2d.forward (model/yolo2.py:61-65), nn.MaxPool2d (:79), reorg (:33-46) */
+/* layers1.0 + its MaxPool: x fp32 NCHW [B,3,H,W] (the caller's tensor) -> y fp16 NHWC [B,H/2,W/2,32]. */
+int yb_conv0_bn_leaky_pool_fwd(const float* x_nchw, const float* w_oihw, const float* scale, const float* shift, float slope,
+                               void* y_nhwc_f16, int batch, int height, int width, int cout, yb_stream_t stream);
+/* k in {1,3}, stride 1, pad (k-1)/2 conv + per-channel scale/shift + leaky(slope) as a tcgen05
+ * implicit GEMM.  x: fp16 NHWC [B,H,W,Cin] with pixel pitch x_ld; w: fp16 [Cout][k][k][Cin];
+ * y: fp16 NHWC (pixel pitch y_ld, first channel y_ch_off) or fp32 NCHW [B,Cout,H,W].
+ * slope = 1 disables the activation; the head passes scale = 1, shift = bias. */
+int yb_conv_bn_act_fwd(const void* x, const void* w, const float* scale, const float* shift, float slope, void* y, int batch,
+                       int height, int width, int cin, int cout, int ksize, int x_ld, long long y_ld, int y_ch_off, int out_mode,
+                       int flags, yb_stream_t stream);
+/* Same contract on CUDA cores (one thread per output): test/bisect utility, not a product path. */
+int yb_conv_ref_fwd(const void* x, const void* w, const float* scale, const float* shift, float slope, void* y, int batch, int height,
+                    int width, int cin, int cout, int ksize, int x_ld, long long y_ld, int y_ch_off, int out_mode, yb_stream_t stream);
+int yb_maxpool2x2_f16(const void* x, void* y, int batch, int height, int width, int channels, int x_ld, yb_stream_t stream);
+/* space-to-depth(2) on fp16 NHWC into channels [y_ch_off, y_ch_off + 4C) of a y_ld-wide buffer
+ * (this plus y_ch_off of the conv replaces torch.cat, model/yolo2.py:129). */
+int yb_reorg_f16(const void* x, void* y, int batch, int height, int width, int channels, int x_ld, int y_ld, int y_ch_off,
+                 yb_stream_t stream);
+/* model.yolo2.reorg(x, stride_h, stride_w) on the caller's fp32 NCHW tensors (model/yolo2.py:33-46). */
+int yb_reorg_f32_nchw(const float* x, float* y, int batch, int channels, int height, int width, int stride_h, int stride_w,
+                      yb_stream_t stream);
+
+/* ---- head: model.Inference.forward (model/__init__.py:117-135) + F.softmax (detect.py:152) ---- */
+/* feature fp32 [B, A*(5+C), rows, cols]; anchors fp32 [A,2] (height,width).  Outputs: iou [B,cells,A],
+ * center_offset/size_norm/yx_min/yx_max [B,cells,A,2], logits/prob [B,cells,A,C] (prob may be NULL;
+ * logits may be NULL when num_cls == 1). */
+int yb_decode_fwd(const float* feature, const float* anchors_hw, float* iou, float* center_offset, float* size_norm, float* yx_min,
+                  float* yx_max, float* logits, float* prob, int batch, int rows, int cols, int num_anchors, int num_cls,
+                  yb_stream_t stream);
+
+/* ---- detection post-filter: detect.filter_visible + utils.postprocess.nms + detect.postprocess
+ *      (detect.py:51-80, utils/postprocess.py:23-49), one CTA per image, no host sync ---------- */
+/* score [B,n], yx_min/yx_max [B,n,2], prob [B,n,C] (NULL for YB_FILTER_NONE).
+ * n_filtered[B]; n_keep[B]; keep_idx[B,limit] = indices into the filtered arrays in descending
+ * score order (exactly the list utils.postprocess.nms returns); keep_box[B,limit] = the same as
+ * indices into the n input boxes.  If n_det != NULL (fix mode): the (kept box, class) pairs with
+ * iou*prob > threshold_cls in mask.nonzero() order: det_keep (rank in the keep list), det_cls,
+ * det_score, each [B,det_cap]; n_det[B].  Optional (NULL to skip): filt_box[B,n] = input box of each
+ * filtered rank (ascending, the order detect.filter_visible returns), best_cls/best_prob[B,n] =
+ * torch.max(prob, -1) per input box (detect.py:52). */
+int yb_filter_nms(const float* score, const float* yx_min, const float* yx_max, const float* prob, int batch, int n, int num_cls,
+                  int mode, float threshold, float threshold_cls, float overlap, int limit, int* n_filtered, int* n_keep,
+                  int* keep_idx, int* keep_box, int* n_det, int* det_keep, int* det_cls, float* det_score, int det_cap,
+                  int* filt_box, int* best_cls, float* best_prob, yb_stream_t stream);
+/* utils.iou.torch.iou_matrix / batch_iou_matrix (utils/iou/torch.py:47-61,139-153): out [B,n1,n2]. */
+int yb_iou_matrix(const float* yx_min1, const float* yx_max1, const float* yx_min2, const float* yx_max2, float* out, int batch,
+                  int n1, int n2, float min_union, yb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YOLO2_B200_H_ */

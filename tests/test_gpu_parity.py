@@ -1,0 +1,337 @@
+"""GPU parity tests: the CUDA path (through the C ABI via b200.ops / the plugin modules) against
+the CPU oracle (oracle/yolo2_oracle.py) on identical seeded inputs, and against the committed golden
+fixtures produced by the reference itself (tests/golden/*.npz).
+
+Tolerances (BASELINE.json north_star): conv/BN activations within 1e-3 relative (max|d|/max|ref|);
+NMS survivor indices, reorg, pooling, filtering: bit-exact; decode within 1e-5 relative.
+"""
+import configparser
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import yolo2_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+DEV = 'cuda'
+
+
+def rel_err(got, ref):
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+    return ((got - ref).abs().max() / ref.abs().max().clamp_min(1e-30)).item()
+
+
+def make_config(fix):
+    config = configparser.ConfigParser()
+    config.read_dict({'batch_norm': {'enable': '1'},
+                      'detect': {'threshold': '0.3', 'threshold_cls': '0.005', 'fix': str(int(fix)), 'overlap': '0.45'}})
+    return config
+
+
+@pytest.fixture(scope='module')
+def ops():
+    from b200 import ops
+    return ops
+
+
+# ------------------------------------------------------------------------------------------------
+# pure data movement: bit-exact
+# ------------------------------------------------------------------------------------------------
+def test_reorg_f32_golden(ops, golden_dir):
+    g = np.load(os.path.join(golden_dir, 'reorg.npz'))
+    y = ops.reorg_f32_nchw(torch.from_numpy(g['x']).to(DEV))
+    assert np.array_equal(y.cpu().numpy(), g['y'])
+
+
+def test_reorg_public_function_large():
+    import model.yolo2
+    x = torch.randn(4, 64, 26, 26, device=DEV)
+    assert torch.equal(model.yolo2.reorg(x).cpu(), O.reorg(x.cpu()))
+
+
+def test_reorg_f16_into_concat_slice(ops):
+    x = torch.randn(3, 26, 26, 64, device=DEV).half()
+    cat = torch.full((3, 13, 13, 1280), 5.0, dtype=torch.float16, device=DEV)
+    ops.reorg_f16(x, cat, 0)
+    ref = O.reorg(x.float().permute(0, 3, 1, 2).cpu()).permute(0, 2, 3, 1).half()
+    assert torch.equal(cat[..., :256].cpu(), ref)
+    assert bool((cat[..., 256:] == 5).all())
+
+
+def test_maxpool_exact(ops):
+    x = torch.randn(2, 52, 52, 128, device=DEV).half()
+    y = ops.maxpool2x2(x)
+    ref = torch.nn.functional.max_pool2d(x.float().permute(0, 3, 1, 2).cpu(), 2).permute(0, 2, 3, 1).half()
+    assert torch.equal(y.cpu(), ref)
+
+
+# ------------------------------------------------------------------------------------------------
+# IoU / NMS / filter: bit-exact indices
+# ------------------------------------------------------------------------------------------------
+def test_iou_known_answers(golden_dir):
+    import utils.iou.torch as iou
+    g = np.load(os.path.join(golden_dir, 'iou.npz'))
+    t = lambda k: torch.from_numpy(g[k]).to(DEV)
+    m0 = iou.iou_matrix(t('c_min'), t('c_max'), t('d_min'), t('d_max')).cpu().numpy()
+    np.testing.assert_almost_equal(m0, np.zeros((1, 8), np.float32))                                      # utils/iou/torch.py:79-95
+    m1 = iou.iou_matrix(t('a_min'), t('a_max'), t('b_min'), t('b_max')).cpu().numpy()
+    np.testing.assert_almost_equal(m1, np.array([[1 / 7] * 4, [4 / 16] * 4], np.float32))                 # :97-113
+    assert np.array_equal(m1, g['m1'])
+    mb = iou.batch_iou_matrix(t('r_min'), t('r_max'), t('s_min'), t('s_max')).cpu().numpy()
+    assert np.array_equal(mb, g['mb'])                                                                    # bit-exact vs the reference
+
+
+@pytest.mark.parametrize('tag', list('abcdef'))
+def test_nms_golden_exact(golden_dir, tag):
+    import utils.postprocess
+    g = np.load(os.path.join(golden_dir, 'nms.npz'))
+    t = lambda k: torch.from_numpy(g[k + '_' + tag]).to(DEV)
+    keep = utils.postprocess.nms(t('score'), t('yx_min'), t('yx_max'), float(g['overlap_' + tag]))
+    assert keep == g['keep_' + tag].tolist()
+
+
+def test_nms_empty_and_stress():
+    import utils.postprocess
+    assert utils.postprocess.nms(torch.zeros(0, device=DEV), torch.zeros(0, 2, device=DEV), torch.zeros(0, 2, device=DEV)) == []
+    for n, seed, limit in ((4096, 21, 200), (845, 22, 200), (5000, 23, 1000), (33, 24, 5)):
+        score, a, b = O.synth_boxes(n, seed)
+        ref = O.nms(score.numpy(), a.numpy(), b.numpy(), 0.45, limit)
+        got = utils.postprocess.nms(score.to(DEV), a.to(DEV), b.to(DEV), 0.45, limit)
+        assert got == ref, (n, seed)
+
+
+@pytest.mark.parametrize('fix', [1, 0])
+def test_filter_and_postprocess_golden(golden_dir, fix):
+    import detect
+    g = np.load(os.path.join(golden_dir, 'postprocess.npz'))
+    d = np.load(os.path.join(golden_dir, 'decode.npz'))
+    cfg = make_config(fix)
+    for img in (0, 1):
+        iou = torch.from_numpy(d['iou'][img]).reshape(-1).to(DEV)
+        yx_min = torch.from_numpy(d['yx_min'][img]).reshape(-1, 2).to(DEV)
+        yx_max = torch.from_numpy(d['yx_max'][img]).reshape(-1, 2).to(DEV)
+        prob = torch.from_numpy(d['prob'][img]).reshape(-1, 20).to(DEV)
+        tag = 'fix%d_img%d_' % (fix, img)
+        fv = detect.filter_visible(cfg, iou, yx_min, yx_max, prob)
+        for name, t in zip(('iou', 'yx_min', 'yx_max', 'prob', 'prob_cls', 'cls'), fv):
+            assert np.array_equal(t.cpu().numpy(), g[tag + 'fv_' + name]), (name, img)
+        res = detect.postprocess(cfg, iou, yx_min, yx_max, prob)
+        assert (res is None) == bool(g[tag + 'none'])
+        if res is not None:
+            for name, t in zip(('iou', 'yx_min', 'yx_max', 'cls', 'score'), res):
+                ref = g[tag + name]
+                assert t.shape == ref.shape, name
+                if name == 'cls':
+                    assert np.array_equal(t.cpu().numpy(), ref)
+                else:
+                    np.testing.assert_allclose(t.cpu().numpy(), ref, rtol=1e-6, atol=0, err_msg=name)
+
+
+def test_postprocess_none():
+    import detect
+    cfg = make_config(0)
+    res = detect.postprocess(cfg, torch.full((845,), 0.1, device=DEV), torch.zeros(845, 2, device=DEV), torch.ones(845, 2, device=DEV),
+                             torch.full((845, 20), 0.05, device=DEV))
+    assert res is None
+
+
+# ------------------------------------------------------------------------------------------------
+# decode + softmax
+# ------------------------------------------------------------------------------------------------
+def test_decode_golden(ops, golden_dir):
+    g = np.load(os.path.join(golden_dir, 'decode.npz'))
+    out = ops.decode(torch.from_numpy(g['feature']).to(DEV), torch.from_numpy(g['anchors']).to(DEV), 20)
+    for k in ('iou', 'center_offset', 'size_norm', 'yx_min', 'yx_max', 'logits', 'prob'):
+        assert rel_err(out[k], torch.from_numpy(g[k])) <= 1e-5, k
+    assert torch.equal(out['logits'].cpu(), torch.from_numpy(g['logits']))          # pure move
+    assert torch.equal(out['size_norm'].cpu(), torch.from_numpy(g['size_norm']))    # pure move
+
+
+@pytest.mark.parametrize('shape', [(32, 13), (3, 19), (5, 10)])
+def test_decode_vs_oracle(ops, shape):
+    b, s = shape
+    feat = torch.randn(b, 125, s, s, generator=torch.Generator().manual_seed(b * 100 + s)) * 2
+    anchors = O.anchors_yolo_voc()
+    ref = O.decode(feat, anchors)
+    ref['prob'] = O.class_prob(ref)
+    out = ops.decode(feat.to(DEV), anchors.to(DEV), 20)
+    for k in ('iou', 'center_offset', 'size_norm', 'yx_min', 'yx_max', 'logits', 'prob'):
+        assert rel_err(out[k], ref[k]) <= 1e-5, k
+
+
+# ------------------------------------------------------------------------------------------------
+# convolutions (tcgen05 implicit GEMM) vs the oracle arithmetic
+# ------------------------------------------------------------------------------------------------
+CONV_CASES = [
+    # b, h, w, cin, cout, k, flags-name
+    (2, 16, 16, 256, 128, 1, 'tiled'),
+    (2, 16, 16, 256, 128, 1, ''),
+    (2, 16, 16, 64, 128, 3, ''),
+    (3, 13, 13, 128, 256, 3, ''),
+    (2, 26, 26, 128, 64, 3, ''),
+    (2, 13, 13, 256, 512, 3, 'wide'),
+    (1, 32, 32, 32, 64, 3, ''),
+    (8, 52, 52, 128, 256, 3, ''),
+    (32, 13, 13, 512, 1024, 3, ''),
+    (2, 13, 13, 1280, 1024, 3, ''),
+]
+
+
+@pytest.mark.parametrize('case', CONV_CASES)
+def test_conv_unit_vs_oracle(ops, case):
+    b, h, w, cin, cout, k, fl = case
+    gen = torch.Generator().manual_seed(cin * 7 + cout)
+    x = torch.randn(b, cin, h, w, generator=gen)
+    wt = torch.randn(cout, cin, k, k, generator=gen) * (2.0 / (cin * k * k)) ** 0.5
+    sd = {'u.conv.weight': wt, 'u.bn.weight': torch.rand(cout, generator=gen) + 0.5, 'u.bn.bias': torch.randn(cout, generator=gen) * 0.1,
+          'u.bn.running_mean': torch.randn(cout, generator=gen) * 0.1, 'u.bn.running_var': torch.rand(cout, generator=gen) + 0.5}
+    ref = O.conv_unit(x, sd, 'u', k, True, True)                      # fp32 oracle on fp32 operands
+    scale, shift = ops.bn_fold(*(sd['u.bn.' + n].to(DEV) for n in ('weight', 'bias', 'running_mean', 'running_var')))
+    w16 = ops.pack_weight_f16(wt.to(DEV))
+    flags = {'tiled': ops.CONV_A_TILED, 'wide': ops.CONV_WIDE_N, '': 0}[fl]
+    y = ops.conv_bn_act(x.to(DEV).permute(0, 2, 3, 1).contiguous().half(), w16, scale, shift, 0.1, flags=flags)
+    err = rel_err(y.permute(0, 3, 1, 2), ref)
+    assert err <= 1e-3, 'rel err %.3e' % err
+
+
+def test_conv_head_fp32_nchw_and_slice(ops):
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 1024, 13, 13, generator=gen)
+    wt = torch.randn(125, 1024, 1, 1, generator=gen) * (1.0 / 1024) ** 0.5
+    bias = torch.randn(125, generator=gen) * 0.1
+    ref = torch.nn.functional.conv2d(x, wt, bias)
+    y = ops.conv_bn_act(x.to(DEV).permute(0, 2, 3, 1).contiguous().half(), ops.pack_weight_f16(wt.to(DEV)),
+                        torch.ones(125, device=DEV), bias.to(DEV), 1.0, out_mode=ops.OUT_F32_NCHW)
+    assert rel_err(y, ref) <= 1e-3
+    # channel-slice output into a wider buffer (in-place concat)
+    wt2 = torch.randn(64, 1024, 1, 1, generator=gen) * (1.0 / 1024) ** 0.5
+    buf = torch.full((2, 13, 13, 320), 3.0, dtype=torch.float16, device=DEV)
+    ops.conv_bn_act(x.to(DEV).permute(0, 2, 3, 1).contiguous().half(), ops.pack_weight_f16(wt2.to(DEV)), torch.ones(64, device=DEV),
+                    torch.zeros(64, device=DEV), 0.1, out=buf, y_ch_off=128)
+    ref2 = torch.nn.functional.leaky_relu(torch.nn.functional.conv2d(x, wt2), 0.1)
+    assert rel_err(buf[..., 128:192].permute(0, 3, 1, 2), ref2) <= 1e-3
+    assert bool((buf[..., :128] == 3).all()) and bool((buf[..., 192:] == 3).all())
+
+
+def test_conv0_vs_oracle(ops):
+    sd = O.make_state_dict(0)
+    x = O.synth_images(2, 64, 96, seed=3)
+    ref = torch.nn.functional.max_pool2d(O.conv_unit(x, sd, 'layers1.0', 3, True, True), 2)
+    scale, shift = ops.bn_fold(*(sd['layers1.0.bn.' + n].to(DEV) for n in ('weight', 'bias', 'running_mean', 'running_var')))
+    y = ops.conv0_bn_leaky_pool(x.to(DEV), sd['layers1.0.conv.weight'].to(DEV), scale, shift, 0.1)
+    assert rel_err(y.permute(0, 3, 1, 2), ref) <= 1e-3
+
+
+# ------------------------------------------------------------------------------------------------
+# whole backbone through the plugin surface
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope='module')
+def darknet():
+    import model
+    import model.yolo2
+    cfg = make_config(1)
+    dnn = model.yolo2.Darknet(model.ConfigChannels(cfg), O.anchors_yolo_voc(), 20)
+    dnn.load_state_dict(O.make_state_dict(0), strict=False)
+    return dnn.to(DEV).eval()
+
+
+def test_darknet_64_every_layer_golden(darknet, golden_dir):
+    """Each unit on the GPU vs the REFERENCE's own activation for the same image (golden), fed by
+    the GPU's own previous layer (so this is the end-to-end drift, layer by layer)."""
+    g = np.load(os.path.join(golden_dir, 'darknet_64.npz'))
+    x = O.synth_images(1, 64, 64, seed=10).to(DEV)
+    collect = {}
+    feature = darknet.engine.forward(x, collect=collect).clone()
+    worst = 0.0
+    for key, act in collect.items():
+        if 'act_' + key not in g:
+            continue
+        e = rel_err(act.permute(0, 3, 1, 2), torch.from_numpy(g['act_' + key]))
+        worst = max(worst, e)
+        assert e <= 3e-3, '%s rel err %.3e' % (key, e)
+    e = rel_err(feature, torch.from_numpy(g['feature']))
+    print('darknet64 worst layer rel %.3e, feature rel %.3e' % (worst, e))
+    assert e <= 3e-3
+
+
+def test_darknet_416_feature_golden(darknet, golden_dir):
+    g = np.load(os.path.join(golden_dir, 'darknet_416.npz'))
+    x = O.synth_images(1, 416, 416, seed=0).to(DEV)
+    f = darknet(x)
+    e = rel_err(f, torch.from_numpy(g['feature']))
+    print('darknet416 feature rel %.3e' % e)
+    assert f.shape == (1, 125, 13, 13)
+    assert e <= 3e-3
+
+
+def test_darknet_per_layer_on_oracle_inputs(darknet, ops):
+    """every unit on the ORACLE's own input to that layer, rel <= 1e-3."""
+    sd = O.make_state_dict(0)
+    x = O.synth_images(2, 128, 128, seed=4)
+    collect = {}
+    O.darknet_forward(sd, x, collect=collect)
+    layers = O.darknet19_layers()
+    eng = darknet.engine
+    eng.refresh()
+    units = dict(zip([l['key'] for l in layers], eng.units1 + eng.units2 + [eng.unit_pt] + eng.units3))
+    prev = x
+    worst = 0.0
+    for l in layers:
+        key = l['key']
+        if key == 'layers1.0':
+            prev = torch.nn.functional.max_pool2d(collect[key], 2)
+            continue
+        if key == 'passthrough':
+            inp = collect['layers1.16']
+        elif key == 'layers2.1':
+            inp = torch.nn.functional.max_pool2d(collect['layers1.16'], 2)
+        elif key == 'layers3.0':
+            inp = torch.cat([O.reorg(collect['passthrough']), collect['layers2.7']], 1)
+        else:
+            inp = prev
+        u = units[key]
+        mode = ops.OUT_F32_NCHW if key == 'layers3.1' else ops.OUT_F16_NHWC
+        y = ops.conv_bn_act(inp.to(DEV).permute(0, 2, 3, 1).contiguous().half(), u.w16, u.scale, u.shift, u.slope, out_mode=mode)
+        got = y if mode == ops.OUT_F32_NCHW else y.permute(0, 3, 1, 2)
+        e = rel_err(got, collect[key])
+        worst = max(worst, e)
+        assert e <= 1e-3, '%s rel err %.3e' % (key, e)
+        prev = torch.nn.functional.max_pool2d(collect[key], 2) if l['pool_after'] else collect[key]
+    print('per-layer worst rel %.3e' % worst)
+
+
+def test_inference_and_postprocess_batch(darknet):
+    """C2 pipeline through the plugin surface: Inference -> postprocess_batch.  Decode + NMS are
+    checked exactly against the oracle run on the GPU's own feature map (identical inputs)."""
+    import detect
+    import model
+    cfg = make_config(1)
+    anchors = O.anchors_yolo_voc()
+    inference = model.Inference(cfg, darknet, anchors).eval()
+    x = O.synth_images(4, 416, 416, seed=7).to(DEV)
+    pred = model._inference(inference, x)
+    assert pred['feature'].shape == (4, 125, 13, 13) and pred['iou'].shape == (4, 169, 5) and pred['logits'].shape == (4, 169, 5, 20)
+    ref = O.decode(pred['feature'].cpu(), anchors)
+    for k in ('iou', 'center_offset', 'yx_min', 'yx_max'):
+        assert rel_err(pred[k], ref[k]) <= 1e-5, k
+    results = detect.postprocess_batch(cfg, pred)
+    for bi, res in enumerate(results):
+        iou, a, b, p = (pred[k][bi].reshape(-1, *pred[k].shape[3:]).cpu() if pred[k].dim() > 3 else pred[k][bi].reshape(-1).cpu()
+                        for k in ('iou', 'yx_min', 'yx_max', 'prob'))
+        exp = O.postprocess(iou, a, b, p, True, 0.3, 0.005, 0.45)
+        assert (res is None) == (exp is None)
+        if res is not None:
+            for name, t, r in zip(('iou', 'yx_min', 'yx_max', 'cls', 'score'), res, exp):
+                assert t.shape == r.shape, (bi, name)
+                if name == 'cls':
+                    assert torch.equal(t.cpu(), r)
+                else:
+                    np.testing.assert_allclose(t.cpu().numpy(), r.numpy(), rtol=1e-6, atol=0)
+
+
+def test_cpu_input_fails_loudly(darknet):
+    with pytest.raises(RuntimeError):
+        darknet(torch.zeros(1, 3, 64, 64))

@@ -1,0 +1,64 @@
+"""ctypes loader for libyolo2_b200.so.  No fallback: a missing library is an ImportError with build
+instructions, a non-zero return code is a RuntimeError carrying yb_last_error()."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), 'libyolo2_b200.so')
+
+c_int, c_float, c_void_p, c_longlong = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_longlong
+P = c_void_p
+
+# name -> argument ctypes (every function returns int); mirrors include/yolo2_b200.h
+SIGNATURES = {
+    'yb_version': [],
+    'yb_debug_read': [ctypes.POINTER(c_int * 4)],
+    'yb_pack_weight_f16': [P, P, c_int, c_int, c_int, c_int, P],
+    'yb_bn_fold': [P, P, P, P, c_float, P, P, c_int, P],
+    'yb_conv0_bn_leaky_pool_fwd': [P, P, P, P, c_float, P, c_int, c_int, c_int, c_int, P],
+    'yb_conv_bn_act_fwd': [P, P, P, P, c_float, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_longlong, c_int, c_int, c_int, P],
+    'yb_conv_ref_fwd': [P, P, P, P, c_float, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_longlong, c_int, c_int, P],
+    'yb_maxpool2x2_f16': [P, P, c_int, c_int, c_int, c_int, c_int, P],
+    'yb_reorg_f16': [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P],
+    'yb_reorg_f32_nchw': [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P],
+    'yb_decode_fwd': [P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P],
+    'yb_filter_nms': [P, P, P, P, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_int, P, P, P, P, P, P, P, P, c_int, P, P, P, P],
+    'yb_iou_matrix': [P, P, P, P, P, c_int, c_int, c_int, c_float, P],
+}
+
+_lib = None
+
+
+def load():
+    """Load (once) and return the ctypes handle."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            'libyolo2_b200.so not found at %s -- build it with `python yolo2-pytorch_b200/build.py` '
+            '(nvcc, sm_100a).  There is no CPU or PyTorch fallback for this path.' % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.argtypes = argtypes
+        fn.restype = c_int
+    lib.yb_last_error.argtypes = []
+    lib.yb_last_error.restype = ctypes.c_char_p
+    _lib = lib
+    return lib
+
+
+def last_error():
+    return load().yb_last_error().decode('utf-8', 'replace')
+
+
+def debug_read():
+    buf = (c_int * 4)()
+    load().yb_debug_read(ctypes.byref(buf))
+    return list(buf)
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError('%s failed (code %d): %s' % (what, rc, last_error()))

@@ -1,0 +1,201 @@
+"""Tensor-level wrappers of the C ABI: each function checks device/dtype/contiguity, passes raw
+device pointers plus torch's current CUDA stream, and raises RuntimeError on a non-zero code.
+PyTorch is plumbing here (storage + streams); all arithmetic happens in libyolo2_b200.so."""
+import ctypes
+
+import torch
+
+from . import lib as _l
+
+OUT_F16_NHWC, OUT_F32_NCHW = 0, 1
+CONV_A_TILED, CONV_WIDE_N = 1, 2
+FILTER_THRESHOLD, FILTER_FIX, FILTER_NONE = 0, 1, 2
+
+
+def conv_force_bn(bn):
+    return bn << 8
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _s():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _req(t, dtype, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise RuntimeError('%s must be a CUDA tensor: the B200 path has no CPU fallback' % name)
+    if t.dtype != dtype:
+        raise TypeError('%s must be %s, got %s' % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError('%s must be contiguous' % name)
+    return t
+
+
+def pack_weight_f16(w, mode=0):
+    """[Cout,Cin,k,k] fp32 -> fp16 [Cout,k,k,Cin] (mode 0) or [Cin,k,k,Cout] rotated (mode 1)."""
+    _req(w, torch.float32, 'weight')
+    cout, cin, k, _ = w.shape
+    shape = (cout, k, k, cin) if mode == 0 else (cin, k, k, cout)
+    out = torch.empty(shape, dtype=torch.float16, device=w.device)
+    _l.check(_l.load().yb_pack_weight_f16(_p(w), _p(out), cout, cin, k, mode, _s()), 'yb_pack_weight_f16')
+    return out
+
+
+def bn_fold(gamma, beta, mean, var, eps=1e-5):
+    for n, t in (('gamma', gamma), ('beta', beta), ('mean', mean), ('var', var)):
+        _req(t, torch.float32, n)
+    c = gamma.numel()
+    scale = torch.empty(c, dtype=torch.float32, device=gamma.device)
+    shift = torch.empty_like(scale)
+    _l.check(_l.load().yb_bn_fold(_p(gamma), _p(beta), _p(mean), _p(var), float(eps), _p(scale), _p(shift), c, _s()), 'yb_bn_fold')
+    return scale, shift
+
+
+def conv0_bn_leaky_pool(x, w, scale, shift, slope, out=None):
+    """x fp32 NCHW [B,3,H,W] -> fp16 NHWC [B,H/2,W/2,32]."""
+    _req(x, torch.float32, 'x'); _req(w, torch.float32, 'w'); _req(scale, torch.float32, 'scale'); _req(shift, torch.float32, 'shift')
+    b, c, h, wd = x.shape
+    if c != 3:
+        raise ValueError('conv0 expects 3 input channels')
+    cout = w.shape[0]
+    if out is None:
+        out = torch.empty(b, h // 2, wd // 2, cout, dtype=torch.float16, device=x.device)
+    _req(out, torch.float16, 'out')
+    _l.check(_l.load().yb_conv0_bn_leaky_pool_fwd(_p(x), _p(w), _p(scale), _p(shift), float(slope), _p(out), b, h, wd, cout, _s()),
+             'yb_conv0_bn_leaky_pool_fwd')
+    return out
+
+
+def _conv_common(fn_name, x, w, scale, shift, slope, out, batch, height, width, cin, cout, k, x_ld, y_ld, y_ch_off, out_mode, flags):
+    fn = getattr(_l.load(), fn_name)
+    args = [_p(x), _p(w), _p(scale), _p(shift), float(slope), _p(out), batch, height, width, cin, cout, k, x_ld, y_ld, y_ch_off, out_mode]
+    if fn_name == 'yb_conv_bn_act_fwd':
+        args.append(flags)
+    args.append(_s())
+    _l.check(fn(*args), fn_name)
+
+
+def conv_bn_act(x, w, scale, shift, slope, out=None, out_mode=OUT_F16_NHWC, y_ch_off=0, cin=None, flags=0, ref=False):
+    """x: fp16 [B,H,W,x_ld] (uses the first `cin` channels, default all); w: fp16 [Cout,k,k,Cin].
+    out (fp16): [B,H,W,y_ld] written at channels [y_ch_off, y_ch_off+Cout); out (fp32): [B,Cout,H,W]."""
+    _req(x, torch.float16, 'x'); _req(w, torch.float16, 'w'); _req(scale, torch.float32, 'scale'); _req(shift, torch.float32, 'shift')
+    b, h, wd, x_ld = x.shape
+    cout, k, _, wcin = w.shape
+    cin = wcin if cin is None else cin
+    if cin != wcin:
+        raise ValueError('weight Cin %d != %d' % (wcin, cin))
+    if out is None:
+        out = (torch.empty(b, h, wd, cout, dtype=torch.float16, device=x.device) if out_mode == OUT_F16_NHWC
+               else torch.empty(b, cout, h, wd, dtype=torch.float32, device=x.device))
+    if out_mode == OUT_F16_NHWC:
+        _req(out, torch.float16, 'out')
+        y_ld = out.shape[-1]
+    else:
+        _req(out, torch.float32, 'out')
+        y_ld = 0
+    _conv_common('yb_conv_ref_fwd' if ref else 'yb_conv_bn_act_fwd', x, w, scale, shift, slope, out, b, h, wd, cin, cout, k, x_ld, y_ld,
+                 y_ch_off, out_mode, flags)
+    return out
+
+
+def maxpool2x2(x, channels=None, out=None):
+    _req(x, torch.float16, 'x')
+    b, h, w, x_ld = x.shape
+    c = x_ld if channels is None else channels
+    if out is None:
+        out = torch.empty(b, h // 2, w // 2, c, dtype=torch.float16, device=x.device)
+    _req(out, torch.float16, 'out')
+    _l.check(_l.load().yb_maxpool2x2_f16(_p(x), _p(out), b, h, w, c, x_ld, _s()), 'yb_maxpool2x2_f16')
+    return out
+
+
+def reorg_f16(x, out, y_ch_off=0):
+    _req(x, torch.float16, 'x'); _req(out, torch.float16, 'out')
+    b, h, w, c = x.shape
+    _l.check(_l.load().yb_reorg_f16(_p(x), _p(out), b, h, w, c, c, out.shape[-1], y_ch_off, _s()), 'yb_reorg_f16')
+    return out
+
+
+def reorg_f32_nchw(x, stride_h=2, stride_w=2):
+    _req(x, torch.float32, 'x')
+    b, c, h, w = x.shape
+    out = torch.empty(b, c * stride_h * stride_w, h // stride_h, w // stride_w, dtype=torch.float32, device=x.device)
+    if out.numel():
+        _l.check(_l.load().yb_reorg_f32_nchw(_p(x), _p(out), b, c, h, w, stride_h, stride_w, _s()), 'yb_reorg_f32_nchw')
+    return out
+
+
+def decode(feature, anchors, num_cls, with_prob=True):
+    """feature fp32 [B,A*(5+C),rows,cols] -> dict(iou, center_offset, size_norm, yx_min, yx_max[, logits, prob])."""
+    _req(feature, torch.float32, 'feature'); _req(anchors, torch.float32, 'anchors')
+    b, ch, rows, cols = feature.shape
+    a = anchors.shape[0]
+    cells = rows * cols
+    dev = feature.device
+    out = dict(
+        iou=torch.empty(b, cells, a, dtype=torch.float32, device=dev),
+        center_offset=torch.empty(b, cells, a, 2, dtype=torch.float32, device=dev),
+        size_norm=torch.empty(b, cells, a, 2, dtype=torch.float32, device=dev),
+        yx_min=torch.empty(b, cells, a, 2, dtype=torch.float32, device=dev),
+        yx_max=torch.empty(b, cells, a, 2, dtype=torch.float32, device=dev),
+    )
+    logits = prob = None
+    if num_cls > 1:
+        logits = out['logits'] = torch.empty(b, cells, a, num_cls, dtype=torch.float32, device=dev)
+    if with_prob:
+        prob = out['prob'] = torch.empty(b, cells, a, max(num_cls, 1), dtype=torch.float32, device=dev)
+    if ch != a * (5 + (num_cls if num_cls > 1 else 0)):
+        raise ValueError('feature has %d channels, expected %d' % (ch, a * (5 + (num_cls if num_cls > 1 else 0))))
+    _l.check(_l.load().yb_decode_fwd(_p(feature), _p(anchors), _p(out['iou']), _p(out['center_offset']), _p(out['size_norm']),
+                                     _p(out['yx_min']), _p(out['yx_max']), _p(logits), _p(prob), b, rows, cols, a, num_cls, _s()),
+             'yb_decode_fwd')
+    return out
+
+
+def filter_nms(score, yx_min, yx_max, prob, mode, threshold, threshold_cls, overlap, limit=200, expand=False, details=False):
+    """Batched filter + NMS (+ per-class expansion).  score [B,n], yx_* [B,n,2], prob [B,n,C] or None.
+    Returns a dict of int32/float32 device tensors (see include/yolo2_b200.h: yb_filter_nms)."""
+    _req(score, torch.float32, 'score'); _req(yx_min, torch.float32, 'yx_min'); _req(yx_max, torch.float32, 'yx_max')
+    if prob is not None:
+        _req(prob, torch.float32, 'prob')
+    b, n = score.shape
+    num_cls = prob.shape[-1] if prob is not None else 1
+    dev = score.device
+    i32 = dict(dtype=torch.int32, device=dev)
+    res = dict(n_filtered=torch.zeros(b, **i32), n_keep=torch.zeros(b, **i32),
+               keep_idx=torch.empty(b, limit, **i32), keep_box=torch.empty(b, limit, **i32))
+    n_det = det_keep = det_cls = det_score = None
+    det_cap = 0
+    if expand:
+        det_cap = limit * num_cls
+        n_det = res['n_det'] = torch.zeros(b, **i32)
+        det_keep = res['det_keep'] = torch.empty(b, det_cap, **i32)
+        det_cls = res['det_cls'] = torch.empty(b, det_cap, **i32)
+        det_score = res['det_score'] = torch.empty(b, det_cap, dtype=torch.float32, device=dev)
+    filt_box = best_cls = best_prob = None
+    if details:
+        filt_box = res['filt_box'] = torch.empty(b, n, **i32)
+        if prob is not None:
+            best_cls = res['best_cls'] = torch.empty(b, n, **i32)
+            best_prob = res['best_prob'] = torch.empty(b, n, dtype=torch.float32, device=dev)
+    _l.check(_l.load().yb_filter_nms(_p(score), _p(yx_min), _p(yx_max), _p(prob), b, n, num_cls, mode, float(threshold),
+                                     float(threshold_cls), float(overlap), limit, _p(res['n_filtered']), _p(res['n_keep']),
+                                     _p(res['keep_idx']), _p(res['keep_box']), _p(n_det), _p(det_keep), _p(det_cls), _p(det_score),
+                                     det_cap, _p(filt_box), _p(best_cls), _p(best_prob), _s()), 'yb_filter_nms')
+    return res
+
+
+def iou_matrix(yx_min1, yx_max1, yx_min2, yx_max2, min_union=1.1920928955078125e-07):
+    """[N1,2]x2,[N2,2]x2 -> [N1,N2]  or batched [B,N1,2]... -> [B,N1,N2]."""
+    for n, t in (('yx_min1', yx_min1), ('yx_max1', yx_max1), ('yx_min2', yx_min2), ('yx_max2', yx_max2)):
+        _req(t, torch.float32, n)
+    batched = yx_min1.dim() == 3
+    b = yx_min1.shape[0] if batched else 1
+    n1, n2 = yx_min1.shape[-2], yx_min2.shape[-2]
+    out = torch.empty((b, n1, n2) if batched else (n1, n2), dtype=torch.float32, device=yx_min1.device)
+    _l.check(_l.load().yb_iou_matrix(_p(yx_min1), _p(yx_max1), _p(yx_min2), _p(yx_max2), _p(out), b, n1, n2, float(min_union), _s()),
+             'yb_iou_matrix')
+    return out

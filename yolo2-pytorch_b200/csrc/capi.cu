@@ -1,0 +1,158 @@
+// extern "C" surface of libyolo2_b200.so (declared in include/yolo2_b200.h) + shared host helpers.
+#include "../../include/yolo2_b200.h"
+#include "yb_common.h"
+#include <stdarg.h>
+#include <stdint.h>
+
+namespace yb {
+
+char* err_buf() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(err_buf(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_launch(const char* what) {
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(static_cast<int>(e), "%s: %s", what, cudaGetErrorString(e));
+  return 0;
+}
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+static int* g_dbg_host = nullptr;
+static int* g_dbg_dev = nullptr;
+
+int* debug_word_device() {
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* h = nullptr;
+    if (cudaHostAlloc(&h, 4 * sizeof(int), cudaHostAllocMapped) == cudaSuccess) {
+      memset(h, 0, 4 * sizeof(int));
+      void* d = nullptr;
+      if (cudaHostGetDevicePointer(&d, h, 0) == cudaSuccess) {
+        g_dbg_host = static_cast<int*>(h);
+        g_dbg_dev = static_cast<int*>(d);
+      }
+    } else {
+      cudaGetLastError();
+    }
+  }
+  return g_dbg_dev;
+}
+
+// implemented in the kernel translation units
+int conv_igemm_forward(const void*, const void*, const float*, const float*, float, void*, int, int, int, int, int, int, int, long long,
+                       int, int, int, cudaStream_t);
+int conv_ref_forward(const void*, const void*, const float*, const float*, float, void*, int, int, int, int, int, int, int, long long,
+                     int, int, cudaStream_t);
+int pack_weight(const float*, void*, int, int, int, int, cudaStream_t);
+int bn_fold(const float*, const float*, const float*, const float*, float, float*, float*, int, cudaStream_t);
+int conv0_forward(const float*, const float*, const float*, const float*, float, void*, int, int, int, int, cudaStream_t);
+int maxpool2x2(const void*, void*, int, int, int, int, int, cudaStream_t);
+int reorg_nhwc(const void*, void*, int, int, int, int, int, int, int, cudaStream_t);
+int reorg_nchw(const float*, float*, int, int, int, int, int, int, cudaStream_t);
+int decode_forward(const float*, const float*, float*, float*, float*, float*, float*, float*, float*, int, int, int, int, int,
+                   cudaStream_t);
+int filter_nms(const float*, const float*, const float*, const float*, int, int, int, int, float, float, float, int, int*, int*, int*,
+               int*, int*, int*, int*, float*, int, int*, int*, float*, cudaStream_t);
+int iou_matrix(const float*, const float*, const float*, const float*, float*, int, int, int, float, cudaStream_t);
+
+}  // namespace yb
+
+#define S(stream) static_cast<cudaStream_t>(stream)
+
+extern "C" {
+
+int yb_version(void) { return 100; }
+
+const char* yb_last_error(void) { return yb::err_buf(); }
+
+int yb_debug_read(int out[4]) {
+  if (out == nullptr) return YB_ERR_BAD_ARG;
+  if (yb::g_dbg_host == nullptr) { out[0] = out[1] = out[2] = out[3] = 0; return 0; }
+  for (int i = 0; i < 4; ++i) { out[i] = yb::g_dbg_host[i]; yb::g_dbg_host[i] = 0; }
+  return 0;
+}
+
+int yb_pack_weight_f16(const float* w_oihw, void* w_f16, int cout, int cin, int ksize, int mode, yb_stream_t stream) {
+  return yb::pack_weight(w_oihw, w_f16, cout, cin, ksize, mode, S(stream));
+}
+
+int yb_bn_fold(const float* gamma, const float* beta, const float* running_mean, const float* running_var, float eps, float* scale,
+               float* shift, int channels, yb_stream_t stream) {
+  return yb::bn_fold(gamma, beta, running_mean, running_var, eps, scale, shift, channels, S(stream));
+}
+
+int yb_conv0_bn_leaky_pool_fwd(const float* x_nchw, const float* w_oihw, const float* scale, const float* shift, float slope,
+                               void* y_nhwc_f16, int batch, int height, int width, int cout, yb_stream_t stream) {
+  return yb::conv0_forward(x_nchw, w_oihw, scale, shift, slope, y_nhwc_f16, batch, height, width, cout, S(stream));
+}
+
+int yb_conv_bn_act_fwd(const void* x, const void* w, const float* scale, const float* shift, float slope, void* y, int batch,
+                       int height, int width, int cin, int cout, int ksize, int x_ld, long long y_ld, int y_ch_off, int out_mode,
+                       int flags, yb_stream_t stream) {
+  return yb::conv_igemm_forward(x, w, scale, shift, slope, y, batch, height, width, cin, cout, ksize, x_ld, y_ld, y_ch_off, out_mode,
+                                flags, S(stream));
+}
+
+int yb_conv_ref_fwd(const void* x, const void* w, const float* scale, const float* shift, float slope, void* y, int batch, int height,
+                    int width, int cin, int cout, int ksize, int x_ld, long long y_ld, int y_ch_off, int out_mode, yb_stream_t stream) {
+  return yb::conv_ref_forward(x, w, scale, shift, slope, y, batch, height, width, cin, cout, ksize, x_ld, y_ld, y_ch_off, out_mode,
+                              S(stream));
+}
+
+int yb_maxpool2x2_f16(const void* x, void* y, int batch, int height, int width, int channels, int x_ld, yb_stream_t stream) {
+  return yb::maxpool2x2(x, y, batch, height, width, channels, x_ld, S(stream));
+}
+
+int yb_reorg_f16(const void* x, void* y, int batch, int height, int width, int channels, int x_ld, int y_ld, int y_ch_off,
+                 yb_stream_t stream) {
+  return yb::reorg_nhwc(x, y, batch, height, width, channels, x_ld, y_ld, y_ch_off, S(stream));
+}
+
+int yb_reorg_f32_nchw(const float* x, float* y, int batch, int channels, int height, int width, int stride_h, int stride_w,
+                      yb_stream_t stream) {
+  return yb::reorg_nchw(x, y, batch, channels, height, width, stride_h, stride_w, S(stream));
+}
+
+int yb_decode_fwd(const float* feature, const float* anchors_hw, float* iou, float* center_offset, float* size_norm, float* yx_min,
+                  float* yx_max, float* logits, float* prob, int batch, int rows, int cols, int num_anchors, int num_cls,
+                  yb_stream_t stream) {
+  return yb::decode_forward(feature, anchors_hw, iou, center_offset, size_norm, yx_min, yx_max, logits, prob, batch, rows, cols,
+                            num_anchors, num_cls, S(stream));
+}
+
+int yb_filter_nms(const float* score, const float* yx_min, const float* yx_max, const float* prob, int batch, int n, int num_cls,
+                  int mode, float threshold, float threshold_cls, float overlap, int limit, int* n_filtered, int* n_keep,
+                  int* keep_idx, int* keep_box, int* n_det, int* det_keep, int* det_cls, float* det_score, int det_cap,
+                  int* filt_box, int* best_cls, float* best_prob, yb_stream_t stream) {
+  return yb::filter_nms(score, yx_min, yx_max, prob, batch, n, num_cls, mode, threshold, threshold_cls, overlap, limit, n_filtered,
+                        n_keep, keep_idx, keep_box, n_det, det_keep, det_cls, det_score, det_cap, filt_box, best_cls, best_prob,
+                        S(stream));
+}
+
+int yb_iou_matrix(const float* yx_min1, const float* yx_max1, const float* yx_min2, const float* yx_max2, float* out, int batch,
+                  int n1, int n2, float min_union, yb_stream_t stream) {
+  return yb::iou_matrix(yx_min1, yx_max1, yx_min2, yx_max2, out, batch, n1, n2, min_union, S(stream));
+}
+
+}  // extern "C"
