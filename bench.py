@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py -- 416x416 images/sec of the YOLOv2 hot path on B200 (BASELINE.json metric).
+
+Workload (BASELINE.json configs[1], "C2"): Darknet-19 416x416 batch-32 inference + anchor decode +
+class softmax + threshold filter + NMS + per-class expansion, synthetic images, random-init
+weights.  One "step" = one batch of 32 images through the whole chain.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # B200 arm (prints ONE JSON line)
+    python bench.py --impl reference [--steps K] [--warmup W]      # the reference's CPU algorithm (oracle port)
+
+N > 1: launched by torch.distributed.run, one rank per GPU; the path shards by image with no
+data-path collective (inference replicas), so scaling is "weak" and `value` is the whole-job rate
+(N * 32 * K images / max-over-ranks device time).
+
+Numbers in the JSON line:
+  value      images/s, inputs resident in HBM (4 rotating input batches = 265 MB > 126 MB L2), CUDA-graph
+             replay of the kernel chain, CUDA events on the launching stream, max over ranks.
+  e2e        same metric through the serving API with HOST (pinned) fp32 batches: H2D copy of every
+             batch and D2H of the detection arrays inside the timed region (double-buffered).
+  roofline   tensor-core roofline of the dominant kernel family (the tcgen05 implicit-GEMM conv, 22
+             launches/step): algorithmic FLOPs of those launches / their summed CUDA-event durations
+             (an instrumented eager pass in the same run), against MEASURED_PEAKS.json bf16_tflops_sustained.
+  cpu_baseline  the oracle (CPU restatement of the reference, torch fp32 on all host cores) on a
+             bounded sample of the same workload; rank 0, N=1 only.
+"""
+import argparse
+import configparser
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, 'yolo2-pytorch_b200')
+for _p in (PKG, ROOT):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+GFLOP_PER_IMAGE_416 = 29.360334848          # sum 2*Cin*Cout*k^2*H*W over the 23 convs
+GFLOP_LAYER0_416 = 0.299040768              # layers1.0 (direct CUDA-core kernel, not tcgen05)
+METRIC = '416x416 images/sec'
+
+
+def make_config():
+    config = configparser.ConfigParser()
+    config.read_dict({'batch_norm': {'enable': '1'}, 'model': {'threshold': '0.6'},
+                      'detect': {'threshold': '0.3', 'threshold_cls': '0.005', 'fix': '1', 'overlap': '0.45'}})
+    return config
+
+
+ANCHORS_HW = [[1.73145, 1.3221], [4.00944, 3.19275], [8.09892, 5.05587], [4.84053, 9.47112], [10.0071, 11.2364]]
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return dict(tflops=float(d.get('bf16_tflops_sustained', d.get('bf16_tflops', 1400.0))), hbm=float(d.get('hbm_gbs', 6650.0)),
+                    source='MEASURED_PEAKS.json (bf16_tflops_sustained)')
+    return dict(tflops=1400.0, hbm=6650.0, source='fallback (B200_PROFILING.md)')
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+        for r in self.rows:
+            parts = [p.strip() for p in r.split(',')]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        sm.sort()
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=(max(mx) if mx else None), samples=len(sm), reasons=sorted(reasons))
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_chain(O, sd, anchors, x):
+    import torch
+    with torch.no_grad():
+        feature = O.darknet_forward(sd, x)
+        pred = O.decode(feature, anchors)
+        prob = O.class_prob(pred)
+        out = []
+        for bi in range(x.size(0)):
+            out.append(O.postprocess(pred['iou'][bi].reshape(-1), pred['yx_min'][bi].reshape(-1, 2), pred['yx_max'][bi].reshape(-1, 2),
+                                     prob[bi].reshape(-1, prob.size(-1)), True, 0.3, 0.005, 0.45))
+    return out
+
+
+def cpu_measure(batch, steps, warmup, budget_s):
+    """Oracle port timed on all host cores.  Returns (images/s, cores, sample description, ms/step)."""
+    import torch
+    from oracle import yolo2_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = O.make_state_dict(0)
+    anchors = O.anchors_yolo_voc()
+    # calibrate on 2 images, then size the per-step sample so the whole run fits the budget
+    x2 = O.synth_images(2, 416, 416, seed=0)
+    cpu_chain(O, sd, anchors, x2)
+    t0 = time.perf_counter()
+    cpu_chain(O, sd, anchors, x2)
+    per_img = (time.perf_counter() - t0) / 2
+    sample = int(max(1, min(batch, budget_s / max(1, steps + warmup) / per_img)))
+    x = O.synth_images(sample, 416, 416, seed=0)
+    for _ in range(warmup):
+        cpu_chain(O, sd, anchors, x)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_chain(O, sd, anchors, x)
+    dt = time.perf_counter() - t0
+    return sample * steps / dt, cores, '%d steps x %d images (of the %d-image batch), fp32, torch %d threads' % (steps, sample, batch, cores), dt / steps * 1e3
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    value, cores, sample, ms = cpu_measure(args.batch, args.steps, args.warmup, budget_s=150.0)
+    line = dict(impl='reference', metric=METRIC, value=value, unit='images/s', n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+                config=dict(workload='Darknet-19 416x416 batch-%d inference + decode + softmax + filter + NMS (BASELINE configs[1])' % args.batch,
+                            global_batch=args.batch, note='CPU: oracle port of the reference algorithm (torch fp32), bounded sample per step'),
+                cpu_baseline=dict(value=value, unit='images/s', cores=cores, kind='port', sample=sample),
+                e2e=dict(value=value, unit='images/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def build_model(device):
+    import torch
+    import model
+    import model.yolo2
+    config = make_config()
+    anchors = torch.tensor(ANCHORS_HW, dtype=torch.float32)
+    torch.manual_seed(0)
+    dnn = model.yolo2.Darknet(model.ConfigChannels(config), anchors, 20)
+    g = torch.Generator().manual_seed(1)
+    for m in dnn.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):      # non-trivial BN so the fused scale/shift is exercised
+            m.weight.data = torch.rand(m.num_features, generator=g) + 0.5
+            m.bias.data = torch.randn(m.num_features, generator=g) * 0.1
+            m.running_mean = torch.randn(m.num_features, generator=g) * 0.1
+            m.running_var = torch.rand(m.num_features, generator=g) + 0.5
+    dnn = dnn.to(device).eval()
+    inference = model.Inference(config, dnn, anchors).eval()
+    return config, dnn, inference
+
+
+def profile_layers(pipe, steps):
+    """Instrumented eager pass: CUDA events around every tcgen05 conv launch (a long spin kernel in
+    front of each step lets the host run ahead so the events bracket back-to-back kernels)."""
+    import torch
+    from b200 import ops
+    records = []
+    orig = ops.conv_bn_act
+
+    def timed(x, w, *a, **kw):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        y = orig(x, w, *a, **kw)
+        e.record()
+        b, h, wd, _ = x.shape
+        cout, k, _, cin = w.shape
+        records.append((s, e, 2.0 * b * h * wd * cin * cout * k * k, (h, cin, cout, k)))
+        return y
+
+    ops.conv_bn_act = timed
+    step_events = []
+    try:
+        for _ in range(steps):
+            torch.cuda._sleep(int(8e6))
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            pipe._forward(pipe.x[0])
+            e.record()
+            step_events.append((s, e))
+        torch.cuda.synchronize()
+    finally:
+        ops.conv_bn_act = orig
+    per_step = len(records) // steps
+    layers = []
+    for i in range(per_step):
+        ms = sum(records[j * per_step + i][0].elapsed_time(records[j * per_step + i][1]) for j in range(steps)) / steps
+        fl = records[i][2]
+        layers.append(dict(shape='%dx%d cin%d cout%d k%d' % ((records[i][3][0],) * 2 + records[i][3][1:]), us=ms * 1e3, tflops=fl / ms / 1e9))
+    conv_ms = sum(l['us'] for l in layers) / 1e3
+    conv_flops = sum(records[i][2] for i in range(per_step))
+    step_ms = sum(s.elapsed_time(e) for s, e in step_events) / steps
+    return dict(layers=layers, conv_ms=conv_ms, conv_flops=conv_flops, eager_step_ms=step_ms, launches=per_step)
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from b200 import ops
+    from b200.pipeline import DetectPipeline
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: the B200 arm needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm')
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    config, dnn, inference = build_model(device)
+    B, H, W = args.batch, args.size, args.size
+    slots = 4
+    pipe = DetectPipeline(inference, config, B, H, W, slots=slots, use_graph=not args.no_graph).prepare()
+    g = torch.Generator().manual_seed(100 + rank)
+    host = [torch.rand(B, 3, H, W, generator=g).pin_memory() for _ in range(2)]
+    for s in range(slots):
+        pipe.x[s].copy_(torch.rand(B, 3, H, W, generator=g))
+    torch.cuda.synchronize()
+
+    # ---- device-resident throughput ----
+    for i in range(args.warmup):
+        pipe.run(i % slots)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = ops.launch_count
+    t_wall = time.perf_counter()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for i in range(args.steps):
+        pipe.run(i % slots)
+    end.record()
+    torch.cuda.synchronize()
+    ms = start.elapsed_time(end)
+    wall_ms = (time.perf_counter() - t_wall) * 1e3
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    graph_launches = pipe.launches_per_run * args.steps
+    if world > 1:
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---- end to end through the serving API: pinned host batches in, detection arrays out ----
+    for i in range(max(3, args.warmup)):
+        pipe.load(i % 2, host[i % 2]); pipe.run(i % 2); pipe.fetch(i % 2)
+    barrier()
+    cur = torch.cuda.current_stream()
+    s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s2.record()
+    pipe.copy_stream.wait_event(s2)
+    pipe.load(0, host[0])
+    for i in range(args.steps):
+        if i + 1 < args.steps:
+            pipe.load((i + 1) % 2, host[(i + 1) % 2])
+        pipe.run(i % 2)
+        pipe.fetch(i % 2)
+    e2.record()
+    torch.cuda.synchronize()
+    ms_e2e = s2.elapsed_time(e2)
+    barrier()
+    if world > 1:
+        t = torch.tensor([ms_e2e], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+    e2e_value = world * B * args.steps / (ms_e2e / 1e3)
+    h2d = B * 3 * H * W * 4
+    d2h = pipe.result_bytes()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel family (tcgen05 convs), instrumented pass ----
+    peaks = measured_peaks()
+    prof = profile_layers(pipe, max(3, min(args.steps, 10)))
+    achieved = prof['conv_flops'] / (prof['conv_ms'] / 1e3) / 1e12
+    graph_step_ms = ms / args.steps
+    roofline = dict(bound='tensor', achieved=achieved, peak=peaks['tflops'], unit='TFLOP/s', frac=achieved / peaks['tflops'],
+                    traffic=None, kernel='conv_igemm_kernel (22 launches/step)', peak_source=peaks['source'],
+                    flops_per_launch=prof['conv_flops'] / prof['launches'], us_per_launch=prof['conv_ms'] * 1e3 / prof['launches'],
+                    share_of_step=prof['conv_ms'] / prof['eager_step_ms'],
+                    whole_step_frac=(B * GFLOP_PER_IMAGE_416 / 1e3) / (graph_step_ms / 1e3) / peaks['tflops'])
+    os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+    with open(os.path.join(ROOT, 'gpurun_out', 'bench_layers.json'), 'w') as f:
+        json.dump(dict(prof, graph_step_ms=graph_step_ms, value=value), f, indent=1)
+
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        v, cores, sample, _ = cpu_measure(B, 3, 1, budget_s=20.0)
+        cpu = dict(value=v, unit='images/s', cores=cores, kind='port', sample=sample)
+
+    line = dict(metric=METRIC, value=value, unit='images/s', n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps,
+                higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f16', data='synthetic',
+                config=dict(workload='Darknet-19 416x416 batch-%d inference + decode + softmax + filter + NMS (BASELINE configs[1])' % B,
+                            global_batch=B * world, per_gpu_batch=B, parallelism='replicas x%d (images shard, no collective)' % world,
+                            l2='inputs rotate over %d resident batches (%.0f MB > 126 MB L2); ~0.6 GB of activations streamed per step' % (slots, slots * h2d / 1e6),
+                            cuda_graph=not args.no_graph, weights='random-init (kaiming) + random BN statistics'),
+                clocks=clocks, e2e=dict(value=e2e_value, unit='images/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=ms_e2e / args.steps),
+                gpu_launches=graph_launches, roofline=roofline, cpu_baseline=cpu, wall_ms=wall_ms)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=32)
+    ap.add_argument('--size', type=int, default=416)
+    ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        args.warmup = max(args.warmup, 1)
+        run_reference(args)
+    else:
+        args.warmup = max(args.warmup, 3)
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

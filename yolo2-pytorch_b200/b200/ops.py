@@ -12,6 +12,15 @@ CONV_A_TILED, CONV_WIDE_N = 1, 2
 FILTER_THRESHOLD, FILTER_FIX, FILTER_NONE = 0, 1, 2
 
 
+launch_count = 0  # kernels of libyolo2_b200.so launched through this module (bench.py reports it)
+
+
+def _ck(rc, what):
+    global launch_count
+    _l.check(rc, what)
+    launch_count += 1
+
+
 def conv_force_bn(bn):
     return bn << 8
 
@@ -40,7 +49,7 @@ def pack_weight_f16(w, mode=0):
     cout, cin, k, _ = w.shape
     shape = (cout, k, k, cin) if mode == 0 else (cin, k, k, cout)
     out = torch.empty(shape, dtype=torch.float16, device=w.device)
-    _l.check(_l.load().yb_pack_weight_f16(_p(w), _p(out), cout, cin, k, mode, _s()), 'yb_pack_weight_f16')
+    _ck(_l.load().yb_pack_weight_f16(_p(w), _p(out), cout, cin, k, mode, _s()), 'yb_pack_weight_f16')
     return out
 
 
@@ -50,7 +59,7 @@ def bn_fold(gamma, beta, mean, var, eps=1e-5):
     c = gamma.numel()
     scale = torch.empty(c, dtype=torch.float32, device=gamma.device)
     shift = torch.empty_like(scale)
-    _l.check(_l.load().yb_bn_fold(_p(gamma), _p(beta), _p(mean), _p(var), float(eps), _p(scale), _p(shift), c, _s()), 'yb_bn_fold')
+    _ck(_l.load().yb_bn_fold(_p(gamma), _p(beta), _p(mean), _p(var), float(eps), _p(scale), _p(shift), c, _s()), 'yb_bn_fold')
     return scale, shift
 
 
@@ -64,7 +73,7 @@ def conv0_bn_leaky_pool(x, w, scale, shift, slope, out=None):
     if out is None:
         out = torch.empty(b, h // 2, wd // 2, cout, dtype=torch.float16, device=x.device)
     _req(out, torch.float16, 'out')
-    _l.check(_l.load().yb_conv0_bn_leaky_pool_fwd(_p(x), _p(w), _p(scale), _p(shift), float(slope), _p(out), b, h, wd, cout, _s()),
+    _ck(_l.load().yb_conv0_bn_leaky_pool_fwd(_p(x), _p(w), _p(scale), _p(shift), float(slope), _p(out), b, h, wd, cout, _s()),
              'yb_conv0_bn_leaky_pool_fwd')
     return out
 
@@ -75,7 +84,7 @@ def _conv_common(fn_name, x, w, scale, shift, slope, out, batch, height, width, 
     if fn_name == 'yb_conv_bn_act_fwd':
         args.append(flags)
     args.append(_s())
-    _l.check(fn(*args), fn_name)
+    _ck(fn(*args), fn_name)
 
 
 def conv_bn_act(x, w, scale, shift, slope, out=None, out_mode=OUT_F16_NHWC, y_ch_off=0, cin=None, flags=0, ref=False):
@@ -108,14 +117,14 @@ def maxpool2x2(x, channels=None, out=None):
     if out is None:
         out = torch.empty(b, h // 2, w // 2, c, dtype=torch.float16, device=x.device)
     _req(out, torch.float16, 'out')
-    _l.check(_l.load().yb_maxpool2x2_f16(_p(x), _p(out), b, h, w, c, x_ld, _s()), 'yb_maxpool2x2_f16')
+    _ck(_l.load().yb_maxpool2x2_f16(_p(x), _p(out), b, h, w, c, x_ld, _s()), 'yb_maxpool2x2_f16')
     return out
 
 
 def reorg_f16(x, out, y_ch_off=0):
     _req(x, torch.float16, 'x'); _req(out, torch.float16, 'out')
     b, h, w, c = x.shape
-    _l.check(_l.load().yb_reorg_f16(_p(x), _p(out), b, h, w, c, c, out.shape[-1], y_ch_off, _s()), 'yb_reorg_f16')
+    _ck(_l.load().yb_reorg_f16(_p(x), _p(out), b, h, w, c, c, out.shape[-1], y_ch_off, _s()), 'yb_reorg_f16')
     return out
 
 
@@ -124,7 +133,7 @@ def reorg_f32_nchw(x, stride_h=2, stride_w=2):
     b, c, h, w = x.shape
     out = torch.empty(b, c * stride_h * stride_w, h // stride_h, w // stride_w, dtype=torch.float32, device=x.device)
     if out.numel():
-        _l.check(_l.load().yb_reorg_f32_nchw(_p(x), _p(out), b, c, h, w, stride_h, stride_w, _s()), 'yb_reorg_f32_nchw')
+        _ck(_l.load().yb_reorg_f32_nchw(_p(x), _p(out), b, c, h, w, stride_h, stride_w, _s()), 'yb_reorg_f32_nchw')
     return out
 
 
@@ -149,7 +158,7 @@ def decode(feature, anchors, num_cls, with_prob=True):
         prob = out['prob'] = torch.empty(b, cells, a, max(num_cls, 1), dtype=torch.float32, device=dev)
     if ch != a * (5 + (num_cls if num_cls > 1 else 0)):
         raise ValueError('feature has %d channels, expected %d' % (ch, a * (5 + (num_cls if num_cls > 1 else 0))))
-    _l.check(_l.load().yb_decode_fwd(_p(feature), _p(anchors), _p(out['iou']), _p(out['center_offset']), _p(out['size_norm']),
+    _ck(_l.load().yb_decode_fwd(_p(feature), _p(anchors), _p(out['iou']), _p(out['center_offset']), _p(out['size_norm']),
                                      _p(out['yx_min']), _p(out['yx_max']), _p(logits), _p(prob), b, rows, cols, a, num_cls, _s()),
              'yb_decode_fwd')
     return out
@@ -181,7 +190,7 @@ def filter_nms(score, yx_min, yx_max, prob, mode, threshold, threshold_cls, over
         if prob is not None:
             best_cls = res['best_cls'] = torch.empty(b, n, **i32)
             best_prob = res['best_prob'] = torch.empty(b, n, dtype=torch.float32, device=dev)
-    _l.check(_l.load().yb_filter_nms(_p(score), _p(yx_min), _p(yx_max), _p(prob), b, n, num_cls, mode, float(threshold),
+    _ck(_l.load().yb_filter_nms(_p(score), _p(yx_min), _p(yx_max), _p(prob), b, n, num_cls, mode, float(threshold),
                                      float(threshold_cls), float(overlap), limit, _p(res['n_filtered']), _p(res['n_keep']),
                                      _p(res['keep_idx']), _p(res['keep_box']), _p(n_det), _p(det_keep), _p(det_cls), _p(det_score),
                                      det_cap, _p(filt_box), _p(best_cls), _p(best_prob), _s()), 'yb_filter_nms')
@@ -196,6 +205,6 @@ def iou_matrix(yx_min1, yx_max1, yx_min2, yx_max2, min_union=1.1920928955078125e
     b = yx_min1.shape[0] if batched else 1
     n1, n2 = yx_min1.shape[-2], yx_min2.shape[-2]
     out = torch.empty((b, n1, n2) if batched else (n1, n2), dtype=torch.float32, device=yx_min1.device)
-    _l.check(_l.load().yb_iou_matrix(_p(yx_min1), _p(yx_max1), _p(yx_min2), _p(yx_max2), _p(out), b, n1, n2, float(min_union), _s()),
+    _ck(_l.load().yb_iou_matrix(_p(yx_min1), _p(yx_max1), _p(yx_min2), _p(yx_max2), _p(out), b, n1, n2, float(min_union), _s()),
              'yb_iou_matrix')
     return out
