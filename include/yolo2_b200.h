@@ -58,9 +58,15 @@ int yb_bn_fold(const float* gamma, const float* beta, const float* running_mean,
                float* shift, int channels, yb_stream_t stream);
 
 /* ---- backbone: model.yolo2.Conv2d.forward (model/yolo2.py:61-65), nn.MaxPool2d (:79), reorg (:33-46) */
-/* layers1.0 + its MaxPool: x fp32 NCHW [B,3,H,W] (the caller's tensor) -> y fp16 NHWC [B,H/2,W/2,32]. */
+/* layers1.0 + its MaxPool: x fp32 NCHW [B,3,H,W] (the caller's tensor) -> y fp16 NHWC [B,H/2,W/2,32].
+ * H % 16 == 0, W % 32 == 0. */
 int yb_conv0_bn_leaky_pool_fwd(const float* x_nchw, const float* w_oihw, const float* scale, const float* shift, float slope,
                                void* y_nhwc_f16, int batch, int height, int width, int cout, yb_stream_t stream);
+/* Same layer fed by raw frames: x uint8 NHWC [B,H,W,3] (RGB), scaled by 1/255 in the kernel --
+ * replaces the host-side torchvision ToTensor the reference runs per frame (detect.py:144-145,
+ * transform/__init__.py) and cuts the host->device copy 4x. */
+int yb_conv0_u8_bn_leaky_pool_fwd(const unsigned char* x_nhwc_u8, const float* w_oihw, const float* scale, const float* shift,
+                                  float slope, void* y_nhwc_f16, int batch, int height, int width, int cout, yb_stream_t stream);
 /* k in {1,3}, stride 1, pad (k-1)/2 conv + per-channel scale/shift + leaky(slope) as a tcgen05
  * implicit GEMM.  x: fp16 NHWC [B,H,W,Cin] with pixel pitch x_ld; w: fp16 [Cout][k][k][Cin];
  * y: fp16 NHWC (pixel pitch y_ld, first channel y_ch_off) or fp32 NCHW [B,Cout,H,W].

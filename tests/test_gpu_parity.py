@@ -225,6 +225,31 @@ def test_conv0_vs_oracle(ops):
     assert rel_err(y.permute(0, 3, 1, 2), ref) <= 1e-3
 
 
+def test_conv0_u8_frames_vs_oracle(ops):
+    """Raw uint8 NHWC frames: the kernel's 1/255 scaling == torchvision ToTensor (reference detect.py:144-145)."""
+    sd = O.make_state_dict(0)
+    frames = torch.randint(0, 256, (2, 64, 96, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(9))
+    x = frames.permute(0, 3, 1, 2).float() / 255
+    ref = torch.nn.functional.max_pool2d(O.conv_unit(x, sd, 'layers1.0', 3, True, True), 2)
+    scale, shift = ops.bn_fold(*(sd['layers1.0.bn.' + n].to(DEV) for n in ('weight', 'bias', 'running_mean', 'running_var')))
+    y = ops.conv0_u8_bn_leaky_pool(frames.to(DEV), sd['layers1.0.conv.weight'].to(DEV), scale, shift, 0.1)
+    assert rel_err(y.permute(0, 3, 1, 2), ref) <= 1e-3
+
+
+@pytest.mark.parametrize('cfg', [(128, 2), (256, 2), (256, 1), (64, 2)])
+def test_conv_tile_shapes_agree(ops, cfg):
+    """Every CTA tile shape (BLOCK_N x M-subtiles) computes the same result as the oracle arithmetic."""
+    bn, mt = cfg
+    gen = torch.Generator().manual_seed(bn + mt)
+    cout = 64 if bn == 64 else 512
+    x = torch.randn(5, 256, 13, 13, generator=gen)
+    wt = torch.randn(cout, 256, 3, 3, generator=gen) * (2.0 / (256 * 9)) ** 0.5
+    ref = torch.nn.functional.leaky_relu(torch.nn.functional.conv2d(x, wt, padding=1), 0.1)
+    y = ops.conv_bn_act(x.to(DEV).permute(0, 2, 3, 1).contiguous().half(), ops.pack_weight_f16(wt.to(DEV)), torch.ones(cout, device=DEV),
+                        torch.zeros(cout, device=DEV), 0.1, flags=ops.conv_force_bn(bn) | ops.conv_force_mt(mt))
+    assert rel_err(y.permute(0, 3, 1, 2), ref) <= 1e-3
+
+
 # ------------------------------------------------------------------------------------------------
 # whole backbone through the plugin surface
 # ------------------------------------------------------------------------------------------------

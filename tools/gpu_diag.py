@@ -35,6 +35,15 @@ CASES = [
     dict(name='conv3x3_big_wide', b=32, h=13, w=13, cin=1024, cout=1024, k=3, wide=1),
     dict(name='conv_chan_slice', b=2, h=13, w=13, cin=1024, cout=1024, k=3, ch_off=256, y_ld=1280),
     dict(name='conv_cin1280', b=2, h=13, w=13, cin=1280, cout=1024, k=3),
+    # M-subtiles = 2 (256 x BN CTA tiles)
+    dict(name='mt2_1x1_tiled', b=2, h=16, w=16, cin=256, cout=128, k=1, tiled=1, mt=2),
+    dict(name='mt2_3x3_bn128', b=2, h=16, w=16, cin=64, cout=128, k=3, mt=2),
+    dict(name='mt2_3x3_tail_13x13_bn256', b=3, h=13, w=13, cin=128, cout=256, k=3, mt=2, bn=256),
+    dict(name='mt2_3x3_odd_subtile_tail', b=5, h=13, w=13, cin=128, cout=256, k=3, mt=2, bn=128),
+    dict(name='mt2_cin32_bn64', b=1, h=32, w=32, cin=32, cout=64, k=3, mt=2),
+    dict(name='mt2_head_nchw', b=2, h=13, w=13, cin=1024, cout=125, k=1, nchw=1, noact=1, mt=2),
+    dict(name='mt2_big_bn256', b=32, h=13, w=13, cin=1024, cout=1024, k=3, mt=2, bn=256),
+    dict(name='mt2_multi_tile_persist', b=8, h=52, w=52, cin=128, cout=256, k=3, mt=2, bn=128),
 ]
 
 
@@ -60,6 +69,7 @@ def run_case(idx):
     slope = 1.0 if c.get('noact') else 0.1
     out_mode = ops.OUT_F32_NCHW if c.get('nchw') else ops.OUT_F16_NHWC
     flags = (ops.CONV_A_TILED if c.get('tiled') else 0) | (ops.CONV_WIDE_N if c.get('wide') else 0)
+    flags |= ops.conv_force_mt(c.get('mt', 0)) | ops.conv_force_bn(c.get('bn', 0))
     y_ld = c.get('y_ld', cout)
     ch_off = c.get('ch_off', 0)
 
@@ -111,6 +121,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--case', type=int, default=-1)
     ap.add_argument('--out', default=os.path.join(ROOT, 'gpurun_out', 'diag.json'))
+    ap.add_argument('--start', type=int, default=0, help='first case index to run')
     a = ap.parse_args()
     if a.case >= 0:
         print('DIAG_JSON ' + json.dumps(run_case(a.case)))
@@ -118,6 +129,8 @@ def main():
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     results = []
     for i, c in enumerate(CASES):
+        if i < a.start:
+            continue
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), '--case', str(i)], capture_output=True, text=True, timeout=300)
             rec = None

@@ -131,10 +131,14 @@ class DarknetEngine(object):
         `collect` (dict) receives references to every unit's fp16 NHWC output (tests)."""
         if not x.is_cuda:
             raise RuntimeError('Darknet (B200): input must be a CUDA tensor; there is no CPU fallback')
-        b, c, h, w = x.shape
+        u8 = x.dtype == torch.uint8          # raw RGB frames [B,H,W,3]: the kernel applies ToTensor's 1/255
+        if u8:
+            b, h, w, c = x.shape
+        else:
+            b, c, h, w = x.shape
         if c != 3 or h % 32 or w % 32:
-            raise ValueError('Darknet expects [B,3,H,W] with H, W multiples of 32, got %s' % (tuple(x.shape),))
-        x = x.contiguous().float()
+            raise ValueError('Darknet expects fp32 [B,3,H,W] or uint8 [B,H,W,3] with H, W multiples of 32, got %s' % (tuple(x.shape),))
+        x = x.contiguous() if u8 else x.contiguous().float()
         self.refresh()
         p = self.plan(b, h, w, x.device)
 
@@ -142,7 +146,8 @@ class DarknetEngine(object):
             return ops.conv_bn_act(src, u.w16, u.scale, u.shift, u.slope, out=dst, flags=conv_flags, ref=ref, **kw)
 
         u0 = self.units1[0]
-        cur = ops.conv0_bn_leaky_pool(x, u0.w16, u0.scale, u0.shift, u0.slope, out=p.a0)
+        conv0 = ops.conv0_u8_bn_leaky_pool if u8 else ops.conv0_bn_leaky_pool
+        cur = conv0(x, u0.w16, u0.scale, u0.shift, u0.slope, out=p.a0)
         if collect is not None:
             collect['layers1.0(pooled)'] = cur
         x1 = None

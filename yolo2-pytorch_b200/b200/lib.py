@@ -16,6 +16,7 @@ SIGNATURES = {
     'yb_pack_weight_f16': [P, P, c_int, c_int, c_int, c_int, P],
     'yb_bn_fold': [P, P, P, P, c_float, P, P, c_int, P],
     'yb_conv0_bn_leaky_pool_fwd': [P, P, P, P, c_float, P, c_int, c_int, c_int, c_int, P],
+    'yb_conv0_u8_bn_leaky_pool_fwd': [P, P, P, P, c_float, P, c_int, c_int, c_int, c_int, P],
     'yb_conv_bn_act_fwd': [P, P, P, P, c_float, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_longlong, c_int, c_int, c_int, P],
     'yb_conv_ref_fwd': [P, P, P, P, c_float, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_longlong, c_int, c_int, P],
     'yb_maxpool2x2_f16': [P, P, c_int, c_int, c_int, c_int, c_int, P],

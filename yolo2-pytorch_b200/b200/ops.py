@@ -25,6 +25,10 @@ def conv_force_bn(bn):
     return bn << 8
 
 
+def conv_force_mt(mt):
+    return mt << 20
+
+
 def _p(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
@@ -75,6 +79,21 @@ def conv0_bn_leaky_pool(x, w, scale, shift, slope, out=None):
     _req(out, torch.float16, 'out')
     _ck(_l.load().yb_conv0_bn_leaky_pool_fwd(_p(x), _p(w), _p(scale), _p(shift), float(slope), _p(out), b, h, wd, cout, _s()),
              'yb_conv0_bn_leaky_pool_fwd')
+    return out
+
+
+def conv0_u8_bn_leaky_pool(x, w, scale, shift, slope, out=None):
+    """x uint8 NHWC [B,H,W,3] (raw RGB frames; the kernel applies ToTensor's 1/255) -> fp16 NHWC [B,H/2,W/2,32]."""
+    _req(x, torch.uint8, 'x'); _req(w, torch.float32, 'w'); _req(scale, torch.float32, 'scale'); _req(shift, torch.float32, 'shift')
+    b, h, wd, c = x.shape
+    if c != 3:
+        raise ValueError('conv0 expects 3 input channels')
+    cout = w.shape[0]
+    if out is None:
+        out = torch.empty(b, h // 2, wd // 2, cout, dtype=torch.float16, device=x.device)
+    _req(out, torch.float16, 'out')
+    _ck(_l.load().yb_conv0_u8_bn_leaky_pool_fwd(_p(x), _p(w), _p(scale), _p(shift), float(slope), _p(out), b, h, wd, cout, _s()),
+        'yb_conv0_u8_bn_leaky_pool_fwd')
     return out
 
 

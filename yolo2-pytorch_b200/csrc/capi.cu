@@ -66,7 +66,7 @@ int conv_ref_forward(const void*, const void*, const float*, const float*, float
                      int, int, cudaStream_t);
 int pack_weight(const float*, void*, int, int, int, int, cudaStream_t);
 int bn_fold(const float*, const float*, const float*, const float*, float, float*, float*, int, cudaStream_t);
-int conv0_forward(const float*, const float*, const float*, const float*, float, void*, int, int, int, int, cudaStream_t);
+int conv0_tc_forward(const void*, int, const float*, const float*, const float*, float, void*, int, int, int, int, cudaStream_t);
 int maxpool2x2(const void*, void*, int, int, int, int, int, cudaStream_t);
 int reorg_nhwc(const void*, void*, int, int, int, int, int, int, int, cudaStream_t);
 int reorg_nchw(const float*, float*, int, int, int, int, int, int, cudaStream_t);
@@ -104,7 +104,12 @@ int yb_bn_fold(const float* gamma, const float* beta, const float* running_mean,
 
 int yb_conv0_bn_leaky_pool_fwd(const float* x_nchw, const float* w_oihw, const float* scale, const float* shift, float slope,
                                void* y_nhwc_f16, int batch, int height, int width, int cout, yb_stream_t stream) {
-  return yb::conv0_forward(x_nchw, w_oihw, scale, shift, slope, y_nhwc_f16, batch, height, width, cout, S(stream));
+  return yb::conv0_tc_forward(x_nchw, 0, w_oihw, scale, shift, slope, y_nhwc_f16, batch, height, width, cout, S(stream));
+}
+
+int yb_conv0_u8_bn_leaky_pool_fwd(const unsigned char* x_nhwc_u8, const float* w_oihw, const float* scale, const float* shift,
+                                  float slope, void* y_nhwc_f16, int batch, int height, int width, int cout, yb_stream_t stream) {
+  return yb::conv0_tc_forward(x_nhwc_u8, 1, w_oihw, scale, shift, slope, y_nhwc_f16, batch, height, width, cout, S(stream));
 }
 
 int yb_conv_bn_act_fwd(const void* x, const void* w, const float* scale, const float* shift, float slope, void* y, int batch,

@@ -1,0 +1,225 @@
+// conv0 (layers1.0): 3x3 conv, Cin = 3 -> Cout = 32, + folded BN + leaky-ReLU + 2x2 max-pool, on the
+// tensor cores.  Replaces nn.Conv2d(3,32,3,pad 1) -> BatchNorm2d -> LeakyReLU -> MaxPool2d(2)
+// (/root/reference model/yolo2.py:78-79) and doubles as the layout boundary: it reads the caller's
+// image batch (fp32 NCHW as the reference's ToTensor produces it, or raw uint8 NHWC frames scaled
+// by 1/255 == torchvision ToTensor) and writes the first fp16 NHWC activation.
+//
+// K = 27 is far too small for a TMA-fed pipeline (one pixel's im2col row is 54 bytes), so the CTA
+// builds the A operand itself: a 16x32-pixel conv tile (+1 halo) is staged in shared memory once,
+// each of the 128 threads converts the 4x4x3 patch of ONE 2x2 pool window to fp16 and writes the
+// four im2col rows (K padded to 32, 64-byte rows, 64B-swizzled exactly like a TMA box would be)
+// into four 128-row M-tiles -- M-tile j holds pixel j of every window.  One thread issues
+// 4 x 2 tcgen05.mma (M=128, N=32, K=16) into four TMEM accumulators; in the epilogue thread t reads
+// lane t of all four accumulators = the four conv outputs of its window, applies scale/shift +
+// leaky, takes the max in registers and stores the pooled pixel's 32 channels as 64 contiguous
+// bytes.  Persistent CTAs (4 per SM), weights (B operand) built once per CTA.
+#include "yb_common.h"
+#include "yb_ptx.cuh"
+
+namespace yb {
+
+constexpr int kT0Rows = 16, kT0Cols = 32;          // conv pixels per tile (8 x 16 pool windows = 128)
+constexpr int kPatchRows = kT0Rows + 2, kPatchCols = kT0Cols + 2, kPatchPitch = 48;
+constexpr int kC0Out = 32;
+
+__device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+struct Conv0Params {
+  const void* x;        // fp32 NCHW [B,3,H,W] or uint8 NHWC [B,H,W,3]
+  const float* w;       // fp32 OIHW [32,3,3,3]
+  const float* scale;
+  const float* shift;
+  float slope;
+  __half* y;            // fp16 NHWC [B,H/2,W/2,32]
+  int batch, height, width;
+  int tiles_x, tiles_y, num_tiles;
+  int* dbg;
+};
+
+template <bool kU8>
+__global__ void __launch_bounds__(128, 4) conv0_tc_kernel(const Conv0Params p) {
+  __shared__ __align__(1024) uint8_t a_smem[4 * 128 * 64];          // 4 M-tiles x 128 rows x 64 B (SW64)
+  __shared__ __align__(1024) uint8_t b_smem[kC0Out * 64];           // 32 rows (Cout) x 64 B (SW64)
+  __shared__ __align__(16) float patch[3][kPatchRows][kPatchPitch];
+  __shared__ __align__(16) float sc[kC0Out], sh[kC0Out];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t a_base = smem_u32(a_smem), b_base = smem_u32(b_smem), bar_addr = smem_u32(&bar);
+
+  if (tid == 0) {
+    mbar_init(bar_addr, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(smem_u32(&tmem_slot), 128);
+    tmem_relinquish();
+  }
+  if (tid < kC0Out) { sc[tid] = p.scale[tid]; sh[tid] = p.shift[tid]; }
+  {
+    // B operand: row n = output channel, k = ci*9 + r*3 + s (the OIHW flattening), zero padded to 32
+    const int n = tid >> 2, j = tid & 3;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = j * 8 + e;
+      v[e] = (k < 27) ? __ldg(p.w + n * 27 + k) : 0.f;
+    }
+    const uint4 pk = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+    *reinterpret_cast<uint4*>(b_smem + n * 64 + ((j ^ ((n >> 1) & 3)) << 4)) = pk;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  const int wy = tid >> 4, wx = tid & 15;        // this thread's pool window inside the tile
+  const int oh = p.height >> 1, ow = p.width >> 1;
+  uint32_t phase = 0;
+  constexpr uint32_t idesc = make_idesc_f16(128, kC0Out);
+
+  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    const int tx = tile % p.tiles_x;
+    const int t2 = tile / p.tiles_x;
+    const int ty = t2 % p.tiles_y;
+    const int img = t2 / p.tiles_y;
+    const int y0 = ty * kT0Rows - 1, x0 = tx * kT0Cols - 1;
+    // ---- 1. stage the haloed input patch (zeros outside the image) ----
+    for (int i = tid; i < 3 * kPatchRows * kPatchCols; i += 128) {
+      const int c = i / (kPatchRows * kPatchCols);
+      const int rem = i - c * (kPatchRows * kPatchCols);
+      const int r = rem / kPatchCols, col = rem - r * kPatchCols;
+      const int iy = y0 + r, ix = x0 + col;
+      float v = 0.f;
+      if (iy >= 0 && iy < p.height && ix >= 0 && ix < p.width) {
+        if (kU8) {
+          v = static_cast<float>(__ldg(reinterpret_cast<const uint8_t*>(p.x) + ((static_cast<long long>(img) * p.height + iy) * p.width + ix) * 3 + c)) *
+              (1.f / 255.f);
+        } else {
+          v = __ldg(reinterpret_cast<const float*>(p.x) + ((static_cast<long long>(img) * 3 + c) * p.height + iy) * p.width + ix);
+        }
+      }
+      patch[c][r][col] = v;
+    }
+    __syncthreads();
+    // ---- 2. build the four im2col rows of this thread's window ----
+    float in[3][4][4];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float2 lo = *reinterpret_cast<const float2*>(&patch[c][2 * wy + r][2 * wx]);
+        const float2 hi = *reinterpret_cast<const float2*>(&patch[c][2 * wy + r][2 * wx + 2]);
+        in[c][r][0] = lo.x; in[c][r][1] = lo.y; in[c][r][2] = hi.x; in[c][r][3] = hi.y;
+      }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int dy = j >> 1, dx = j & 1;
+      float k[32];
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int s = 0; s < 3; ++s) k[c * 9 + r * 3 + s] = in[c][dy + r][dx + s];
+#pragma unroll
+      for (int e = 27; e < 32; ++e) k[e] = 0.f;
+      uint8_t* row = a_smem + j * (128 * 64) + tid * 64;
+      const int sw = (tid >> 1) & 3;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 pk = make_uint4(pack_h2(k[q * 8 + 0], k[q * 8 + 1]), pack_h2(k[q * 8 + 2], k[q * 8 + 3]),
+                                    pack_h2(k[q * 8 + 4], k[q * 8 + 5]), pack_h2(k[q * 8 + 6], k[q * 8 + 7]));
+        *reinterpret_cast<uint4*>(row + ((q ^ sw) << 4)) = pk;
+      }
+    }
+    // generic-proxy smem writes -> visible to the tensor core (async proxy); previous tile's TMEM
+    // reads are ordered before the MMAs that overwrite the accumulators
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    // ---- 3. MMA: 4 accumulators x (K = 32 = 2 x 16) ----
+    if (tid == 0) {
+      tc_fence_after();
+      const uint64_t bdesc = make_kmajor_desc<64>(b_base);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint64_t adesc = make_kmajor_desc<64>(a_base + j * (128 * 64));
+        umma_f16(tmem_base + j * kC0Out, adesc, bdesc, idesc, 0);
+        umma_f16(tmem_base + j * kC0Out, adesc + 2, bdesc + 2, idesc, 1);
+      }
+      umma_commit(bar_addr);
+    }
+    mbar_wait(bar_addr, phase, p.dbg, 0x500);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- 4. epilogue: scale/shift + leaky on the 4 pixels of the window, max, fp16 NHWC store ----
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const int py = ty * (kT0Rows / 2) + wy, px = tx * (kT0Cols / 2) + wx;
+    __half* dst = p.y + ((static_cast<long long>(img) * oh + py) * ow + px) * kC0Out;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint32_t v[4][8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) tmem_ld_32x32b_x8(lane_addr + j * kC0Out + g * 8, v[j]);
+      tmem_ld_wait();
+      float m[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float s = sc[g * 8 + e], b = sh[g * 8 + e];
+        float best = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float t = __uint_as_float(v[j][e]) * s + b;
+          t = t > 0.f ? t : t * p.slope;
+          best = fmaxf(best, t);
+        }
+        m[e] = best;
+      }
+      *reinterpret_cast<uint4*>(dst + g * 8) = make_uint4(pack_h2(m[0], m[1]), pack_h2(m[2], m[3]), pack_h2(m[4], m[5]), pack_h2(m[6], m[7]));
+    }
+    // The next tile's barriers (after patch staging and before its MMAs) order these TMEM reads
+    // and this tile's smem reads before anything is overwritten.
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 128);
+  }
+}
+
+int conv0_tc_forward(const void* x, int x_is_u8, const float* w, const float* scale, const float* shift, float slope, void* y, int batch,
+                     int height, int width, int cout, cudaStream_t stream) {
+  YB_REQUIRE(x && w && scale && shift && y, "conv0: null pointer");
+  YB_REQUIRE(cout == kC0Out, "conv0: Cout=%d unsupported (32)", cout);
+  YB_REQUIRE(batch > 0 && height > 0 && width > 0 && height % kT0Rows == 0 && width % kT0Cols == 0,
+             "conv0: H must be a multiple of %d and W of %d (got %dx%d)", kT0Rows, kT0Cols, height, width);
+  Conv0Params p;
+  p.x = x; p.w = w; p.scale = scale; p.shift = shift; p.slope = slope; p.y = reinterpret_cast<__half*>(y);
+  p.batch = batch; p.height = height; p.width = width;
+  p.tiles_x = width / kT0Cols; p.tiles_y = height / kT0Rows;
+  const long long tiles = static_cast<long long>(p.tiles_x) * p.tiles_y * batch;
+  YB_REQUIRE(tiles < (1ll << 31), "conv0: too many tiles");
+  p.num_tiles = static_cast<int>(tiles);
+  p.dbg = debug_word_device();
+  const int max_ctas = sm_count() * 4;
+  const int grid = p.num_tiles < max_ctas ? p.num_tiles : max_ctas;
+  if (x_is_u8) conv0_tc_kernel<true><<<grid, 128, 0, stream>>>(p);
+  else conv0_tc_kernel<false><<<grid, 128, 0, stream>>>(p);
+  return check_launch("conv0_tc_kernel");
+}
+
+}  // namespace yb

@@ -47,21 +47,28 @@ constexpr int UMMA_K = 16;
 constexpr int kNumThreads = 192;
 constexpr int kEpiThreads = 128;
 
-template <int BN, int BK>
+// MT = number of 128-pixel M-subtiles per CTA tile (1 or 2).  MT = 2 makes the CTA tile 256 x BN: both
+// subtiles reuse the same weight (B) tile from shared memory, halving the L2->SM weight traffic per MAC.
+template <int BN, int BK, int MT>
 struct ConvCfg {
   static constexpr int kSwizzle = BK * 2;                       // bytes per smem row
-  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kASubBytes = BM * BK * 2;
+  static constexpr int kABytes = MT * kASubBytes;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (196608 / kStageBytes) > 8 ? 8 : (196608 / kStageBytes);
-  static constexpr int kTmemCols = 2 * BN;                      // two accumulator stages (power of 2 >= 32)
+  static constexpr int kAccCols = MT * BN;                      // TMEM columns of one accumulator stage
+  static constexpr int kAccStages = (2 * kAccCols <= 512) ? 2 : 1;
+  static constexpr int kTmemCols = kAccStages * kAccCols;       // power of two in [64, 512]
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 2 * 2 * BN * 4 /*scale/shift x2*/ + 256 /*barriers*/;
+  static_assert(kAccCols <= 512, "accumulator does not fit TMEM");
 };
 
-template <int BN, int BK>
+template <int BN, int BK, int MT>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const ConvParams p) {
-  using Cfg = ConvCfg<BN, BK>;
+  using Cfg = ConvCfg<BN, BK, MT>;
+  constexpr int kAccStages = Cfg::kAccStages;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the swizzle atoms
@@ -113,23 +120,37 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int n_tile = tile % p.n_tiles;
         const int m_tile = tile / p.n_tiles;
-        const int m0 = m_tile * BM;
-        const int img = m0 / p.hw;
-        const int rem = m0 - img * p.hw;
-        const int h0 = rem / p.width;
-        const int w0 = rem - h0 * p.width;
+        const int m0 = m_tile * (BM * MT);
+        int img[MT], h0[MT], w0[MT];
+        int nsub = 0;                      // subtiles that start inside the tensor (the rest are skipped)
+#pragma unroll
+        for (int t = 0; t < MT; ++t) {
+          const int ms = m0 + t * BM;
+          if (ms < p.m_total) nsub = t + 1;
+          img[t] = ms / p.hw;
+          const int rem = ms - img[t] * p.hw;
+          h0[t] = rem / p.width;
+          w0[t] = rem - h0[t] * p.width;
+        }
+        const uint32_t tx_bytes = nsub * Cfg::kASubBytes + Cfg::kBBytes;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           const int tap = kb / p.kb_per_tap;
           const int c0 = (kb - tap * p.kb_per_tap) * BK;
           const int r = tap / p.ksize;
           const int s = tap - r * p.ksize;
           mbar_wait(bar_empty + 8 * stage, phase ^ 1, p.dbg, 0x100 | stage);
-          mbar_arrive_expect_tx(bar_full + 8 * stage, Cfg::kStageBytes);
-          if (p.a_im2col) {
-            tma_load_im2col_4d(smem_a + stage * Cfg::kABytes, &tmap_a, bar_full + 8 * stage, c0, w0 - p.pad, h0 - p.pad, img,
-                               static_cast<uint16_t>(s), static_cast<uint16_t>(r));
-          } else {
-            tma_load_2d(smem_a + stage * Cfg::kABytes, &tmap_a, bar_full + 8 * stage, c0, m0);
+          mbar_arrive_expect_tx(bar_full + 8 * stage, tx_bytes);
+#pragma unroll
+          for (int t = 0; t < MT; ++t) {
+            if (t < nsub) {
+              const uint32_t dst = smem_a + stage * Cfg::kABytes + t * Cfg::kASubBytes;
+              if (p.a_im2col) {
+                tma_load_im2col_4d(dst, &tmap_a, bar_full + 8 * stage, c0, w0[t] - p.pad, h0[t] - p.pad, img[t],
+                                   static_cast<uint16_t>(s), static_cast<uint16_t>(r));
+              } else {
+                tma_load_2d(dst, &tmap_a, bar_full + 8 * stage, c0, m0 + t * BM);
+              }
+            }
           }
           tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, bar_full + 8 * stage, tap * p.cin + c0, n_tile * BN);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -147,22 +168,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1, p.dbg, 0x200 | acc);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_base + acc * Cfg::kAccCols;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(bar_full + 8 * stage, phase, p.dbg, 0x300 | stage);
           tc_fence_after();
-          const uint64_t adesc = make_kmajor_desc<Cfg::kSwizzle>(smem_a + stage * Cfg::kABytes);
           const uint64_t bdesc = make_kmajor_desc<Cfg::kSwizzle>(smem_b + stage * Cfg::kBBytes);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // advance 16 fp16 = 32 bytes inside the swizzled row: +2 in the 16-byte address field
-            umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          for (int t = 0; t < MT; ++t) {
+            const uint64_t adesc = make_kmajor_desc<Cfg::kSwizzle>(smem_a + stage * Cfg::kABytes + t * Cfg::kASubBytes);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // advance 16 fp16 = 32 bytes inside the swizzled row: +2 in the 16-byte address field
+              umma_f16(d_tmem + t * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            }
           }
           umma_commit(bar_empty + 8 * stage);  // frees the smem slot once these MMAs retire
           if (kb == p.num_kb - 1) umma_commit(bar_tfull + 8 * acc);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
@@ -171,13 +195,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const int et = threadIdx.x - 64;           // 0..127
     int acc = 0;
     uint32_t acc_phase = 0;
+    int buf = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.n_tiles;
       const int m_tile = tile / p.n_tiles;
       const int n0 = n_tile * BN;
-      // stage this tile's per-channel scale/shift (double-buffered by accumulator stage)
-      float* sc = ep_scale + acc * BN;
-      float* sh = ep_shift + acc * BN;
+      // stage this tile's per-channel scale/shift (double-buffered: a warp can be one tile ahead)
+      float* sc = ep_scale + buf * BN;
+      float* sh = ep_shift + buf * BN;
+      buf ^= 1;
       for (int i = et; i < BN; i += kEpiThreads) {
         const int c = n0 + i;
         sc[i] = (c < p.cout) ? __ldg(p.scale + c) : 0.f;
@@ -186,11 +212,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       asm volatile("bar.sync 1, 128;" ::: "memory");
       mbar_wait(bar_tfull + 8 * acc, acc_phase, p.dbg, 0x400 | acc);
       tc_fence_after();
-      const int row = m_tile * BM + q * 32 + lane;
+#pragma unroll 1
+      for (int t = 0; t < MT; ++t) {
+      const int row = m_tile * (BM * MT) + t * BM + q * 32 + lane;
       const bool row_ok = row < p.m_total;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * Cfg::kAccCols + t * BN;
       int img = 0, pix = 0;
       if (p.out_mode == 1) { img = row / p.hw; pix = row - img * p.hw; }
+      if (m_tile * (BM * MT) + t * BM >= p.m_total) break;   // warp-uniform: subtile entirely past the end
 #pragma unroll 1
       for (int cc = 0; cc < BN / 32; ++cc) {
         uint32_t v[32];
@@ -233,11 +262,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           }
         }
       }
+      }  // M-subtiles
       // release this accumulator stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
   }
 
@@ -278,18 +308,30 @@ static int get_encoders(EncodeTiledFn* tiled, EncodeIm2colFn* im2col) {
   return 0;
 }
 
-template <int BN, int BK>
+template <int BN, int BK, int MT>
 static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, cudaStream_t stream) {
-  using Cfg = ConvCfg<BN, BK>;
+  using Cfg = ConvCfg<BN, BK, MT>;
   static bool attr_set = false;
   if (!attr_set) {
-    YB_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    YB_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, BK, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  conv_igemm_kernel<BN, BK><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  conv_igemm_kernel<BN, BK, MT><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
   return check_launch("conv_igemm_kernel");
+}
+
+template <int BK>
+static int dispatch_conv(int bn, int mt, const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, cudaStream_t stream) {
+  if (mt == 1) {
+    if (bn == 64) return launch_conv<64, BK, 1>(ta, tb, p, stream);
+    if (bn == 128) return launch_conv<128, BK, 1>(ta, tb, p, stream);
+    return launch_conv<256, BK, 1>(ta, tb, p, stream);
+  }
+  if (bn == 64) return launch_conv<64, BK, 2>(ta, tb, p, stream);
+  if (bn == 128) return launch_conv<128, BK, 2>(ta, tb, p, stream);
+  return launch_conv<256, BK, 2>(ta, tb, p, stream);
 }
 
 int conv_igemm_forward(const void* x, const void* w, const float* scale, const float* shift, float slope, void* y, int batch,
@@ -309,13 +351,17 @@ int conv_igemm_forward(const void* x, const void* w, const float* scale, const f
   const long long m_total_ll = static_cast<long long>(batch) * height * width;
   YB_REQUIRE(m_total_ll < (1ll << 31) - BM, "conv: too many pixels");
   const int bk = (cin % 64 == 0) ? 64 : 32;
-  int bn;
+  // tile shape: flags may force BLOCK_N (bits 8..17) and the number of M-subtiles (bits 20..21)
+  int bn, mt;
   const int force_bn = (flags >> 8) & 0x3FF;
+  const int force_mt = (flags >> 20) & 0x3;
   if (force_bn) bn = force_bn;
   else if (cout <= 64) bn = 64;
   else if (cout % 256 == 0 && ((flags & 2) != 0)) bn = 256;
   else bn = 128;
+  mt = force_mt ? force_mt : 1;
   YB_REQUIRE(bn == 64 || bn == 128 || bn == 256, "conv: BN=%d", bn);
+  YB_REQUIRE(mt == 1 || mt == 2, "conv: MT=%d", mt);
   const int a_im2col = (ksize == 3) ? 1 : ((flags & 1) ? 0 : 1);
 
   EncodeTiledFn enc_tiled;
@@ -328,7 +374,7 @@ int conv_igemm_forward(const void* x, const void* w, const float* scale, const f
   p.height = height; p.width = width; p.cin = cin; p.cout = cout; p.ksize = ksize; p.pad = (ksize - 1) / 2;
   p.kb_per_tap = cin / bk;
   p.num_kb = ksize * ksize * p.kb_per_tap;
-  p.m_tiles = (p.m_total + BM - 1) / BM;
+  p.m_tiles = (p.m_total + BM * mt - 1) / (BM * mt);
   p.n_tiles = (cout + bn - 1) / bn;
   p.a_im2col = a_im2col;
   p.scale = scale; p.shift = shift; p.slope = slope;
@@ -377,15 +423,8 @@ int conv_igemm_forward(const void* x, const void* w, const float* scale, const f
     if (cr != CUDA_SUCCESS) return fail(YB_ERR_DRIVER, "cuTensorMapEncodeTiled(W) failed (%d)", static_cast<int>(cr));
   }
 
-  if (bk == 64) {
-    if (bn == 64) return launch_conv<64, 64>(ta, tb, p, stream);
-    if (bn == 128) return launch_conv<128, 64>(ta, tb, p, stream);
-    return launch_conv<256, 64>(ta, tb, p, stream);
-  } else {
-    if (bn == 64) return launch_conv<64, 32>(ta, tb, p, stream);
-    if (bn == 128) return launch_conv<128, 32>(ta, tb, p, stream);
-    return launch_conv<256, 32>(ta, tb, p, stream);
-  }
+  if (bk == 64) return dispatch_conv<64>(bn, mt, ta, tb, p, stream);
+  return dispatch_conv<32>(bn, mt, ta, tb, p, stream);
 }
 
 // ---------------------------------------------------------------------------------------------

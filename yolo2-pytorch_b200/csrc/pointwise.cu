@@ -1,8 +1,6 @@
 // HBM-bound layout / pointwise kernels of the Darknet-19 path (coalesced, 16-byte vectorised):
 //   pack_weight      fp32 OIHW -> fp16 KRSC (the K-major B operand of the implicit GEMM)
 //   bn_fold          eval-mode BatchNorm2d -> per-channel fp32 (scale, shift)      model/yolo2.py:58
-//   conv0            layer "layers1.0": 3x3 Cin=3 conv + BN + leaky + 2x2 max-pool, reading the
-//                    caller's fp32 NCHW image and writing fp16 NHWC              model/yolo2.py:78-79
 //   maxpool2x2       nn.MaxPool2d(2) on fp16 NHWC                                 model/yolo2.py:79,86,97
 //   reorg            space-to-depth, offset-major channel order                   model/yolo2.py:33-46
 #include "yb_common.h"
@@ -57,106 +55,6 @@ int bn_fold(const float* gamma, const float* beta, const float* mean, const floa
   YB_REQUIRE(gamma && beta && mean && var && scale && shift && c > 0, "bn_fold: bad argument");
   bn_fold_kernel<<<(c + 127) / 128, 128, 0, stream>>>(gamma, beta, mean, var, eps, scale, shift, c);
   return check_launch("bn_fold_kernel");
-}
-
-// ------------------------------------------------------------------------------------------
-// conv0: block = 128 pooled pixels (along x) x 2 channel halves (16 each); fp32 FMA, weights
-// broadcast from shared memory as float4, the 4x4x3 input patch of a pool window in registers.
-constexpr int kC0 = 32;
-
-__global__ void __launch_bounds__(256) conv0_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                    const float* __restrict__ scale, const float* __restrict__ shift, float slope,
-                                                    __half* __restrict__ y, int height, int width) {
-  __shared__ __align__(16) float ws[27][kC0];  // [ci*9 + r*3 + s][co]
-  __shared__ float sc[kC0], sh[kC0];
-  for (int i = threadIdx.x; i < 27 * kC0; i += blockDim.x) {
-    const int co = i % kC0, kk = i / kC0;     // w is OIHW: [co][ci][r][s] -> flat co*27 + kk
-    ws[kk][co] = w[co * 27 + kk];
-  }
-  if (threadIdx.x < kC0) { sc[threadIdx.x] = scale[threadIdx.x]; sh[threadIdx.x] = shift[threadIdx.x]; }
-  __syncthreads();
-  const int ow = width >> 1, oh = height >> 1;
-  const int half = threadIdx.x >> 7;                 // warp-uniform channel half
-  const int px = blockIdx.x * 128 + (threadIdx.x & 127);
-  const int py = blockIdx.y;
-  const int img = blockIdx.z;
-  if (px >= ow) return;
-  float in[3][4][4];
-  const float* xb = x + static_cast<long long>(img) * 3 * height * width;
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-#pragma unroll
-    for (int dy = 0; dy < 4; ++dy) {
-      const int iy = 2 * py - 1 + dy;
-      const bool yok = iy >= 0 && iy < height;
-      const float* row = xb + (static_cast<long long>(c) * height + (yok ? iy : 0)) * width;
-#pragma unroll
-      for (int dx = 0; dx < 4; ++dx) {
-        const int ix = 2 * px - 1 + dx;
-        in[c][dy][dx] = (yok && ix >= 0 && ix < width) ? __ldg(row + ix) : 0.f;
-      }
-    }
-  }
-  float acc[4][16];
-#pragma unroll
-  for (int p = 0; p < 4; ++p)
-#pragma unroll
-    for (int j = 0; j < 16; ++j) acc[p][j] = 0.f;
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-#pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const float4* wp = reinterpret_cast<const float4*>(&ws[c * 9 + r * 3 + s][half * 16]);
-        float wv[16];
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          const float4 t = wp[v];
-          wv[4 * v] = t.x; wv[4 * v + 1] = t.y; wv[4 * v + 2] = t.z; wv[4 * v + 3] = t.w;
-        }
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          const float xv = in[c][(p >> 1) + r][(p & 1) + s];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) acc[p][j] = fmaf(xv, wv[j], acc[p][j]);
-        }
-      }
-    }
-  }
-  uint32_t packed[8];
-#pragma unroll
-  for (int j = 0; j < 16; j += 2) {
-    float o[2];
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int co = half * 16 + j + e;
-      float m = -INFINITY;
-#pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        float v = acc[p][j + e] * sc[co] + sh[co];
-        v = v > 0.f ? v : v * slope;
-        m = fmaxf(m, v);
-      }
-      o[e] = m;
-    }
-    const __half2 h = __floats2half2_rn(o[0], o[1]);
-    packed[j >> 1] = *reinterpret_cast<const uint32_t*>(&h);
-  }
-  uint4* dst = reinterpret_cast<uint4*>(y + ((static_cast<long long>(img) * oh + py) * ow + px) * kC0 + half * 16);
-  dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-  dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-}
-
-int conv0_forward(const float* x, const float* w, const float* scale, const float* shift, float slope, void* y, int batch, int height,
-                  int width, int cout, cudaStream_t stream) {
-  YB_REQUIRE(x && w && scale && shift && y, "conv0: null pointer");
-  YB_REQUIRE(cout == kC0, "conv0: Cout=%d unsupported (32)", cout);
-  YB_REQUIRE(batch > 0 && height > 0 && width > 0 && height % 2 == 0 && width % 2 == 0, "conv0: bad shape %dx%dx%d", batch, height, width);
-  YB_REQUIRE(batch <= 65535 && height / 2 <= 65535, "conv0: grid too large");
-  dim3 grid((width / 2 + 127) / 128, height / 2, batch);
-  conv0_kernel<<<grid, 256, 0, stream>>>(x, w, scale, shift, slope, reinterpret_cast<__half*>(y), height, width);
-  return check_launch("conv0_kernel");
 }
 
 // ------------------------------------------------------------------------------------------
