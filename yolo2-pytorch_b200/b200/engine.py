@@ -113,8 +113,8 @@ class DarknetEngine(object):
     def all_units(self):
         return self.units1 + self.units2 + [self.unit_pt] + self.units3
 
-    def plan(self, batch, height, width, device):
-        key = (batch, height, width, str(device))
+    def plan(self, batch, height, width, device, plan_id=0):
+        key = (batch, height, width, str(device), plan_id)
         p = self.plans.get(key)
         if p is None:
             p = DarknetPlan(self.units1, self.units2, self.unit_pt, self.units3, self.pools1, batch, height, width, device)
@@ -125,7 +125,7 @@ class DarknetEngine(object):
         for i, u in enumerate(self.all_units()):
             u.refresh(first_layer=(i == 0))
 
-    def forward(self, x, conv_flags=0, ref=False, collect=None):
+    def forward(self, x, conv_flags=0, ref=False, collect=None, plan_id=0):
         """x: fp32 NCHW [B,3,H,W] on the GPU -> feature fp32 NCHW [B,A*(5+C),H/32,W/32]
         (a plan-owned buffer, overwritten by the next call with the same shape).
         `collect` (dict) receives references to every unit's fp16 NHWC output (tests)."""
@@ -140,7 +140,7 @@ class DarknetEngine(object):
             raise ValueError('Darknet expects fp32 [B,3,H,W] or uint8 [B,H,W,3] with H, W multiples of 32, got %s' % (tuple(x.shape),))
         x = x.contiguous() if u8 else x.contiguous().float()
         self.refresh()
-        p = self.plan(b, h, w, x.device)
+        p = self.plan(b, h, w, x.device, plan_id)   # plan_id: independent buffer sets for concurrent streams
 
         def conv(u, src, dst, **kw):
             return ops.conv_bn_act(src, u.w16, u.scale, u.shift, u.slope, out=dst, flags=conv_flags, ref=ref, **kw)

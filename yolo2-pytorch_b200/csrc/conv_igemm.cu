@@ -351,15 +351,39 @@ int conv_igemm_forward(const void* x, const void* w, const float* scale, const f
   const long long m_total_ll = static_cast<long long>(batch) * height * width;
   YB_REQUIRE(m_total_ll < (1ll << 31) - BM, "conv: too many pixels");
   const int bk = (cin % 64 == 0) ? 64 : 32;
-  // tile shape: flags may force BLOCK_N (bits 8..17) and the number of M-subtiles (bits 20..21)
-  int bn, mt;
+  // tile shape: flags may force BLOCK_N (bits 8..17) and the number of M-subtiles (bits 20..21);
+  // otherwise pick the (BLOCK_N, M-subtiles) pair with the lowest modelled time.  The model was
+  // fitted to tools/conv_sweep.py on B200 (profiles/r01_conv_sweep.md): the kernel is bound by the
+  // L2->SM operand feed (~95 B/ns per SM, ~11 TB/s chip-wide), a tile costs its operand bytes at
+  // that rate (or its MMA time if larger), tiles run in ceil(tiles/SMs) rounds, and a CTA tile whose
+  // accumulator fills all of TMEM (256x256) cannot overlap its epilogue with the next mainloop.
+  int bn = 0, mt = 0;
   const int force_bn = (flags >> 8) & 0x3FF;
   const int force_mt = (flags >> 20) & 0x3;
-  if (force_bn) bn = force_bn;
-  else if (cout <= 64) bn = 64;
-  else if (cout % 256 == 0 && ((flags & 2) != 0)) bn = 256;
-  else bn = 128;
-  mt = force_mt ? force_mt : 1;
+  {
+    double best = 1e300;
+    const int sms = sm_count();
+    const int num_kb = ksize * ksize * (cin / bk);
+    for (int cbn = 64; cbn <= 256; cbn *= 2) {
+      if (force_bn && cbn != force_bn) continue;
+      if (!force_bn && cbn > 64 && cbn / 2 >= cout) continue;       // do not pad Cout by more than 2x
+      for (int cmt = 1; cmt <= 2; ++cmt) {
+        if (force_mt && cmt != force_mt) continue;
+        const double tiles = static_cast<double>((m_total_ll + BM * cmt - 1) / (BM * cmt)) * ((cout + cbn - 1) / cbn);
+        const double rounds = static_cast<double>((static_cast<long long>(tiles) + sms - 1) / sms);
+        const double bytes_kb = (cmt * BM + cbn) * bk * 2.0;
+        const double mma_ns_kb = cmt * (bk / 16) * (cbn >= 128 ? cbn / 2.0 : 64.0) / 1.9;   // cycles(N) = max(N,128)/2 @ ~1.9 GHz
+        const double kb_ns = bytes_kb / 95.0 > mma_ns_kb ? bytes_kb / 95.0 : mma_ns_kb;
+        const bool single_acc = 2 * cmt * cbn > 512;
+        const double tile_ns = num_kb * kb_ns + (single_acc ? 8000.0 : 500.0);
+        const double agg_ns = tiles * num_kb * bytes_kb / 11000.0;
+        double t = rounds * tile_ns;
+        if (agg_ns > t) t = agg_ns;
+        if (t < best) { best = t; bn = cbn; mt = cmt; }
+      }
+    }
+    if (bn == 0) { bn = force_bn ? force_bn : 128; mt = force_mt ? force_mt : 1; }
+  }
   YB_REQUIRE(bn == 64 || bn == 128 || bn == 256, "conv: BN=%d", bn);
   YB_REQUIRE(mt == 1 || mt == 2, "conv: MT=%d", mt);
   const int a_im2col = (ksize == 3) ? 1 : ((flags & 1) ? 0 : 1);

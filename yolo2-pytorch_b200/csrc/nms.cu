@@ -87,9 +87,29 @@ __global__ void __launch_bounds__(kNmsThreads) filter_nms_kernel(const NmsParams
       float mx = -INFINITY;
       if (prob != nullptr && (p.mode == 1 || p.best_cls != nullptr || p.best_prob != nullptr)) {
         int arg = 0;
-        for (int c = 0; c < p.num_cls; ++c) {
-          const float v = prob[static_cast<long long>(i) * p.num_cls + c];
-          if (v > mx) { mx = v; arg = c; }   // first maximum wins, as torch.max does
+        const float* pr = prob + static_cast<long long>(i) * p.num_cls;
+        if ((p.num_cls & 3) == 0) {
+          // 16-byte loads, all issued before the first use (one exposed L2 latency instead of num_cls)
+          for (int c0 = 0; c0 < p.num_cls; c0 += 20) {
+            float4 q[5];
+#pragma unroll
+            for (int u = 0; u < 5; ++u)
+              if (c0 + 4 * u < p.num_cls) q[u] = __ldg(reinterpret_cast<const float4*>(pr + c0) + u);
+#pragma unroll
+            for (int u = 0; u < 5; ++u) {
+              if (c0 + 4 * u < p.num_cls) {
+                const float e[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+                for (int z = 0; z < 4; ++z)
+                  if (e[z] > mx) { mx = e[z]; arg = c0 + 4 * u + z; }   // first maximum wins, as torch.max does
+              }
+            }
+          }
+        } else {
+          for (int c = 0; c < p.num_cls; ++c) {
+            const float v = pr[c];
+            if (v > mx) { mx = v; arg = c; }
+          }
         }
         if (p.best_cls) p.best_cls[static_cast<long long>(img) * p.n + i] = arg;
         if (p.best_prob) p.best_prob[static_cast<long long>(img) * p.n + i] = mx;
@@ -199,34 +219,79 @@ __global__ void __launch_bounds__(kNmsThreads) filter_nms_kernel(const NmsParams
   if (p.mode != 1) { if (tid == 0) p.n_det[img] = 0; return; }
   __syncthreads();
   int* cnt = reinterpret_cast<int*>(keys);  // reuse: [nk + 1] exclusive offsets
+  uint32_t* cmask = sup;                    // reuse: passing-class bitmask per kept box (num_cls <= 32 fast path)
+  const bool fast = (p.num_cls <= 32) && ((p.num_cls & 3) == 0);
   for (int k = tid; k < nk; k += kNmsThreads) {
     const int box = filt[cfilt[keep_rank[k]]];
     const float sc = score[box];
+    const float* pr = prob + static_cast<long long>(box) * p.num_cls;
     int c_pass = 0;
-    for (int c = 0; c < p.num_cls; ++c) c_pass += (__fmul_rn(sc, prob[static_cast<long long>(box) * p.num_cls + c]) > p.threshold_cls) ? 1 : 0;
+    if (fast) {
+      uint32_t m = 0;
+#pragma unroll 5
+      for (int c0 = 0; c0 < p.num_cls; c0 += 4) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(pr + c0));
+        m |= (__fmul_rn(sc, q.x) > p.threshold_cls ? 1u : 0u) << c0;
+        m |= (__fmul_rn(sc, q.y) > p.threshold_cls ? 2u : 0u) << c0;
+        m |= (__fmul_rn(sc, q.z) > p.threshold_cls ? 4u : 0u) << c0;
+        m |= (__fmul_rn(sc, q.w) > p.threshold_cls ? 8u : 0u) << c0;
+      }
+      cmask[k] = m;
+      c_pass = __popc(m);
+    } else {
+      for (int c = 0; c < p.num_cls; ++c) c_pass += (__fmul_rn(sc, pr[c]) > p.threshold_cls) ? 1 : 0;
+    }
     cnt[k + 1] = c_pass;
   }
   if (tid == 0) cnt[0] = 0;
   __syncthreads();
-  if (tid == 0) {
-    for (int k = 0; k < nk; ++k) cnt[k + 1] += cnt[k];
-    p.n_det[img] = cnt[nk] < p.det_cap ? cnt[nk] : p.det_cap;
+  if (wid == 0) {
+    // inclusive warp scan over cnt[1..nk] in chunks of 32
+    int carry = 0;
+    for (int base = 0; base < nk; base += 32) {
+      const int k = base + lane;
+      int v = (k < nk) ? cnt[k + 1] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+      }
+      if (k < nk) cnt[k + 1] = v + carry;
+      carry += __shfl_sync(0xffffffffu, v, 31);
+    }
+    if (lane == 0) p.n_det[img] = carry < p.det_cap ? carry : p.det_cap;
   }
   __syncthreads();
   for (int k = tid; k < nk; k += kNmsThreads) {
     const int box = filt[cfilt[keep_rank[k]]];
     const float sc = score[box];
+    const float* pr = prob + static_cast<long long>(box) * p.num_cls;
     int o = cnt[k];
-    for (int c = 0; c < p.num_cls; ++c) {
-      const float v = __fmul_rn(sc, prob[static_cast<long long>(box) * p.num_cls + c]);
-      if (v > p.threshold_cls) {
+    if (fast) {
+      uint32_t m = cmask[k];
+      while (m) {
+        const int c = __ffs(m) - 1;
+        m &= m - 1;
         if (o < p.det_cap) {
           const long long d = static_cast<long long>(img) * p.det_cap + o;
           p.det_keep[d] = k;
           p.det_cls[d] = c;
-          p.det_score[d] = v;
+          p.det_score[d] = __fmul_rn(sc, __ldg(pr + c));
         }
         ++o;
+      }
+    } else {
+      for (int c = 0; c < p.num_cls; ++c) {
+        const float v = __fmul_rn(sc, pr[c]);
+        if (v > p.threshold_cls) {
+          if (o < p.det_cap) {
+            const long long d = static_cast<long long>(img) * p.det_cap + o;
+            p.det_keep[d] = k;
+            p.det_cls[d] = c;
+            p.det_score[d] = v;
+          }
+          ++o;
+        }
       }
     }
   }
