@@ -209,6 +209,24 @@ def profile_layers(pipe, steps):
         return y
 
     ops.conv_bn_act = timed
+    other_records = []
+    originals = {}
+
+    def wrap_other(name):
+        fn = getattr(ops, name)
+        originals[name] = fn
+
+        def timed_other(*a, **kw):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            y = fn(*a, **kw)
+            e.record()
+            other_records.append((name, s, e))
+            return y
+        setattr(ops, name, timed_other)
+
+    for name in ('conv0_bn_leaky_pool', 'conv0_u8_bn_leaky_pool', 'maxpool2x2', 'reorg_f16', 'decode', 'filter_nms'):
+        wrap_other(name)
     step_events = []
     try:
         for _ in range(steps):
@@ -221,6 +239,12 @@ def profile_layers(pipe, steps):
         torch.cuda.synchronize()
     finally:
         ops.conv_bn_act = orig
+        for name, fn in originals.items():
+            setattr(ops, name, fn)
+    others = {}
+    for name, s, e in other_records:
+        others.setdefault(name, []).append(s.elapsed_time(e) * 1e3)
+    others = {k: dict(launches_per_step=len(v) // steps, us_per_step=sum(v) / steps) for k, v in others.items()}
     per_step = len(records) // steps
     layers = []
     for i in range(per_step):
@@ -230,7 +254,7 @@ def profile_layers(pipe, steps):
     conv_ms = sum(l['us'] for l in layers) / 1e3
     conv_flops = sum(records[i][2] for i in range(per_step))
     step_ms = sum(s.elapsed_time(e) for s, e in step_events) / steps
-    return dict(layers=layers, conv_ms=conv_ms, conv_flops=conv_flops, eager_step_ms=step_ms, launches=per_step)
+    return dict(layers=layers, others=others, conv_ms=conv_ms, conv_flops=conv_flops, eager_step_ms=step_ms, launches=per_step)
 
 
 def run_b200(args):

@@ -89,28 +89,54 @@ __global__ void __launch_bounds__(128, 4) conv0_tc_kernel(const Conv0Params p) {
   uint32_t phase = 0;
   constexpr uint32_t idesc = make_idesc_f16(128, kC0Out);
 
+  constexpr int kPatchElems = 3 * kPatchRows * kPatchCols;
+  constexpr int kPatchIters = (kPatchElems + 127) / 128;
+  // All of a tile's patch loads are issued back to back into registers (one exposed memory latency,
+  // not kPatchIters of them) and, from the second tile on, while the previous tile's MMAs and
+  // epilogue are still running.
+  auto prefetch = [&](int t, float (&v)[kPatchIters]) {
+    const int ptx = t % p.tiles_x;
+    const int pt2 = t / p.tiles_x;
+    const int pty = pt2 % p.tiles_y;
+    const int pimg = pt2 / p.tiles_y;
+    const int y0 = pty * kT0Rows - 1, x0 = ptx * kT0Cols - 1;
+#pragma unroll
+    for (int k = 0; k < kPatchIters; ++k) {
+      const int i = tid + k * 128;
+      const int c = i / (kPatchRows * kPatchCols);
+      const int rem = i - c * (kPatchRows * kPatchCols);
+      const int r = rem / kPatchCols, col = rem - r * kPatchCols;
+      const int iy = y0 + r, ix = x0 + col;
+      float val = 0.f;
+      if (i < kPatchElems && iy >= 0 && iy < p.height && ix >= 0 && ix < p.width) {
+        if (kU8) {
+          val = static_cast<float>(__ldg(reinterpret_cast<const uint8_t*>(p.x) + ((static_cast<long long>(pimg) * p.height + iy) * p.width + ix) * 3 + c)) *
+                (1.f / 255.f);
+        } else {
+          val = __ldg(reinterpret_cast<const float*>(p.x) + ((static_cast<long long>(pimg) * 3 + c) * p.height + iy) * p.width + ix);
+        }
+      }
+      v[k] = val;
+    }
+  };
+  float pre[kPatchIters];
+  if (static_cast<int>(blockIdx.x) < p.num_tiles) prefetch(blockIdx.x, pre);
+
   for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
     const int tx = tile % p.tiles_x;
     const int t2 = tile / p.tiles_x;
     const int ty = t2 % p.tiles_y;
     const int img = t2 / p.tiles_y;
-    const int y0 = ty * kT0Rows - 1, x0 = tx * kT0Cols - 1;
-    // ---- 1. stage the haloed input patch (zeros outside the image) ----
-    for (int i = tid; i < 3 * kPatchRows * kPatchCols; i += 128) {
-      const int c = i / (kPatchRows * kPatchCols);
-      const int rem = i - c * (kPatchRows * kPatchCols);
-      const int r = rem / kPatchCols, col = rem - r * kPatchCols;
-      const int iy = y0 + r, ix = x0 + col;
-      float v = 0.f;
-      if (iy >= 0 && iy < p.height && ix >= 0 && ix < p.width) {
-        if (kU8) {
-          v = static_cast<float>(__ldg(reinterpret_cast<const uint8_t*>(p.x) + ((static_cast<long long>(img) * p.height + iy) * p.width + ix) * 3 + c)) *
-              (1.f / 255.f);
-        } else {
-          v = __ldg(reinterpret_cast<const float*>(p.x) + ((static_cast<long long>(img) * 3 + c) * p.height + iy) * p.width + ix);
-        }
+    // ---- 1. stage the haloed input patch (zeros outside the image) from the prefetched registers ----
+#pragma unroll
+    for (int k = 0; k < kPatchIters; ++k) {
+      const int i = tid + k * 128;
+      if (i < kPatchElems) {
+        const int c = i / (kPatchRows * kPatchCols);
+        const int rem = i - c * (kPatchRows * kPatchCols);
+        const int r = rem / kPatchCols, col = rem - r * kPatchCols;
+        patch[c][r][col] = pre[k];
       }
-      patch[c][r][col] = v;
     }
     __syncthreads();
     // ---- 2. build the four im2col rows of this thread's window ----
@@ -160,6 +186,10 @@ __global__ void __launch_bounds__(128, 4) conv0_tc_kernel(const Conv0Params p) {
         umma_f16(tmem_base + j * kC0Out, adesc + 2, bdesc + 2, idesc, 1);
       }
       umma_commit(bar_addr);
+    }
+    {
+      const int next = tile + gridDim.x;          // overlap the next tile's input fetch with MMA + epilogue
+      if (next < p.num_tiles) prefetch(next, pre);
     }
     mbar_wait(bar_addr, phase, p.dbg, 0x500);
     phase ^= 1;

@@ -14,7 +14,7 @@
 
 namespace yb {
 
-constexpr int kNmsThreads = 256;
+constexpr int kNmsThreads = 1024;   // one CTA per image; the phases are latency-bound, so go wide
 constexpr int kMaxLimit = 1024;
 
 __device__ __forceinline__ uint32_t float_orderable(float f) {
