@@ -29,6 +29,7 @@ def main():
     ap.add_argument('--batch', type=int, default=32)
     ap.add_argument('--size', type=int, default=416)
     ap.add_argument('--iters', type=int, default=20)
+    ap.add_argument('--no-pair', action='store_true')
     a = ap.parse_args()
     dev = 'cuda'
     results = []
@@ -49,13 +50,15 @@ def main():
                 continue
             if cout <= 64 and bn != 64:
                 continue
-            for mt in (1, 2):
-                flags = ops.conv_force_bn(bn) | (mt << 20)
+            for mt, pr in ((1, 1), (2, 1), (1, 2), (2, 2)):
+                flags = ops.conv_force_bn(bn) | (mt << 20) | ops.conv_force_pair(pr)
+                if pr == 2 and a.no_pair:
+                    continue
                 try:
                     y = ops.conv_bn_act(xs[0], w, scale, shift, 0.1, out_mode=mode, flags=flags)
                     torch.cuda.synchronize()
                 except RuntimeError as e:
-                    row['configs']['bn%d_mt%d' % (bn, mt)] = dict(error=str(e)[:120])
+                    row['configs']['bn%d_mt%d%s' % (bn, mt, 'p' if pr == 2 else '')] = dict(error=str(e)[:120])
                     continue
                 if base is None:
                     base = y.clone()
@@ -71,12 +74,12 @@ def main():
                 e.record()
                 torch.cuda.synchronize()
                 us = s.elapsed_time(e) / a.iters * 1e3
-                row['configs']['bn%d_mt%d' % (bn, mt)] = dict(us=us, tflops=flops / us / 1e6, maxdiff_vs_first=diff)
+                row['configs']['bn%d_mt%d%s' % (bn, mt, 'p' if pr == 2 else '')] = dict(us=us, tflops=flops / us / 1e6, maxdiff_vs_first=diff)
         best = min((v['us'], kk) for kk, v in row['configs'].items() if 'us' in v)
         row['best'] = best[1]
         results.append(row)
         print('%-30s %7.2f GF  ' % (row['shape'], row['gflop']) + '  '.join(
-            '%s:%6.1fus/%4.0fTF%s' % (kk, v['us'], v['tflops'], '' if v['maxdiff_vs_first'] < 1e-2 else ' DIFF!') if 'us' in v else '%s:ERR' % kk
+            '%s:%.0f%s' % (kk, v['us'], '' if v['maxdiff_vs_first'] < 1e-2 else ' DIFF!') if 'us' in v else '%s:ERR' % kk
             for kk, v in row['configs'].items()) + '   best=' + row['best'], flush=True)
     os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
     with open(os.path.join(ROOT, 'gpurun_out', 'conv_sweep.json'), 'w') as f:

@@ -44,6 +44,18 @@ CASES = [
     dict(name='mt2_head_nchw', b=2, h=13, w=13, cin=1024, cout=125, k=1, nchw=1, noact=1, mt=2),
     dict(name='mt2_big_bn256', b=32, h=13, w=13, cin=1024, cout=1024, k=3, mt=2, bn=256),
     dict(name='mt2_multi_tile_persist', b=8, h=52, w=52, cin=128, cout=256, k=3, mt=2, bn=128),
+    # CTA pairs (cta_group::2), index 23..
+    dict(name='pair_1x1_tiled_single_tile', b=1, h=16, w=16, cin=64, cout=128, k=1, tiled=1, pair=2, mt=1, bn=128),
+    dict(name='pair_1x1_im2col', b=2, h=16, w=16, cin=256, cout=128, k=1, pair=2, mt=1, bn=128),
+    dict(name='pair_3x3_bn128', b=2, h=16, w=16, cin=64, cout=128, k=3, pair=2, mt=1, bn=128),
+    dict(name='pair_3x3_bn256_tail', b=3, h=13, w=13, cin=128, cout=512, k=3, pair=2, mt=1, bn=256),
+    dict(name='pair_3x3_bn64', b=2, h=26, w=26, cin=128, cout=64, k=3, pair=2, mt=1, bn=64),
+    dict(name='pair_mt2_bn256', b=5, h=13, w=13, cin=256, cout=512, k=3, pair=2, mt=2, bn=256),
+    dict(name='pair_mt2_bn128_persist', b=8, h=52, w=52, cin=128, cout=256, k=3, pair=2, mt=2, bn=128),
+    dict(name='pair_cin32', b=1, h=32, w=32, cin=32, cout=64, k=3, pair=2, mt=1, bn=64),
+    dict(name='pair_head_nchw', b=2, h=13, w=13, cin=1024, cout=125, k=1, nchw=1, noact=1, pair=2, mt=1, bn=128),
+    dict(name='pair_big', b=32, h=13, w=13, cin=1024, cout=1024, k=3, pair=2, mt=2, bn=256),
+    dict(name='pair_chan_slice', b=2, h=13, w=13, cin=1024, cout=1024, k=3, ch_off=256, y_ld=1280, pair=2, mt=1, bn=256),
 ]
 
 
@@ -69,7 +81,7 @@ def run_case(idx):
     slope = 1.0 if c.get('noact') else 0.1
     out_mode = ops.OUT_F32_NCHW if c.get('nchw') else ops.OUT_F16_NHWC
     flags = (ops.CONV_A_TILED if c.get('tiled') else 0) | (ops.CONV_WIDE_N if c.get('wide') else 0)
-    flags |= ops.conv_force_mt(c.get('mt', 0)) | ops.conv_force_bn(c.get('bn', 0))
+    flags |= ops.conv_force_mt(c.get('mt', 0)) | ops.conv_force_bn(c.get('bn', 0)) | ops.conv_force_pair(c.get('pair', 0))
     y_ld = c.get('y_ld', cout)
     ch_off = c.get('ch_off', 0)
 
@@ -122,9 +134,21 @@ def main():
     ap.add_argument('--case', type=int, default=-1)
     ap.add_argument('--out', default=os.path.join(ROOT, 'gpurun_out', 'diag.json'))
     ap.add_argument('--start', type=int, default=0, help='first case index to run')
+    ap.add_argument('--inproc', action='store_true', help='run cases [start, end) in THIS process (fast; a trap ends the run)')
+    ap.add_argument('--end', type=int, default=len(CASES))
     a = ap.parse_args()
     if a.case >= 0:
         print('DIAG_JSON ' + json.dumps(run_case(a.case)))
+        return
+    if a.inproc:
+        keys = ('name', 'error', 'rel_vs_oracle', 'rel_vs_refkernel', 'untouched_ok', 'nan', 'unwritten', 'bad_frac', 'debug_word',
+                'bad_by_channel_first16', 'bad_by_row_img0', 'sample_got', 'sample_ref')
+        for i in range(a.start, min(a.end, len(CASES))):
+            print('running %d %s' % (i, CASES[i]['name']), flush=True)
+            rec = run_case(i)
+            print(json.dumps({k: v for k, v in rec.items() if k in keys}), flush=True)
+            if 'error' in rec:
+                break
         return
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     results = []

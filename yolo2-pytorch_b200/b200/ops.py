@@ -29,6 +29,14 @@ def conv_force_mt(mt):
     return mt << 20
 
 
+def conv_force_pair(v):
+    """0 = auto, 1 = single-CTA tiles, 2 = CTA pairs (cta_group::2)."""
+    return v << 22
+
+
+CONV_ALLOW_PAIR = 4
+
+
 def _p(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
