@@ -39,6 +39,7 @@ struct ConvParams {
   int y_ch_off;     // fp16 NHWC: first destination channel
   int out_mode;     // 0: fp16 NHWC, 1: fp32 NCHW
   int hw;           // H*W
+  int skip;         // profiling ablation (results are garbage): 1 = no A loads, 2 = no B loads, 4 = no MMA, 8 = no stores
   int* dbg;
 };
 
@@ -141,7 +142,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           h0[t] = rem / p.width;
           w0[t] = rem - h0[t] * p.width;
         }
-        uint32_t tx_bytes = nsub * Cfg::kASubBytes + Cfg::kBBytes;
+        if (p.skip & 1) nsub = 0;
+        uint32_t tx_bytes = nsub * Cfg::kASubBytes + ((p.skip & 2) ? 0 : Cfg::kBBytes);
         if (kPair) {
           // the leader's barrier also counts the peer's bytes: recompute the peer's live subtiles
           const int m_peer = m_tile * Cfg::kRowsPerTile + Cfg::kRowsPerCta;
@@ -149,7 +151,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
           for (int t = 0; t < MT; ++t)
             if (m_peer + t * BM < p.m_total) nsub_peer = t + 1;
-          tx_bytes += nsub_peer * Cfg::kASubBytes + Cfg::kBBytes;     // (only used by rank 0, whose own nsub is MT here or the tile is the last one)
+          if (p.skip & 1) nsub_peer = 0;
+          tx_bytes += nsub_peer * Cfg::kASubBytes + ((p.skip & 2) ? 0 : Cfg::kBBytes);     // (only used by rank 0, whose own nsub is MT here or the tile is the last one)
         }
         for (int kb = 0; kb < p.num_kb; ++kb) {
           const int tap = kb / p.kb_per_tap;
@@ -174,7 +177,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             }
           }
           const int brow = n_tile * BN + static_cast<int>(rank) * Cfg::kBRows;
-          if (kPair) tma_load_2d_pair(smem_b + stage * Cfg::kBBytes, &tmap_b, full, tap * p.cin + c0, brow);
+          if (p.skip & 2) { /* ablation: weights not fetched */ }
+          else if (kPair) tma_load_2d_pair(smem_b + stage * Cfg::kBBytes, &tmap_b, full, tap * p.cin + c0, brow);
           else tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, full, tap * p.cin + c0, brow);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -198,6 +202,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           const uint64_t bdesc = make_kmajor_desc<Cfg::kSwizzle>(smem_b + stage * Cfg::kBBytes);
 #pragma unroll
           for (int t = 0; t < MT; ++t) {
+            if (p.skip & 4) break;
             const uint64_t adesc = make_kmajor_desc<Cfg::kSwizzle>(smem_a + stage * Cfg::kABytes + t * Cfg::kASubBytes);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
@@ -261,6 +266,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             float x = __uint_as_float(v[j]) * sc[cc * 32 + j] + sh[cc * 32 + j];
             f[j] = x > 0.f ? x : x * p.slope;
           }
+          if (p.skip & 8) continue;
           if (p.out_mode == 0) {
             if (row_ok) {
               __half* dst = reinterpret_cast<__half*>(p.y) + static_cast<long long>(row) * p.y_ld + p.y_ch_off + cbase;
@@ -459,6 +465,7 @@ int conv_igemm_forward(const void* x, const void* w, const float* scale, const f
   p.y = y; p.y_ld = y_ld; p.y_ch_off = y_ch_off; p.out_mode = out_mode;
   p.hw = height * width;
   p.dbg = debug_word_device();
+  p.skip = (flags >> 24) & 0xF;
 
   const CUtensorMapSwizzle swz = (bk == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   alignas(64) CUtensorMap ta, tb;
