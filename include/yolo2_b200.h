@@ -112,6 +112,21 @@ int yb_filter_nms(const float* score, const float* yx_min, const float* yx_max, 
 int yb_iou_matrix(const float* yx_min1, const float* yx_max1, const float* yx_min2, const float* yx_max2, float* out, int batch,
                   int n1, int n2, float min_union, yb_stream_t stream);
 
+/* ---- training: region loss, model.loss + iou_match / fit_positive / fill_norm (model/__init__.py:59-107,138-167) ---- */
+/* feature fp32 [B,A*(5+C),rows,cols] (the head output); GT in GRID units (train.norm_data, train.py:57-62):
+ * gt_yx_min/gt_yx_max [B,G,2], gt_cls int64 [B,G], zero-padded slots allowed (utils/data.py:38-41).
+ * Outputs: losses[5] = (foreground, background, center, size, cls), each already / (B*cells*A); positive /
+ * negative uint8 [B,cells,A]; best_iou [B,cells,A]; and the UNWEIGHTED per-term gradients w.r.t. feature
+ * (grad_terms: feature layout, grad_bg [B,A,cells]) consumed by yb_region_loss_bwd.  pos_count[B] and
+ * partial[B*5] are scratch.  cross_entropy: train/cross_entropy (config.ini:77). */
+int yb_region_loss_fwd(const float* feature, const float* anchors_hw, const float* gt_yx_min, const float* gt_yx_max,
+                       const long long* gt_cls, int batch, int rows, int cols, int num_anchors, int num_cls, int num_gt, float threshold,
+                       int cross_entropy, float* losses, unsigned char* positive, unsigned char* negative, float* best_iou, int* pos_count,
+                       float* partial, float* grad_terms, float* grad_bg, yb_stream_t stream);
+/* dfeature = sum_k weights5[k] * d loss_k / d feature; weights5 is a DEVICE array (hparam * upstream grad, train.py:348-351). */
+int yb_region_loss_bwd(const float* grad_terms, const float* grad_bg, const float* weights5, float* dfeature, int batch, int rows, int cols,
+                       int num_anchors, int num_cls, yb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

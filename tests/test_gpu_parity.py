@@ -357,6 +357,33 @@ def test_inference_and_postprocess_batch(darknet):
                     np.testing.assert_allclose(t.cpu().numpy(), r.numpy(), rtol=1e-6, atol=0)
 
 
+@pytest.mark.parametrize('case', [(4, 13, 16, 0), (7, 19, 6, 1), (2, 10, 1, 2)])
+def test_region_loss_values_masks_and_gradient(case):
+    """K8/K9 vs the oracle's restated model.loss (PARITY UNPINNED BY EXECUTION, see oracle header):
+    the five scalars, positive/negative masks, matched IoU and d(total)/dfeature via autograd."""
+    import model
+    b, s, g, seed = case
+    anchors = O.anchors_yolo_voc()
+    gen = torch.Generator().manual_seed(seed)
+    feat = (torch.randn(b, 125, s, s, generator=gen) * 0.7)
+    data = O.norm_data(O.synth_targets(b, s * 32, s * 32, slots=g, seed=seed + 5), s * 32, s * 32, s, s)
+    # oracle
+    f_ref = feat.clone().requires_grad_(True)
+    l_ref, dbg_ref = O.loss(anchors, data, O.decode(f_ref, anchors), 0.6)
+    O.loss_total(l_ref).backward()
+    # CUDA
+    f_gpu = feat.to(DEV).requires_grad_(True)
+    l_gpu, dbg = model.loss(anchors, {k: v.to(DEV) for k, v in data.items()}, dict(feature=f_gpu), 0.6)
+    total = sum(l_gpu[k] * O.HPARAM_DEFAULT[k] for k in l_gpu)
+    total.backward()
+    assert torch.equal(dbg['positive'].cpu().bool(), dbg_ref['positive'])
+    assert torch.equal(dbg['negative'].cpu().bool(), dbg_ref['negative'])
+    np.testing.assert_allclose(dbg['iou'].cpu().numpy(), dbg_ref['iou'].numpy(), rtol=1e-5, atol=1e-6)
+    for k in ('foreground', 'background', 'center', 'size', 'cls'):
+        assert abs(l_gpu[k].item() - l_ref[k].item()) <= 1e-4 * abs(l_ref[k].item()) + 1e-9, (k, l_gpu[k].item(), l_ref[k].item())
+    assert rel_err(f_gpu.grad, f_ref.grad) <= 1e-4
+
+
 def test_cpu_input_fails_loudly(darknet):
     with pytest.raises(RuntimeError):
         darknet(torch.zeros(1, 3, 64, 64))

@@ -235,3 +235,45 @@ def iou_matrix(yx_min1, yx_max1, yx_min2, yx_max2, min_union=1.1920928955078125e
     _ck(_l.load().yb_iou_matrix(_p(yx_min1), _p(yx_max1), _p(yx_min2), _p(yx_max2), _p(out), b, n1, n2, float(min_union), _s()),
              'yb_iou_matrix')
     return out
+
+
+def region_loss_forward(feature, anchors, gt_yx_min, gt_yx_max, gt_cls, threshold, cross_entropy=True):
+    """Region loss values + unweighted per-term gradients (see include/yolo2_b200.h: yb_region_loss_fwd).
+    Returns dict(losses[5], positive, negative, best_iou, grad_terms, grad_bg)."""
+    _req(feature, torch.float32, 'feature'); _req(anchors, torch.float32, 'anchors')
+    _req(gt_yx_min, torch.float32, 'gt_yx_min'); _req(gt_yx_max, torch.float32, 'gt_yx_max')
+    b, ch, rows, cols = feature.shape
+    a = anchors.shape[0]
+    per = ch // a
+    num_cls = per - 5 if per > 5 else 1
+    g = gt_yx_min.shape[1]
+    if num_cls > 1:
+        _req(gt_cls, torch.int64, 'gt_cls')
+    cells = rows * cols
+    dev = feature.device
+    out = dict(losses=torch.empty(5, dtype=torch.float32, device=dev),
+               positive=torch.empty(b, cells, a, dtype=torch.uint8, device=dev),
+               negative=torch.empty(b, cells, a, dtype=torch.uint8, device=dev),
+               best_iou=torch.empty(b, cells, a, dtype=torch.float32, device=dev),
+               grad_terms=torch.empty_like(feature),
+               grad_bg=torch.empty(b, a, cells, dtype=torch.float32, device=dev))
+    pos_count = torch.empty(b, dtype=torch.int32, device=dev)
+    partial = torch.empty(b * 5, dtype=torch.float32, device=dev)
+    _ck(_l.load().yb_region_loss_fwd(_p(feature), _p(anchors), _p(gt_yx_min), _p(gt_yx_max), _p(gt_cls if num_cls > 1 else None), b, rows,
+                                     cols, a, num_cls, g, float(threshold), int(bool(cross_entropy)), _p(out['losses']),
+                                     _p(out['positive']), _p(out['negative']), _p(out['best_iou']), _p(pos_count), _p(partial),
+                                     _p(out['grad_terms']), _p(out['grad_bg']), _s()), 'yb_region_loss_fwd')
+    out['pos_count'] = pos_count
+    return out
+
+
+def region_loss_backward(grad_terms, grad_bg, weights5, num_anchors):
+    """dfeature = sum_k weights5[k] * dloss_k/dfeature (weights5: device float32[5])."""
+    _req(grad_terms, torch.float32, 'grad_terms'); _req(grad_bg, torch.float32, 'grad_bg'); _req(weights5, torch.float32, 'weights5')
+    b, ch, rows, cols = grad_terms.shape
+    per = ch // num_anchors
+    num_cls = per - 5 if per > 5 else 1
+    out = torch.empty_like(grad_terms)
+    _ck(_l.load().yb_region_loss_bwd(_p(grad_terms), _p(grad_bg), _p(weights5), _p(out), b, rows, cols, num_anchors, num_cls, _s()),
+        'yb_region_loss_bwd')
+    return out

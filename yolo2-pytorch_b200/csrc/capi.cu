@@ -75,6 +75,9 @@ int decode_forward(const float*, const float*, float*, float*, float*, float*, f
 int filter_nms(const float*, const float*, const float*, const float*, int, int, int, int, float, float, float, int, int*, int*, int*,
                int*, int*, int*, int*, float*, int, int*, int*, float*, cudaStream_t);
 int iou_matrix(const float*, const float*, const float*, const float*, float*, int, int, int, float, cudaStream_t);
+int region_loss_forward(const float*, const float*, const float*, const float*, const long long*, int, int, int, int, int, int, float, int,
+                        float*, unsigned char*, unsigned char*, float*, int*, float*, float*, float*, cudaStream_t);
+int region_loss_backward(const float*, const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
 
 }  // namespace yb
 
@@ -158,6 +161,20 @@ int yb_filter_nms(const float* score, const float* yx_min, const float* yx_max, 
 int yb_iou_matrix(const float* yx_min1, const float* yx_max1, const float* yx_min2, const float* yx_max2, float* out, int batch,
                   int n1, int n2, float min_union, yb_stream_t stream) {
   return yb::iou_matrix(yx_min1, yx_max1, yx_min2, yx_max2, out, batch, n1, n2, min_union, S(stream));
+}
+
+int yb_region_loss_fwd(const float* feature, const float* anchors_hw, const float* gt_yx_min, const float* gt_yx_max,
+                       const long long* gt_cls, int batch, int rows, int cols, int num_anchors, int num_cls, int num_gt, float threshold,
+                       int cross_entropy, float* losses, unsigned char* positive, unsigned char* negative, float* best_iou, int* pos_count,
+                       float* partial, float* grad_terms, float* grad_bg, yb_stream_t stream) {
+  return yb::region_loss_forward(feature, anchors_hw, gt_yx_min, gt_yx_max, gt_cls, batch, rows, cols, num_anchors, num_cls, num_gt,
+                                 threshold, cross_entropy, losses, positive, negative, best_iou, pos_count, partial, grad_terms, grad_bg,
+                                 S(stream));
+}
+
+int yb_region_loss_bwd(const float* grad_terms, const float* grad_bg, const float* weights5, float* dfeature, int batch, int rows, int cols,
+                       int num_anchors, int num_cls, yb_stream_t stream) {
+  return yb::region_loss_backward(grad_terms, grad_bg, weights5, dfeature, batch, rows, cols, num_anchors, num_cls, S(stream));
 }
 
 }  // extern "C"

@@ -94,8 +94,46 @@ def _inference(inference, tensor):
     return pred
 
 
-def loss(anchors, data, pred, threshold):
-    """Region loss (reference model/__init__.py:138-167).  The fused target-assignment + loss
-    kernels are the next row of the hot-path table; this build fails loudly rather
-    than fall back to torch ops."""
-    raise NotImplementedError('model.loss (B200): region-loss kernels are not part of this build yet')
+class _RegionLoss(torch.autograd.Function):
+    """feature -> the five region-loss scalars; backward = one kernel combining the stored per-term
+    gradients with the upstream weights (no host sync)."""
+
+    @staticmethod
+    def forward(ctx, feature, anchors, yx_min, yx_max, cls, threshold, cross_entropy, holder):
+        out = _ops.region_loss_forward(feature.detach().contiguous().float(), anchors, yx_min, yx_max, cls, threshold, cross_entropy)
+        ctx.save_for_backward(out['grad_terms'], out['grad_bg'])
+        ctx.num_anchors = anchors.size(0)
+        holder.update(out)
+        losses = out['losses']
+        return losses[0], losses[1], losses[2], losses[3], losses[4]
+
+    @staticmethod
+    def backward(ctx, g0, g1, g2, g3, g4):
+        grad_terms, grad_bg = ctx.saved_tensors
+        zero = torch.zeros((), dtype=torch.float32, device=grad_terms.device)
+        w = torch.stack([zero if g is None else g.float() for g in (g0, g1, g2, g3, g4)])
+        return _ops.region_loss_backward(grad_terms, grad_bg, w.contiguous(), ctx.num_anchors), None, None, None, None, None, None, None
+
+
+def loss(anchors, data, pred, threshold, cross_entropy=True):
+    """Region loss (reference model/__init__.py:138-167) as fused CUDA kernels: target assignment
+    (iou_match :59-73, fit_positive :76-95, fill_norm :98-103), the five terms and the closed-form
+    gradient w.r.t. the head feature map.  `data` holds yx_min / yx_max [B,G,2] in GRID units
+    (train.norm_data) and cls [B,G]; zero-padded slots are allowed.  Returns (dict of 5 scalars that
+    back-propagate into pred['feature'], debug dict) like the reference.  `cross_entropy` mirrors
+    train/cross_entropy (config.ini:77; the reference infers it from the rank of data['cls'])."""
+    feature = pred['feature']
+    if not feature.is_cuda:
+        raise RuntimeError('model.loss (B200): tensors must be on the GPU; there is no CPU fallback')
+    dev = feature.device
+    anchors = anchors.detach().to(device=dev, dtype=torch.float32).contiguous()
+    yx_min = data['yx_min'].to(device=dev, dtype=torch.float32).contiguous()
+    yx_max = data['yx_max'].to(device=dev, dtype=torch.float32).contiguous()
+    cls = data['cls'].to(device=dev, dtype=torch.int64).contiguous()
+    aux = {}
+    values = _RegionLoss.apply(feature, anchors, yx_min, yx_max, cls, float(threshold), bool(cross_entropy), aux)
+    names = ('foreground', 'background', 'center', 'size', 'cls')
+    per = feature.size(1) // anchors.size(0)
+    losses = {k: v for k, v in zip(names, values) if k != 'cls' or per > 5}
+    debug = dict(iou=aux['best_iou'], positive=aux['positive'], negative=aux['negative'], pos_count=aux['pos_count'])
+    return losses, debug
