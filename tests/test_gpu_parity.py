@@ -387,3 +387,85 @@ def test_region_loss_values_masks_and_gradient(case):
 def test_cpu_input_fails_loudly(darknet):
     with pytest.raises(RuntimeError):
         darknet(torch.zeros(1, 3, 64, 64))
+
+
+# ------------------------------------------------------------------------------------------------
+# training path: weight gradient kernel, train-mode forward, full backward vs the oracle's autograd
+# ------------------------------------------------------------------------------------------------
+WGRAD_CASES = [  # b, h, cin, cout, k, dz_ld
+    (2, 16, 64, 128, 3, 128), (3, 13, 256, 512, 3, 512), (1, 32, 32, 64, 3, 64), (2, 26, 512, 64, 1, 64),
+    (2, 13, 1024, 125, 1, 128), (8, 52, 128, 256, 3, 256), (4, 13, 1280, 1024, 3, 1024),
+]
+
+
+@pytest.mark.parametrize('case', WGRAD_CASES)
+def test_conv_wgrad_vs_torch(ops, case):
+    b, h, cin, cout, k, dz_ld = case
+    gen = torch.Generator().manual_seed(cin + cout + k)
+    x = torch.randn(b, h, h, cin, generator=gen).half()
+    dz = torch.zeros(b, h, h, dz_ld).half()
+    dz[..., :cout] = (torch.randn(b, h, h, cout, generator=gen) * 0.1).half()
+    ref = torch.nn.grad.conv2d_weight(x.float().permute(0, 3, 1, 2), (cout, cin, k, k), dz[..., :cout].float().permute(0, 3, 1, 2),
+                                      padding=(k - 1) // 2)
+    dw_krsc = torch.empty(cout, k, k, cin, dtype=torch.float32, device=DEV)
+    ops.call('yb_conv_wgrad', x.to(DEV), dz.to(DEV), dw_krsc, b, h, h, cin, cout, k, cin, dz_ld)
+    dw = torch.empty(cout, cin, k, k, dtype=torch.float32, device=DEV)
+    ops.call('yb_unpack_wgrad', dw_krsc, dw, cout, cin, k)
+    err = rel_err(dw, ref)
+    assert err <= 2e-3, 'rel err %.3e' % err
+
+
+def _oracle_train_step(sd_in, x, data, anchors):
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'running' not in k else v.clone()) for k, v in sd_in.items()}
+    stats = {}
+    feature = O.darknet_forward(sd, x, train=True, stats=stats)
+    losses, _ = O.loss(anchors, data, O.decode(feature, anchors), 0.6)
+    total = O.loss_total(losses)
+    total.backward()
+    return feature.detach(), {k: v.item() for k, v in losses.items()}, {k: v.grad for k, v in sd.items() if v.requires_grad}, stats
+
+
+def test_training_step_vs_oracle():
+    """C3-style step at a small size: train-mode forward (batch-stat BN), region loss, full backward.
+    Compared with torch autograd over the oracle (fp32): forward rel <= 5e-3, loss rel <= 1e-2, every
+    parameter gradient cosine >= 0.98 (fp16 activations/gradients over 23 layers), running stats rel <= 1e-3."""
+    import model
+    import model.yolo2
+    cfg = make_config(1)
+    anchors = O.anchors_yolo_voc()
+    sd0 = O.make_state_dict(0)
+    b, size = 4, 128
+    s = size // 32
+    x = O.synth_images(b, size, size, seed=12)
+    data = O.norm_data(O.synth_targets(b, size, size, slots=6, seed=13), size, size, s, s)
+    f_ref, l_ref, g_ref, stats = _oracle_train_step(sd0, x, data, anchors)
+
+    dnn = model.yolo2.Darknet(model.ConfigChannels(cfg), anchors, 20)
+    dnn.load_state_dict(sd0, strict=False)
+    dnn = dnn.to(DEV).train()
+    inference = model.Inference(cfg, dnn, anchors).train()
+    pred = model._inference(inference, x.to(DEV))
+    losses, _ = model.loss(anchors, {k: v.to(DEV) for k, v in data.items()}, pred, 0.6)
+    total = sum(losses[k] * O.HPARAM_DEFAULT[k] for k in losses)
+    total.backward()
+    e_f = rel_err(pred['feature'], f_ref)
+    print('train forward feature rel %.3e' % e_f)
+    assert e_f <= 5e-3
+    for k in l_ref:
+        assert abs(losses[k].item() - l_ref[k]) <= 1e-2 * abs(l_ref[k]) + 1e-7, (k, losses[k].item(), l_ref[k])
+    worst = (1.0, None)
+    for name, p in dnn.named_parameters():
+        assert p.grad is not None, name
+        g, r = p.grad.detach().float().cpu().flatten(), g_ref[name].flatten()
+        cos = torch.dot(g, r) / (g.norm() * r.norm() + 1e-30)
+        rel = ((g - r).norm() / (r.norm() + 1e-30)).item()
+        if cos.item() < worst[0]:
+            worst = (cos.item(), name, rel)
+        assert cos.item() >= 0.98, '%s: cosine %.4f rel %.3e' % (name, cos.item(), rel)
+    print('worst gradient cosine %.5f (%s, rel %.3e)' % worst)
+    # running statistics after one step (momentum 0.01, unbiased variance)
+    for key, (mean, var) in stats.items():
+        n = b * f_ref.shape[-1] ** 2 if False else None
+        rm = dict(dnn.named_buffers())[key + '.bn.running_mean'].cpu()
+        exp = 0.99 * sd0[key + '.bn.running_mean'] + 0.01 * mean.detach()
+        assert rel_err(rm, exp) <= 2e-3, key

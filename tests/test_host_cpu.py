@@ -103,5 +103,5 @@ def test_plugin_surface_state_dict_and_channels():
     pruned['layers1.5.conv.weight'] = ref['layers1.5.conv.weight'][:, :96]
     dnn2 = cls(model.ConfigChannels(config, pruned), O.anchors_yolo_voc(), 20)
     assert dnn2.layers1[4].conv.weight.shape[0] == 96 and dnn2.layers1[5].conv.weight.shape[1] == 96
-    with pytest.raises(NotImplementedError):
-        dnn.train()(torch.zeros(1, 3, 32, 32))
+    with pytest.raises(RuntimeError):
+        dnn.train()(torch.zeros(1, 3, 32, 32))     # CPU tensor: no fallback in train mode either

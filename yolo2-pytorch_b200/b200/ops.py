@@ -277,3 +277,9 @@ def region_loss_backward(grad_terms, grad_bg, weights5, num_anchors):
     _ck(_l.load().yb_region_loss_bwd(_p(grad_terms), _p(grad_bg), _p(weights5), _p(out), b, rows, cols, num_anchors, num_cls, _s()),
         'yb_region_loss_bwd')
     return out
+
+
+def call(name, *args):
+    """Generic C-ABI call: tensors become device pointers (None -> NULL), the current stream is appended."""
+    conv = [(_p(a) if isinstance(a, torch.Tensor) or a is None else a) for a in args]
+    _ck(getattr(_l.load(), name)(*conv, _s()), name)

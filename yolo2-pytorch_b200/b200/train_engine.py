@@ -1,0 +1,244 @@
+"""Training-mode forward and backward of the Darknet-19 backbone on the B200 kernels.
+
+What the reference gets from torch autograd over nn.Conv2d / BatchNorm2d(train) / LeakyReLU / MaxPool2d /
+reorg / cat (model/yolo2.py:49-65,125-130; train.py:344-351) is issued here as an explicit kernel chain:
+
+  forward, per unit : tcgen05 conv -> raw z (fp16 NHWC) -> batch statistics (double) -> running-stat update
+                      (momentum 0.01) -> normalise + leaky (+ 2x2 max-pool) -> a
+  backward, per unit: leaky/BN(/pool) backward in two passes (reduce, apply) -> dgamma, dbeta, dz (fp16)
+                      -> tcgen05 weight gradient (pixels are the reduction dim) + tcgen05 data gradient
+                      (the forward kernel on dz with rotated, transposed weights)
+
+Gradients travel in fp16 multiplied by `grad_scale` (static loss scaling; parameter gradients are un-scaled in fp32).
+BatchNorm statistics are per process (per GPU), exactly like the per-replica statistics of the reference's
+nn.DataParallel.
+"""
+import torch
+
+from . import ops
+
+SLOPE = 0.1
+
+
+class _Saved(object):
+    pass
+
+
+class DarknetTrainer(object):
+    def __init__(self, engine, grad_scale=16384.0):
+        self.engine = engine
+        self.grad_scale = float(grad_scale)
+        self.sums = {}       # per-unit double[2C] accumulators (self-cleaning)
+        self.wd_cache = {}   # dgrad weights per unit, keyed by parameter version
+
+    # ---- helpers -------------------------------------------------------------------------------------
+    def _sums(self, key, channels, device):
+        t = self.sums.get(key)
+        if t is None or t.numel() != 2 * channels or t.device != device:
+            t = torch.zeros(2 * channels, dtype=torch.float64, device=device)
+            self.sums[key] = t
+        return t
+
+    def _ones(self, c, device):
+        key = ('ones', c, str(device))
+        t = self.sums.get(key)
+        if t is None:
+            t = (torch.ones(c, dtype=torch.float32, device=device), torch.zeros(c, dtype=torch.float32, device=device))
+            self.sums[key] = t
+        return t
+
+    def _raw_conv(self, u, src, out=None, **kw):
+        one, zero = self._ones(u.cout, src.device)
+        return ops.conv_bn_act(src, u.w16, one, zero, 1.0, out=out, **kw)
+
+    def _bn_forward(self, key, u, z, rows):
+        bn = u.bn
+        c = u.cout
+        dev = z.device
+        sums = self._sums(('f', key), c, dev)
+        mean = torch.empty(c, dtype=torch.float32, device=dev)
+        invstd = torch.empty(c, dtype=torch.float32, device=dev)
+        ops.call('yb_bn_stats', z, z.shape[-1], rows, c, sums)
+        ops.call('yb_bn_finalize', sums, rows, c, float(bn.eps), float(bn.momentum), bn.running_mean, bn.running_var, mean, invstd)
+        if bn.num_batches_tracked is not None:
+            bn.num_batches_tracked += 1
+        u._bver = None      # running stats changed behind torch's version counter: re-fold on the next eval forward
+        return mean, invstd
+
+    def _apply(self, u, z, mean, invstd, b, h, w, pool, out=None, a_off=0):
+        c = u.cout
+        if out is None:
+            out = torch.empty(b, h // 2 if pool else h, w // 2 if pool else w, c, dtype=torch.float16, device=z.device)
+        ops.call('yb_bn_act_apply', z, z.shape[-1], mean, invstd, u.bn.weight.detach(), u.bn.bias.detach(), SLOPE, out, out.shape[-1], a_off,
+                 b, h, w, c, int(pool))
+        return out
+
+    # ---- forward -------------------------------------------------------------------------------------
+    def forward(self, x):
+        eng = self.engine
+        if not x.is_cuda:
+            raise RuntimeError('Darknet (B200) training: input must be a CUDA tensor')
+        b, _, h, w = x.shape
+        x = x.contiguous().float()
+        eng.refresh()
+        for u in eng.all_units()[:-1]:
+            if u.bn is None:
+                raise NotImplementedError('training path requires batch_norm/enable = 1')
+        dev = x.device
+        saved = _Saved()
+        saved.x, saved.b, saved.h, saved.w = x, b, h, w
+        saved.units = {}
+
+        def record(key, u, ain, z, mean, invstd, hh, ww, pooled):
+            s = _Saved()
+            s.u, s.ain, s.z, s.mean, s.invstd, s.h, s.w, s.pooled = u, ain, z, mean, invstd, hh, ww, pooled
+            saved.units[key] = s
+
+        # layers1.0 (direct from the fp32 image)
+        u0 = eng.units1[0]
+        z = torch.empty(b, h, w, u0.cout, dtype=torch.float16, device=dev)
+        ops.call('yb_conv0_raw_fwd', x, u0.w16, z, b, h, w, u0.cout)
+        mean, invstd = self._bn_forward('layers1.0', u0, z, b * h * w)
+        cur = self._apply(u0, z, mean, invstd, b, h, w, True)
+        record('layers1.0', u0, None, z, mean, invstd, h, w, True)
+        hh, ww = h // 2, w // 2
+        for u, key, pooled in zip(eng.units1[1:], eng._k1[1:], eng.pools1[1:]):
+            z = self._raw_conv(u, cur)
+            mean, invstd = self._bn_forward(key, u, z, b * hh * ww)
+            last = key == eng._k1[-1]
+            a = self._apply(u, z, mean, invstd, b, hh, ww, pooled and not last)
+            record(key, u, cur, z, mean, invstd, hh, ww, pooled)
+            cur = a
+            if pooled and not last:
+                hh, ww = hh // 2, ww // 2
+        x1 = cur                                    # layers1.16 output, unpooled (hh x ww)
+        # passthrough -> reorg -> concat[..., :4*Cpt]
+        upt = eng.unit_pt
+        cat_ch = upt.cout * 4 + eng.units2[-1].cout
+        cat = torch.empty(b, hh // 2, ww // 2, cat_ch, dtype=torch.float16, device=dev)
+        z = self._raw_conv(upt, x1)
+        mean, invstd = self._bn_forward('passthrough', upt, z, b * hh * ww)
+        a_pt = self._apply(upt, z, mean, invstd, b, hh, ww, False)
+        record('passthrough', upt, x1, z, mean, invstd, hh, ww, False)
+        ops.reorg_f16(a_pt, cat, 0)
+        # trunk
+        cur = ops.maxpool2x2(x1)
+        h32, w32 = hh // 2, ww // 2
+        for i, (u, key) in enumerate(zip(eng.units2, eng._k2)):
+            z = self._raw_conv(u, cur)
+            mean, invstd = self._bn_forward(key, u, z, b * h32 * w32)
+            if i == len(eng.units2) - 1:
+                self._apply(u, z, mean, invstd, b, h32, w32, False, out=cat, a_off=upt.cout * 4)
+                a = cat
+            else:
+                a = self._apply(u, z, mean, invstd, b, h32, w32, False)
+            record(key, u, cur, z, mean, invstd, h32, w32, False)
+            cur = a
+        saved.keys2 = list(eng._k2[:len(eng.units2)])
+        u30, u31 = eng.units3
+        z = self._raw_conv(u30, cat)
+        mean, invstd = self._bn_forward('layers3.0', u30, z, b * h32 * w32)
+        a30 = self._apply(u30, z, mean, invstd, b, h32, w32, False)
+        record('layers3.0', u30, cat, z, mean, invstd, h32, w32, False)
+        feature = ops.conv_bn_act(a30, u31.w16, u31.scale, u31.shift, 1.0, out_mode=ops.OUT_F32_NCHW)
+        saved.a30, saved.cat, saved.x1, saved.h16, saved.w16, saved.h32, saved.w32 = a30, cat, x1, hh, ww, h32, w32
+        return feature, saved
+
+    # ---- backward ------------------------------------------------------------------------------------
+    def _wd(self, key, u, cout_pad=0):
+        w = u.conv.weight
+        ver = (w.data_ptr(), w._version)
+        hit = self.wd_cache.get(key)
+        if hit is None or hit[0] != ver:
+            cout, cin, k, _ = w.shape
+            cp = max(cout, cout_pad)
+            wd = torch.empty(cin, k, k, cp, dtype=torch.float16, device=w.device)
+            ops.call('yb_pack_weight_dgrad_f16', w.detach().contiguous(), wd, cout, cin, k, cp)
+            self.wd_cache[key] = (ver, wd)
+            hit = self.wd_cache[key]
+        return hit[1]
+
+    def _wgrad(self, u, ain, dz, b, hh, ww, grads, name, cout=None):
+        cout = u.cout if cout is None else cout
+        cin, k = u.cin, u.ksize
+        dw_krsc = torch.empty(cout, k, k, cin, dtype=torch.float32, device=dz.device)
+        ops.call('yb_conv_wgrad', ain, dz, dw_krsc, b, hh, ww, cin, cout, k, ain.shape[-1], dz.shape[-1])
+        dw = torch.empty(cout, cin, k, k, dtype=torch.float32, device=dz.device)
+        ops.call('yb_unpack_wgrad', dw_krsc, dw, cout, cin, k)
+        grads[name + '.conv.weight'] = dw.mul_(1.0 / self.grad_scale)
+
+    def _unit_backward(self, key, s, b, grads, da=None, da_off=0, dap=None, dap_off=0, need_dgrad=True):
+        """Backward of one BN unit; returns the gradient w.r.t. the unit's input activation (or None)."""
+        u = s.u
+        c = u.cout
+        dev = s.z.device
+        window = 1 if (dap is not None) else 0
+        sums = self._sums(('b', key), c, dev)
+        bnw, bnb = u.bn.weight.detach(), u.bn.bias.detach()
+        args = (s.z, s.z.shape[-1], s.mean, s.invstd, bnw, bnb, SLOPE, da, 0 if da is None else da.shape[-1], da_off, dap,
+                0 if dap is None else dap.shape[-1], dap_off, b, s.h, s.w, c, window, sums)
+        ops.call('yb_bn_act_bwd', 0, *args, None, 0, 1)
+        dgamma = torch.empty(c, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(c, dtype=torch.float32, device=dev)
+        ops.call('yb_bn_param_grad', sums, c, dgamma, dbeta, 0)
+        dz = torch.empty(b, s.h, s.w, c, dtype=torch.float16, device=dev)
+        ops.call('yb_bn_act_bwd', 1, *args, dz, c, 1)
+        sums.zero_()
+        grads[key + '.bn.weight'] = dgamma.mul_(1.0 / self.grad_scale)
+        grads[key + '.bn.bias'] = dbeta.mul_(1.0 / self.grad_scale)
+        if s.ain is None:
+            return dz
+        self._wgrad(u, s.ain, dz, b, s.h, s.w, grads, key)
+        if not need_dgrad:
+            return None
+        one, zero = self._ones(u.cin, dev)
+        return ops.conv_bn_act(dz, self._wd(key, u), one, zero, 1.0)
+
+    def backward(self, saved, dfeature):
+        """dfeature: fp32 NCHW gradient of the loss w.r.t. the head output.  Returns {state_dict key: fp32 grad}."""
+        eng = self.engine
+        b = saved.b
+        grads = {}
+        dev = dfeature.device
+        u30, u31 = eng.units3
+        h32, w32 = saved.h32, saved.w32
+        chead = u31.cout
+        cpad = (chead + 31) // 32 * 32
+        # head: bias gradient from the unscaled fp32 gradient, dz scaled into fp16
+        dzh = torch.empty(b, h32, w32, cpad, dtype=torch.float16, device=dev)
+        dbias = torch.empty(chead, dtype=torch.float32, device=dev)
+        scaled = (dfeature.contiguous().float() * self.grad_scale)
+        ops.call('yb_head_grad_prepare', scaled, dzh, dbias, b, chead, cpad, h32 * w32)
+        grads['layers3.1.conv.bias'] = dbias.mul_(1.0 / self.grad_scale)
+        self._wgrad(u31, saved.a30, dzh, b, h32, w32, grads, 'layers3.1', cout=chead)
+        one, zero = self._ones(u31.cin, dev)
+        da = ops.conv_bn_act(dzh, self._wd('layers3.1', u31, cpad), one, zero, 1.0)
+        # layers3.0 -> gradient of the concat buffer
+        dcat = self._unit_backward('layers3.0', saved.units['layers3.0'], b, grads, da=da)
+        cpt4 = eng.unit_pt.cout * 4
+        # trunk: layers2.* (the last one reads its gradient from channels [cpt4, ...) of dcat)
+        g, g_off = dcat, cpt4
+        for key in reversed(saved.keys2):
+            g = self._unit_backward(key, saved.units[key], b, grads, da=g, da_off=g_off)
+            g_off = 0
+        d_x1_pool = g                                              # [B,h32,w32,C16]
+        # passthrough branch
+        d_apt = torch.empty(b, saved.h16, saved.w16, eng.unit_pt.cout, dtype=torch.float16, device=dev)
+        ops.call('yb_reorg_bwd_f16', dcat, dcat.shape[-1], 0, d_apt, b, saved.h16, saved.w16, eng.unit_pt.cout)
+        d_x1 = self._unit_backward('passthrough', saved.units['passthrough'], b, grads, da=d_apt)
+        # layers1.* in reverse; the branch point layers1.16 gets both gradients
+        keys1 = eng._k1
+        g_da, g_dap = d_x1, d_x1_pool
+        for key in reversed(keys1[1:]):
+            s = saved.units[key]
+            g = self._unit_backward(key, s, b, grads, da=g_da, dap=g_dap)
+            prev_key = keys1[keys1.index(key) - 1]
+            prev_pooled = saved.units[prev_key].pooled
+            g_da, g_dap = (None, g) if prev_pooled else (g, None)
+        # layers1.0: weight gradient straight from the fp32 image
+        s0 = saved.units['layers1.0']
+        dz0 = self._unit_backward('layers1.0', s0, b, grads, da=g_da, dap=g_dap)
+        dw0 = torch.empty_like(eng.units1[0].conv.weight, dtype=torch.float32)
+        ops.call('yb_conv0_wgrad', saved.x, dz0, dw0, b, saved.h, saved.w)
+        grads['layers1.0.conv.weight'] = dw0.mul_(1.0 / self.grad_scale)
+        return grads

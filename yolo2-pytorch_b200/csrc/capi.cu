@@ -64,9 +64,9 @@ int conv_igemm_forward(const void*, const void*, const float*, const float*, flo
                        int, int, int, cudaStream_t);
 int conv_ref_forward(const void*, const void*, const float*, const float*, float, void*, int, int, int, int, int, int, int, long long,
                      int, int, cudaStream_t);
-int pack_weight(const float*, void*, int, int, int, int, cudaStream_t);
+int pack_weight(const float*, void*, int, int, int, int, int, cudaStream_t);
 int bn_fold(const float*, const float*, const float*, const float*, float, float*, float*, int, cudaStream_t);
-int conv0_tc_forward(const void*, int, const float*, const float*, const float*, float, void*, int, int, int, int, cudaStream_t);
+int conv0_tc_forward(const void*, int, const float*, const float*, const float*, float, void*, int, int, int, int, int, cudaStream_t);
 int maxpool2x2(const void*, void*, int, int, int, int, int, cudaStream_t);
 int reorg_nhwc(const void*, void*, int, int, int, int, int, int, int, cudaStream_t);
 int reorg_nchw(const float*, float*, int, int, int, int, int, int, cudaStream_t);
@@ -78,6 +78,18 @@ int iou_matrix(const float*, const float*, const float*, const float*, float*, i
 int region_loss_forward(const float*, const float*, const float*, const float*, const long long*, int, int, int, int, int, int, float, int,
                         float*, unsigned char*, unsigned char*, float*, int*, float*, float*, float*, cudaStream_t);
 int region_loss_backward(const float*, const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
+int bn_stats(const void*, long long, long long, int, double*, cudaStream_t);
+int bn_finalize(double*, long long, int, float, float, float*, float*, float*, float*, cudaStream_t);
+int bn_act_apply(const void*, long long, const float*, const float*, const float*, const float*, float, void*, long long, int, int, int, int, int,
+                 int, cudaStream_t);
+int bn_act_bwd(int, const void*, long long, const float*, const float*, const float*, const float*, float, const void*, long long, int,
+               const void*, long long, int, int, int, int, int, int, double*, void*, long long, int, cudaStream_t);
+int bn_param_grad(double*, int, float*, float*, int, cudaStream_t);
+int reorg_bwd(const void*, long long, int, void*, int, int, int, int, cudaStream_t);
+int head_grad_prepare(const float*, void*, float*, int, int, int, int, cudaStream_t);
+int conv0_wgrad(const float*, const void*, float*, int, int, int, cudaStream_t);
+int unpack_wgrad(const float*, float*, int, int, int, cudaStream_t);
+int conv_wgrad_forward(const void*, const void*, float*, int, int, int, int, int, int, int, int, cudaStream_t);
 
 }  // namespace yb
 
@@ -97,7 +109,7 @@ int yb_debug_read(int out[4]) {
 }
 
 int yb_pack_weight_f16(const float* w_oihw, void* w_f16, int cout, int cin, int ksize, int mode, yb_stream_t stream) {
-  return yb::pack_weight(w_oihw, w_f16, cout, cin, ksize, mode, S(stream));
+  return yb::pack_weight(w_oihw, w_f16, cout, cin, ksize, mode, 0, S(stream));
 }
 
 int yb_bn_fold(const float* gamma, const float* beta, const float* running_mean, const float* running_var, float eps, float* scale,
@@ -107,12 +119,12 @@ int yb_bn_fold(const float* gamma, const float* beta, const float* running_mean,
 
 int yb_conv0_bn_leaky_pool_fwd(const float* x_nchw, const float* w_oihw, const float* scale, const float* shift, float slope,
                                void* y_nhwc_f16, int batch, int height, int width, int cout, yb_stream_t stream) {
-  return yb::conv0_tc_forward(x_nchw, 0, w_oihw, scale, shift, slope, y_nhwc_f16, batch, height, width, cout, S(stream));
+  return yb::conv0_tc_forward(x_nchw, 0, w_oihw, scale, shift, slope, y_nhwc_f16, batch, height, width, cout, 0, S(stream));
 }
 
 int yb_conv0_u8_bn_leaky_pool_fwd(const unsigned char* x_nhwc_u8, const float* w_oihw, const float* scale, const float* shift,
                                   float slope, void* y_nhwc_f16, int batch, int height, int width, int cout, yb_stream_t stream) {
-  return yb::conv0_tc_forward(x_nhwc_u8, 1, w_oihw, scale, shift, slope, y_nhwc_f16, batch, height, width, cout, S(stream));
+  return yb::conv0_tc_forward(x_nhwc_u8, 1, w_oihw, scale, shift, slope, y_nhwc_f16, batch, height, width, cout, 0, S(stream));
 }
 
 int yb_conv_bn_act_fwd(const void* x, const void* w, const float* scale, const float* shift, float slope, void* y, int batch,
@@ -175,6 +187,64 @@ int yb_region_loss_fwd(const float* feature, const float* anchors_hw, const floa
 int yb_region_loss_bwd(const float* grad_terms, const float* grad_bg, const float* weights5, float* dfeature, int batch, int rows, int cols,
                        int num_anchors, int num_cls, yb_stream_t stream) {
   return yb::region_loss_backward(grad_terms, grad_bg, weights5, dfeature, batch, rows, cols, num_anchors, num_cls, S(stream));
+}
+
+int yb_conv0_raw_fwd(const float* x_nchw, const float* w_oihw, void* z_nhwc_f16, int batch, int height, int width, int cout,
+                     yb_stream_t stream) {
+  return yb::conv0_tc_forward(x_nchw, 0, w_oihw, nullptr, nullptr, 1.f, z_nhwc_f16, batch, height, width, cout, 1, S(stream));
+}
+
+int yb_pack_weight_dgrad_f16(const float* w_oihw, void* w_f16, int cout, int cin, int ksize, int cout_pad, yb_stream_t stream) {
+  return yb::pack_weight(w_oihw, w_f16, cout, cin, ksize, 1, cout_pad, S(stream));
+}
+
+int yb_bn_stats(const void* z, long long ld, long long rows, int channels, double* sums, yb_stream_t stream) {
+  return yb::bn_stats(z, ld, rows, channels, sums, S(stream));
+}
+
+int yb_bn_finalize(double* sums, long long rows, int channels, float eps, float momentum, float* running_mean, float* running_var,
+                   float* mean, float* invstd, yb_stream_t stream) {
+  return yb::bn_finalize(sums, rows, channels, eps, momentum, running_mean, running_var, mean, invstd, S(stream));
+}
+
+int yb_bn_act_apply(const void* z, long long ld_z, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                    float slope, void* a, long long ld_a, int a_ch_off, int batch, int height, int width, int channels, int pool,
+                    yb_stream_t stream) {
+  return yb::bn_act_apply(z, ld_z, mean, invstd, gamma, beta, slope, a, ld_a, a_ch_off, batch, height, width, channels, pool, S(stream));
+}
+
+int yb_bn_act_bwd(int mode, const void* z, long long ld_z, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                  float slope, const void* da, long long ld_da, int da_off, const void* dap, long long ld_dap, int dap_off, int batch,
+                  int height, int width, int channels, int window, double* sums, void* dz, long long ld_dz, int has_bn, yb_stream_t stream) {
+  return yb::bn_act_bwd(mode, z, ld_z, mean, invstd, gamma, beta, slope, da, ld_da, da_off, dap, ld_dap, dap_off, batch, height, width,
+                        channels, window, sums, dz, ld_dz, has_bn, S(stream));
+}
+
+int yb_bn_param_grad(double* sums, int channels, float* dgamma, float* dbeta, int reset, yb_stream_t stream) {
+  return yb::bn_param_grad(sums, channels, dgamma, dbeta, reset, S(stream));
+}
+
+int yb_reorg_bwd_f16(const void* dy, long long ld_dy, int dy_off, void* dx, int batch, int height, int width, int channels,
+                     yb_stream_t stream) {
+  return yb::reorg_bwd(dy, ld_dy, dy_off, dx, batch, height, width, channels, S(stream));
+}
+
+int yb_head_grad_prepare(const float* dfeature, void* dz_nhwc_f16, float* dbias, int batch, int channels, int channels_pad, int cells,
+                         yb_stream_t stream) {
+  return yb::head_grad_prepare(dfeature, dz_nhwc_f16, dbias, batch, channels, channels_pad, cells, S(stream));
+}
+
+int yb_conv0_wgrad(const float* x_nchw, const void* dz_nhwc_f16, float* dw_oihw, int batch, int height, int width, yb_stream_t stream) {
+  return yb::conv0_wgrad(x_nchw, dz_nhwc_f16, dw_oihw, batch, height, width, S(stream));
+}
+
+int yb_conv_wgrad(const void* x, const void* dz, float* dw_krsc, int batch, int height, int width, int cin, int cout, int ksize, int x_ld,
+                  int dz_ld, yb_stream_t stream) {
+  return yb::conv_wgrad_forward(x, dz, dw_krsc, batch, height, width, cin, cout, ksize, x_ld, dz_ld, S(stream));
+}
+
+int yb_unpack_wgrad(const float* dw_krsc, float* dw_oihw, int cout, int cin, int ksize, yb_stream_t stream) {
+  return yb::unpack_wgrad(dw_krsc, dw_oihw, cout, cin, ksize, S(stream));
 }
 
 }  // extern "C"

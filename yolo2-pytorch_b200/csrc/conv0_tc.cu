@@ -43,6 +43,7 @@ struct Conv0Params {
   __half* y;            // fp16 NHWC [B,H/2,W/2,32]
   int batch, height, width;
   int tiles_x, tiles_y, num_tiles;
+  int raw;              // 1: write the raw conv output, unpooled fp16 NHWC [B,H,W,32] (training forward)
   int* dbg;
 };
 
@@ -204,6 +205,17 @@ __global__ void __launch_bounds__(128, 4) conv0_tc_kernel(const Conv0Params p) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) tmem_ld_32x32b_x8(lane_addr + j * kC0Out + g * 8, v[j]);
       tmem_ld_wait();
+      if (p.raw) {
+        // training mode: the raw (pre-BatchNorm) conv output of the 4 pixels of this window, unpooled
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int yy = ty * kT0Rows + 2 * wy + (j >> 1), xx = tx * kT0Cols + 2 * wx + (j & 1);
+          *reinterpret_cast<uint4*>(p.y + ((static_cast<long long>(img) * p.height + yy) * p.width + xx) * kC0Out + g * 8) =
+              make_uint4(pack_h2(__uint_as_float(v[j][0]), __uint_as_float(v[j][1])), pack_h2(__uint_as_float(v[j][2]), __uint_as_float(v[j][3])),
+                         pack_h2(__uint_as_float(v[j][4]), __uint_as_float(v[j][5])), pack_h2(__uint_as_float(v[j][6]), __uint_as_float(v[j][7])));
+        }
+        continue;
+      }
       float m[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
@@ -232,8 +244,8 @@ __global__ void __launch_bounds__(128, 4) conv0_tc_kernel(const Conv0Params p) {
 }
 
 int conv0_tc_forward(const void* x, int x_is_u8, const float* w, const float* scale, const float* shift, float slope, void* y, int batch,
-                     int height, int width, int cout, cudaStream_t stream) {
-  YB_REQUIRE(x && w && scale && shift && y, "conv0: null pointer");
+                     int height, int width, int cout, int raw, cudaStream_t stream) {
+  YB_REQUIRE(x && w && y && (raw || (scale && shift)), "conv0: null pointer");
   YB_REQUIRE(cout == kC0Out, "conv0: Cout=%d unsupported (32)", cout);
   YB_REQUIRE(batch > 0 && height > 0 && width > 0 && height % kT0Rows == 0 && width % kT0Cols == 0,
              "conv0: H must be a multiple of %d and W of %d (got %dx%d)", kT0Rows, kT0Cols, height, width);
@@ -244,6 +256,8 @@ int conv0_tc_forward(const void* x, int x_is_u8, const float* w, const float* sc
   const long long tiles = static_cast<long long>(p.tiles_x) * p.tiles_y * batch;
   YB_REQUIRE(tiles < (1ll << 31), "conv0: too many tiles");
   p.num_tiles = static_cast<int>(tiles);
+  p.raw = raw;
+  if (raw) { p.scale = w; p.shift = w; }   // unused in raw mode, must be readable
   p.dbg = debug_word_device();
   const int max_ctas = sm_count() * 4;
   const int grid = p.num_tiles < max_ctas ? p.num_tiles : max_ctas;

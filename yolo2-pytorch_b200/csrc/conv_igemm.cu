@@ -345,6 +345,8 @@ static int get_encoders(EncodeTiledFn* tiled, EncodeIm2colFn* im2col) {
   return 0;
 }
 
+int get_tensor_map_encoders(EncodeTiledFn* tiled, EncodeIm2colFn* im2col) { return get_encoders(tiled, im2col); }
+
 template <int BN, int BK, int MT, bool kPair>
 static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, cudaStream_t stream) {
   using Cfg = ConvCfg<BN, BK, MT, kPair>;

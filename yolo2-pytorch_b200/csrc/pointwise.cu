@@ -10,8 +10,8 @@
 namespace yb {
 
 // ------------------------------------------------------------------------------------------
-__global__ void pack_weight_kernel(const float* __restrict__ w, __half* __restrict__ out, int cout, int cin, int k, int mode) {
-  const long long total = static_cast<long long>(cout) * cin * k * k;
+__global__ void pack_weight_kernel(const float* __restrict__ w, __half* __restrict__ out, int cout, int cin, int k, int mode, int cout_pad) {
+  const long long total = static_cast<long long>(mode == 0 ? cout : cout_pad) * cin * k * k;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   if (mode == 0) {
@@ -24,19 +24,21 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __half* __restri
     out[idx] = __float2half_rn(w[((static_cast<long long>(co) * cin + ci) * k + r) * k + s]);
   } else {
     // data-gradient operand: out[ci][r][s][co] = w[co][ci][k-1-r][k-1-s]  (rotated, in/out swapped)
-    const int co = static_cast<int>(idx % cout);
-    long long t = idx / cout;
+    // (the reduction dimension Cout may be zero-padded to cout_pad so that it is a multiple of 32)
+    const int co = static_cast<int>(idx % cout_pad);
+    long long t = idx / cout_pad;
     const int s = static_cast<int>(t % k); t /= k;
     const int r = static_cast<int>(t % k);
     const int ci = static_cast<int>(t / k);
-    out[idx] = __float2half_rn(w[((static_cast<long long>(co) * cin + ci) * k + (k - 1 - r)) * k + (k - 1 - s)]);
+    out[idx] = co < cout ? __float2half_rn(w[((static_cast<long long>(co) * cin + ci) * k + (k - 1 - r)) * k + (k - 1 - s)]) : __float2half_rn(0.f);
   }
 }
 
-int pack_weight(const float* w, void* out, int cout, int cin, int k, int mode, cudaStream_t stream) {
+int pack_weight(const float* w, void* out, int cout, int cin, int k, int mode, int cout_pad, cudaStream_t stream) {
   YB_REQUIRE(w && out && cout > 0 && cin > 0 && (k == 1 || k == 3) && (mode == 0 || mode == 1), "pack_weight: bad argument");
-  const long long total = static_cast<long long>(cout) * cin * k * k;
-  pack_weight_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(w, reinterpret_cast<__half*>(out), cout, cin, k, mode);
+  if (cout_pad < cout) cout_pad = cout;
+  const long long total = static_cast<long long>(mode == 0 ? cout : cout_pad) * cin * k * k;
+  pack_weight_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(w, reinterpret_cast<__half*>(out), cout, cin, k, mode, cout_pad);
   return check_launch("pack_weight_kernel");
 }
 

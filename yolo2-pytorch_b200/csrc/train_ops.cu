@@ -1,0 +1,479 @@
+// Training-mode companions of the conv kernel (HBM-bound, 16-byte vectorised, fp16 NHWC activations):
+//   bn_stats / bn_finalize      batch statistics of the raw conv output z and running-stat update
+//                               (nn.BatchNorm2d(momentum=0.01) in train mode, model/yolo2.py:58)
+//   bn_act_apply                a = leaky(gamma * (z - mean) * invstd + beta) [+ fused MaxPool2d(2)]   (yolo2.py:58-59,79)
+//   bn_act_bwd_reduce / _apply  backward of leaky + BN (+ max-pool routing, + a second unpooled gradient for
+//                               the passthrough branch point): dgamma, dbeta and dz
+//   reorg_bwd, head_grad_prepare, conv0_wgrad, unpack_wgrad
+// Everything the reference gets from torch autograd over nn.BatchNorm2d / LeakyReLU / MaxPool2d / reorg / cat.
+#include "yb_common.h"
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace yb {
+
+constexpr int kTrainThreads = 256;
+
+__device__ __forceinline__ void h8_to_f(const uint4& v, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __half22float2(h[i]);
+    f[2 * i] = t.x; f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 f_to_h8(const float (&f)[8]) {
+  uint4 v;
+  __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// sums[0..C) += sum_rows z, sums[C..2C) += sum_rows z^2   (double accumulators, zero on entry)
+__global__ void __launch_bounds__(kTrainThreads) bn_stats_kernel(const __half* __restrict__ z, long long ld, long long rows, int channels,
+                                                                 double* __restrict__ sums) {
+  extern __shared__ float s_acc[];  // [2][channels]
+  for (int i = threadIdx.x; i < 2 * channels; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  const int c8 = channels >> 3;
+  const int cg = threadIdx.x % c8;
+  const int rpi = blockDim.x / c8;                 // rows per iteration
+  const int rib = threadIdx.x / c8;
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
+  if (rib < rpi) {
+    for (long long r = static_cast<long long>(blockIdx.x) * rpi + rib; r < rows; r += static_cast<long long>(gridDim.x) * rpi) {
+      float f[8];
+      h8_to_f(__ldg(reinterpret_cast<const uint4*>(z + r * ld + cg * 8)), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] += f[i] * f[i]; }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(&s_acc[cg * 8 + i], s[i]);
+      atomicAdd(&s_acc[channels + cg * 8 + i], q[i]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * channels; i += blockDim.x) atomicAdd(&sums[i], static_cast<double>(s_acc[i]));
+}
+
+// mean/invstd for this batch, running-stat update (unbiased variance, like torch), sums reset to 0
+__global__ void bn_finalize_kernel(double* __restrict__ sums, long long rows, int channels, float eps, float momentum,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ mean_out,
+                                   float* __restrict__ invstd_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= channels) return;
+  const double m = sums[c] / static_cast<double>(rows);
+  double var = sums[channels + c] / static_cast<double>(rows) - m * m;
+  if (var < 0.0) var = 0.0;
+  mean_out[c] = static_cast<float>(m);
+  invstd_out[c] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  if (running_mean != nullptr) {
+    const double unbiased = rows > 1 ? var * static_cast<double>(rows) / static_cast<double>(rows - 1) : var;
+    running_mean[c] = static_cast<float>((1.0 - momentum) * running_mean[c] + momentum * m);
+    running_var[c] = static_cast<float>((1.0 - momentum) * running_var[c] + momentum * unbiased);
+  }
+  sums[c] = 0.0;
+  sums[channels + c] = 0.0;
+}
+
+struct BnParams {
+  const float* mean;
+  const float* invstd;
+  const float* gamma;
+  const float* beta;
+  float slope;
+  int channels;
+};
+
+__device__ __forceinline__ void load_affine(const BnParams& bn, float* s_scale, float* s_shift) {
+  for (int c = threadIdx.x; c < bn.channels; c += blockDim.x) {
+    const float sc = bn.gamma[c] * bn.invstd[c];
+    s_scale[c] = sc;
+    s_shift[c] = bn.beta[c] - bn.mean[c] * sc;
+  }
+  __syncthreads();
+}
+
+// a = leaky(scale * z + shift); pool = 1 additionally takes the 2x2 max (thread = 8 channels of one OUTPUT pixel)
+__global__ void __launch_bounds__(kTrainThreads) bn_act_apply_kernel(const __half* __restrict__ z, long long ld_z, BnParams bn,
+                                                                     __half* __restrict__ a, long long ld_a, int a_ch_off, int batch, int height,
+                                                                     int width, int pool) {
+  extern __shared__ float s_aff[];
+  float* s_scale = s_aff;
+  float* s_shift = s_aff + bn.channels;
+  load_affine(bn, s_scale, s_shift);
+  const int c8 = bn.channels >> 3;
+  const int oh = pool ? height >> 1 : height, ow = pool ? width >> 1 : width;
+  const long long total = static_cast<long long>(batch) * oh * ow * c8;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(idx % c8);
+    long long t = idx / c8;
+    const int px = static_cast<int>(t % ow); t /= ow;
+    const int py = static_cast<int>(t % oh);
+    const int img = static_cast<int>(t / oh);
+    float best[8];
+    const int nwin = pool ? 4 : 1;
+    for (int k = 0; k < nwin; ++k) {
+      const int iy = pool ? 2 * py + (k >> 1) : py, ix = pool ? 2 * px + (k & 1) : px;
+      float f[8];
+      h8_to_f(__ldg(reinterpret_cast<const uint4*>(z + ((static_cast<long long>(img) * height + iy) * width + ix) * ld_z + cg * 8)), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float y = f[i] * s_scale[cg * 8 + i] + s_shift[cg * 8 + i];
+        y = y > 0.f ? y : y * bn.slope;
+        best[i] = (k == 0) ? y : fmaxf(best[i], y);
+      }
+    }
+    *reinterpret_cast<uint4*>(a + ((static_cast<long long>(img) * oh + py) * ow + px) * ld_a + a_ch_off + cg * 8) = f_to_h8(best);
+  }
+}
+
+// Gradient arriving at the activated output of one unit: optional unpooled part (da) plus optional part that
+// arrives through the unit's 2x2 max-pool (dap, routed to the window's first maximum as torch does).
+struct GradIn {
+  const __half* da;   long long ld_da;  int da_off;     // [B,H,W,*]
+  const __half* dap;  long long ld_dap; int dap_off;    // [B,H/2,W/2,*]
+};
+
+// One thread handles 8 channels of one 2x2 window (pool / branch layers) or of one pixel (window = 0).
+// mode 0: accumulate sum(dy), sum(dy * xhat) ; mode 1: write dz.
+template <int kMode, int kWin>
+__global__ void __launch_bounds__(kTrainThreads) bn_act_bwd_kernel(const __half* __restrict__ z, long long ld_z, BnParams bn, GradIn g, int batch,
+                                                                   int height, int width, double* __restrict__ sums,
+                                                                   __half* __restrict__ dz, long long ld_dz, int has_bn) {
+  constexpr int window = kWin;
+  constexpr int nwin = kWin ? 4 : 1;
+  extern __shared__ float s_buf[];
+  float* s_scale = s_buf;                         // gamma * invstd        (has_bn) else 1
+  float* s_shift = s_buf + bn.channels;           // beta - mean * scale   (has_bn) else 0
+  float* s_m1 = s_buf + 2 * bn.channels;          // mode 1: sum(dy) / M
+  float* s_m2 = s_buf + 3 * bn.channels;          // mode 1: sum(dy xhat) / M
+  float* s_acc = s_buf + 2 * bn.channels;         // mode 0: [2][C] block accumulators
+  const long long rows = static_cast<long long>(batch) * height * width;
+  if (has_bn) {
+    load_affine(bn, s_scale, s_shift);
+  } else {
+    for (int c = threadIdx.x; c < bn.channels; c += blockDim.x) { s_scale[c] = 1.f; s_shift[c] = 0.f; }
+    __syncthreads();
+  }
+  if (kMode == 0) {
+    for (int i = threadIdx.x; i < 2 * bn.channels; i += blockDim.x) s_acc[i] = 0.f;
+  } else {
+    for (int c = threadIdx.x; c < bn.channels; c += blockDim.x) {
+      s_m1[c] = has_bn ? static_cast<float>(sums[c] / static_cast<double>(rows)) : 0.f;
+      s_m2[c] = has_bn ? static_cast<float>(sums[bn.channels + c] / static_cast<double>(rows)) : 0.f;
+    }
+  }
+  __syncthreads();
+  const int c8 = bn.channels >> 3;
+  const int oh = window ? height >> 1 : height, ow = window ? width >> 1 : width;
+  const long long total = static_cast<long long>(batch) * oh * ow * c8;
+  float acc1[8], acc2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { acc1[i] = 0.f; acc2[i] = 0.f; }
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(idx % c8);
+    long long t = idx / c8;
+    const int px = static_cast<int>(t % ow); t /= ow;
+    const int py = static_cast<int>(t % oh);
+    const int img = static_cast<int>(t / oh);
+    float zf[nwin][8], yv[nwin][8], besty[8];
+    int arg[8];
+#pragma unroll
+    for (int k = 0; k < nwin; ++k) {
+      const int iy = window ? 2 * py + (k >> 1) : py, ix = window ? 2 * px + (k & 1) : px;
+      h8_to_f(__ldg(reinterpret_cast<const uint4*>(z + ((static_cast<long long>(img) * height + iy) * width + ix) * ld_z + cg * 8)), zf[k]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        yv[k][i] = zf[k][i] * s_scale[cg * 8 + i] + s_shift[cg * 8 + i];
+        if (k == 0 || yv[k][i] > besty[i]) { besty[i] = yv[k][i]; arg[i] = k; }   // first maximum wins (leaky is strictly increasing)
+      }
+    }
+    float gp[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) gp[i] = 0.f;
+    if (g.dap != nullptr) h8_to_f(__ldg(reinterpret_cast<const uint4*>(g.dap + ((static_cast<long long>(img) * oh + py) * ow + px) * g.ld_dap + g.dap_off + cg * 8)), gp);
+#pragma unroll
+    for (int k = 0; k < nwin; ++k) {
+      const int iy = window ? 2 * py + (k >> 1) : py, ix = window ? 2 * px + (k & 1) : px;
+      const long long pix = (static_cast<long long>(img) * height + iy) * width + ix;
+      float gd[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) gd[i] = 0.f;
+      if (g.da != nullptr) h8_to_f(__ldg(reinterpret_cast<const uint4*>(g.da + pix * g.ld_da + g.da_off + cg * 8)), gd);
+      float out[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float gin = gd[i];
+        if (g.dap != nullptr && (!window || arg[i] == k)) gin += gp[i];
+        const float dy = gin * (yv[k][i] > 0.f ? 1.f : bn.slope);
+        if (has_bn) {
+          const float xhat = (zf[k][i] - bn.mean[cg * 8 + i]) * bn.invstd[cg * 8 + i];
+          if (kMode == 0) { acc1[i] += dy; acc2[i] += dy * xhat; }
+          else out[i] = s_scale[cg * 8 + i] * (dy - s_m1[cg * 8 + i] - xhat * s_m2[cg * 8 + i]);
+        } else {
+          if (kMode == 0) acc1[i] += dy;           // bias gradient
+          else out[i] = dy;
+        }
+      }
+      if (kMode == 1) *reinterpret_cast<uint4*>(dz + pix * ld_dz + cg * 8) = f_to_h8(out);
+    }
+  }
+  if (kMode == 0) {
+    const int cg = threadIdx.x % c8;    // blockDim is a multiple of c8 and the grid stride keeps cg fixed per thread
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(&s_acc[cg * 8 + i], acc1[i]);
+      atomicAdd(&s_acc[bn.channels + cg * 8 + i], acc2[i]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * bn.channels; i += blockDim.x) atomicAdd(&sums[i], static_cast<double>(s_acc[i]));
+  }
+}
+
+// dgamma = sum(dy xhat), dbeta = sum(dy)  (fp32 parameter gradients) ; optionally reset the accumulators
+__global__ void bn_param_grad_kernel(double* __restrict__ sums, int channels, float* __restrict__ dgamma, float* __restrict__ dbeta, int reset) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= channels) return;
+  if (dbeta) dbeta[c] = static_cast<float>(sums[c]);
+  if (dgamma) dgamma[c] = static_cast<float>(sums[channels + c]);
+  if (reset) { sums[c] = 0.0; sums[channels + c] = 0.0; }
+}
+
+static int grid_for(long long work_items) {
+  long long blocks = (work_items + kTrainThreads - 1) / kTrainThreads;
+  const long long cap = static_cast<long long>(sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+// keep cg = threadIdx % c8 constant along the grid stride: total stride must be a multiple of c8
+static int grid_for_groups(long long work_items, int c8) {
+  int g = grid_for(work_items);
+  (void)c8;  // blockDim (256) is a multiple of every supported c8 (4..128), so any grid size works
+  return g;
+}
+
+int bn_stats(const void* z, long long ld, long long rows, int channels, double* sums, cudaStream_t stream) {
+  YB_REQUIRE(z && sums && rows > 0 && channels >= 32 && channels % 8 == 0 && channels <= 2048 && kTrainThreads % (channels / 8) == 0 && ld % 8 == 0,
+             "bn_stats: unsupported shape (C=%d)", channels);
+  const int rpi = kTrainThreads / (channels / 8);
+  long long blocks = (rows + rpi - 1) / rpi;
+  const long long cap = static_cast<long long>(sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
+  bn_stats_kernel<<<static_cast<int>(blocks), kTrainThreads, 2 * channels * sizeof(float), stream>>>(reinterpret_cast<const __half*>(z), ld, rows,
+                                                                                                  channels, sums);
+  return check_launch("bn_stats_kernel");
+}
+
+int bn_finalize(double* sums, long long rows, int channels, float eps, float momentum, float* running_mean, float* running_var, float* mean,
+                float* invstd, cudaStream_t stream) {
+  YB_REQUIRE(sums && mean && invstd && rows > 0 && channels > 0, "bn_finalize: bad argument");
+  bn_finalize_kernel<<<(channels + 127) / 128, 128, 0, stream>>>(sums, rows, channels, eps, momentum, running_mean, running_var, mean, invstd);
+  return check_launch("bn_finalize_kernel");
+}
+
+int bn_act_apply(const void* z, long long ld_z, const float* mean, const float* invstd, const float* gamma, const float* beta, float slope,
+                 void* a, long long ld_a, int a_ch_off, int batch, int height, int width, int channels, int pool, cudaStream_t stream) {
+  YB_REQUIRE(z && mean && invstd && gamma && beta && a && channels % 8 == 0 && channels <= 2048 && ld_z % 8 == 0 && ld_a % 8 == 0 && a_ch_off % 8 == 0,
+             "bn_act_apply: bad argument");
+  YB_REQUIRE(!pool || (height % 2 == 0 && width % 2 == 0), "bn_act_apply: pooling needs even H, W");
+  BnParams bn{mean, invstd, gamma, beta, slope, channels};
+  const long long total = static_cast<long long>(batch) * (pool ? height / 2 : height) * (pool ? width / 2 : width) * (channels / 8);
+  bn_act_apply_kernel<<<grid_for(total), kTrainThreads, 2 * channels * sizeof(float), stream>>>(
+      reinterpret_cast<const __half*>(z), ld_z, bn, reinterpret_cast<__half*>(a), ld_a, a_ch_off, batch, height, width, pool);
+  return check_launch("bn_act_apply_kernel");
+}
+
+// mode 0: reduce into sums ; mode 1: write dz.  has_bn = 0: plain leaky/bias unit (mean..beta may be null).
+int bn_act_bwd(int mode, const void* z, long long ld_z, const float* mean, const float* invstd, const float* gamma, const float* beta,
+               float slope, const void* da, long long ld_da, int da_off, const void* dap, long long ld_dap, int dap_off, int batch, int height,
+               int width, int channels, int window, double* sums, void* dz, long long ld_dz, int has_bn, cudaStream_t stream) {
+  YB_REQUIRE(z && sums && (da || dap) && channels % 8 == 0 && channels <= 1024 && kTrainThreads % (channels / 8) == 0, "bn_act_bwd: bad argument (C=%d)", channels);
+  YB_REQUIRE(!has_bn || (mean && invstd && gamma && beta), "bn_act_bwd: BN parameters missing");
+  YB_REQUIRE(mode == 0 || dz != nullptr, "bn_act_bwd: dz missing");
+  YB_REQUIRE(!window || (height % 2 == 0 && width % 2 == 0), "bn_act_bwd: window mode needs even H, W");
+  YB_REQUIRE(dap == nullptr || window, "bn_act_bwd: a pooled gradient needs window mode");
+  BnParams bn{mean, invstd, gamma, beta, slope, channels};
+  GradIn g{reinterpret_cast<const __half*>(da), ld_da, da_off, reinterpret_cast<const __half*>(dap), ld_dap, dap_off};
+  const long long total = static_cast<long long>(batch) * (window ? height / 2 : height) * (window ? width / 2 : width) * (channels / 8);
+  const int grid = grid_for_groups(total, channels / 8);
+  const size_t smem = 4 * channels * sizeof(float);
+  const __half* zp = reinterpret_cast<const __half*>(z);
+  __half* dzp = reinterpret_cast<__half*>(dz);
+  if (mode == 0 && window) bn_act_bwd_kernel<0, 1><<<grid, kTrainThreads, smem, stream>>>(zp, ld_z, bn, g, batch, height, width, sums, nullptr, 0, has_bn);
+  else if (mode == 0) bn_act_bwd_kernel<0, 0><<<grid, kTrainThreads, smem, stream>>>(zp, ld_z, bn, g, batch, height, width, sums, nullptr, 0, has_bn);
+  else if (window) bn_act_bwd_kernel<1, 1><<<grid, kTrainThreads, smem, stream>>>(zp, ld_z, bn, g, batch, height, width, sums, dzp, ld_dz, has_bn);
+  else bn_act_bwd_kernel<1, 0><<<grid, kTrainThreads, smem, stream>>>(zp, ld_z, bn, g, batch, height, width, sums, dzp, ld_dz, has_bn);
+  return check_launch("bn_act_bwd_kernel");
+}
+
+int bn_param_grad(double* sums, int channels, float* dgamma, float* dbeta, int reset, cudaStream_t stream) {
+  YB_REQUIRE(sums && channels > 0, "bn_param_grad: bad argument");
+  bn_param_grad_kernel<<<(channels + 127) / 128, 128, 0, stream>>>(sums, channels, dgamma, dbeta, reset);
+  return check_launch("bn_param_grad_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
+// reorg backward: d_in[b, 2h'+sh, 2w'+sw, c] = d_out[b, h', w', off + (sh*2+sw)*C + c]
+__global__ void reorg_bwd_kernel(const __half* __restrict__ dy, long long ld_dy, int dy_off, __half* __restrict__ dx, int batch, int height, int width,
+                                 int channels) {
+  const int c8 = channels >> 3;
+  const int oh = height >> 1, ow = width >> 1;
+  const long long total = static_cast<long long>(batch) * oh * ow * 4 * c8;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cg = static_cast<int>(idx % c8);
+  long long t = idx / c8;
+  const int off = static_cast<int>(t % 4); t /= 4;
+  const int px = static_cast<int>(t % ow); t /= ow;
+  const int py = static_cast<int>(t % oh);
+  const int img = static_cast<int>(t / oh);
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(dy + ((static_cast<long long>(img) * oh + py) * ow + px) * ld_dy + dy_off + off * channels + cg * 8));
+  *reinterpret_cast<uint4*>(dx + ((static_cast<long long>(img) * height + 2 * py + (off >> 1)) * width + 2 * px + (off & 1)) * channels + cg * 8) = v;
+}
+
+int reorg_bwd(const void* dy, long long ld_dy, int dy_off, void* dx, int batch, int height, int width, int channels, cudaStream_t stream) {
+  YB_REQUIRE(dy && dx && batch > 0 && height % 2 == 0 && width % 2 == 0 && channels % 8 == 0 && ld_dy % 8 == 0 && dy_off % 8 == 0, "reorg_bwd: bad argument");
+  const long long total = static_cast<long long>(batch) * (height / 2) * (width / 2) * 4 * (channels / 8);
+  reorg_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const __half*>(dy), ld_dy, dy_off,
+                                                                                   reinterpret_cast<__half*>(dx), batch, height, width, channels);
+  return check_launch("reorg_bwd_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Head gradient: dfeature fp32 NCHW [B,C,S,S] -> fp16 NHWC [B,S,S,Cpad] (zero padded) and bias gradient db[C]
+__global__ void head_grad_kernel(const float* __restrict__ df, __half* __restrict__ dz, float* __restrict__ dbias, int batch, int channels, int cpad,
+                                 int cells) {
+  // block = one channel; threads stride over (b, cell)
+  const int c = blockIdx.x;
+  float acc = 0.f;
+  const long long n = static_cast<long long>(batch) * cells;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const long long b = i / cells, cell = i - b * cells;
+    float v = 0.f;
+    if (c < channels) { v = df[(b * channels + c) * cells + cell]; acc += v; }
+    dz[i * cpad + c] = __float2half_rn(v);
+  }
+  __shared__ float red[32];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0 && c < channels && dbias != nullptr) {
+    float t = 0.f;
+    for (int w = 0; w < (blockDim.x + 31) / 32; ++w) t += red[w];
+    dbias[c] = t;
+  }
+}
+
+int head_grad_prepare(const float* dfeature, void* dz, float* dbias, int batch, int channels, int cpad, int cells, cudaStream_t stream) {
+  YB_REQUIRE(dfeature && dz && batch > 0 && channels > 0 && cpad >= channels && cpad % 8 == 0, "head_grad_prepare: bad argument");
+  head_grad_kernel<<<cpad, 256, 0, stream>>>(dfeature, reinterpret_cast<__half*>(dz), dbias, batch, channels, cpad, cells);
+  return check_launch("head_grad_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv0 weight gradient: dW[co][ci][r][s] = sum_{b,y,x} dz[b,y,x,co] * x[b,ci,y+r-1,x+s-1]   (Cout = 32, Cin = 3)
+// Persistent blocks over 8x32-pixel tiles; the haloed input patch and the dz tile are staged in shared memory;
+// lane k (< 27) of every warp owns filter tap k for all 32 output channels (32 fp32 accumulators).
+constexpr int kW0Rows = 8, kW0Cols = 32;
+
+__global__ void __launch_bounds__(256) conv0_wgrad_kernel(const float* __restrict__ x, const __half* __restrict__ dz, float* __restrict__ dw, int batch,
+                                                          int height, int width, int tiles_x, int tiles_y, int num_tiles) {
+  __shared__ float patch[3][kW0Rows + 2][kW0Cols + 2];
+  __shared__ __align__(16) __half dzs[kW0Rows * kW0Cols][32];
+  __shared__ float s_dw[27 * 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 27 * 32; i += 256) s_dw[i] = 0.f;
+  float acc[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+  const int kc = lane / 9, kr = (lane % 9) / 3, ks = lane % 3;   // tap of this lane (lane < 27)
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int tx = tile % tiles_x;
+    const int t2 = tile / tiles_x;
+    const int ty = t2 % tiles_y;
+    const int img = t2 / tiles_y;
+    const int y0 = ty * kW0Rows, x0 = tx * kW0Cols;
+    __syncthreads();
+    for (int i = tid; i < 3 * (kW0Rows + 2) * (kW0Cols + 2); i += 256) {
+      const int c = i / ((kW0Rows + 2) * (kW0Cols + 2));
+      const int rem = i - c * ((kW0Rows + 2) * (kW0Cols + 2));
+      const int r = rem / (kW0Cols + 2), col = rem - r * (kW0Cols + 2);
+      const int iy = y0 - 1 + r, ix = x0 - 1 + col;
+      patch[c][r][col] = (iy >= 0 && iy < height && ix >= 0 && ix < width) ? __ldg(x + ((static_cast<long long>(img) * 3 + c) * height + iy) * width + ix) : 0.f;
+    }
+    for (int i = tid; i < kW0Rows * kW0Cols * 4; i += 256) {        // 4 x 16 B per pixel
+      const int pix = i >> 2, part = i & 3;
+      const int py = pix / kW0Cols, pxx = pix % kW0Cols;
+      reinterpret_cast<uint4*>(&dzs[pix][0])[part] =
+          __ldg(reinterpret_cast<const uint4*>(dz + ((static_cast<long long>(img) * height + y0 + py) * width + x0 + pxx) * 32) + part);
+    }
+    __syncthreads();
+    if (lane < 27) {
+      // warp w handles image row w of the tile
+      for (int pxx = 0; pxx < kW0Cols; ++pxx) {
+        const float xv = patch[kc][warp + kr][pxx + ks];
+        const uint4* dp = reinterpret_cast<const uint4*>(&dzs[warp * kW0Cols + pxx][0]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float f[8];
+          h8_to_f(dp[q], f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[q * 8 + i] = fmaf(xv, f[i], acc[q * 8 + i]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (lane < 27) {
+#pragma unroll
+    for (int co = 0; co < 32; ++co) atomicAdd(&s_dw[lane * 32 + co], acc[co]);
+  }
+  __syncthreads();
+  for (int i = tid; i < 27 * 32; i += 256) {
+    const int k = i / 32, co = i % 32;                 // k = ci*9 + r*3 + s  -> OIHW flat index co*27 + k
+    atomicAdd(&dw[co * 27 + k], s_dw[i]);
+  }
+}
+
+int conv0_wgrad(const float* x, const void* dz, float* dw, int batch, int height, int width, cudaStream_t stream) {
+  YB_REQUIRE(x && dz && dw && batch > 0 && height % kW0Rows == 0 && width % kW0Cols == 0, "conv0_wgrad: H %% 8 == 0 and W %% 32 == 0 required");
+  YB_CUDA(cudaMemsetAsync(dw, 0, 27 * 32 * sizeof(float), stream));
+  const int tiles_x = width / kW0Cols, tiles_y = height / kW0Rows;
+  const long long tiles = static_cast<long long>(tiles_x) * tiles_y * batch;
+  const int cap = sm_count() * 4;
+  const int grid = tiles < cap ? static_cast<int>(tiles) : cap;
+  conv0_wgrad_kernel<<<grid, 256, 0, stream>>>(x, reinterpret_cast<const __half*>(dz), dw, batch, height, width, tiles_x, tiles_y,
+                                               static_cast<int>(tiles));
+  return check_launch("conv0_wgrad_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 [Cout][k][k][Cin] (the wgrad kernel's accumulation layout) -> fp32 OIHW parameter gradient
+__global__ void unpack_wgrad_kernel(const float* __restrict__ g, float* __restrict__ out, int cout, int cin, int k) {
+  const long long total = static_cast<long long>(cout) * cin * k * k;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int s = static_cast<int>(idx % k);
+  long long t = idx / k;
+  const int r = static_cast<int>(t % k); t /= k;
+  const int ci = static_cast<int>(t % cin);
+  const int co = static_cast<int>(t / cin);
+  out[idx] = g[((static_cast<long long>(co) * k + r) * k + s) * cin + ci];
+}
+
+int unpack_wgrad(const float* g_krsc, float* out_oihw, int cout, int cin, int k, cudaStream_t stream) {
+  YB_REQUIRE(g_krsc && out_oihw && cout > 0 && cin > 0 && k > 0, "unpack_wgrad: bad argument");
+  const long long total = static_cast<long long>(cout) * cin * k * k;
+  unpack_wgrad_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(g_krsc, out_oihw, cout, cin, k);
+  return check_launch("unpack_wgrad_kernel");
+}
+
+}  // namespace yb

@@ -12,14 +12,13 @@ The modules here only HOLD parameters (so `.cuda()`, `.state_dict()`, `load_stat
 pass is the kernel chain in b200.engine (tcgen05 implicit-GEMM convs with fused BN + leaky-ReLU,
 fp16 NHWC activations, in-place concat).  There is no CPU fallback.
 """
-import math
-
 import torch
 import torch.nn as nn
 
 import model
 from b200 import engine as _engine
 from b200 import ops as _ops
+from b200 import train_engine as _train
 
 settings = {
     'size': (416, 416),
@@ -81,6 +80,28 @@ class Conv2d(nn.Module):
         return y
 
 
+class _DarknetTrainFunction(torch.autograd.Function):
+    """Training-mode forward/backward of the whole backbone as one autograd node: forward runs the
+    train-mode kernel chain (batch-statistics BatchNorm, running-stat update), backward the explicit
+    backward chain (b200.train_engine) and hands every parameter its fp32 gradient."""
+
+    @staticmethod
+    def forward(ctx, dnn, x, *params):
+        feature, saved = dnn.trainer.forward(x)
+        ctx.dnn, ctx.saved = dnn, saved
+        return feature
+
+    @staticmethod
+    def backward(ctx, dfeature):
+        grads = ctx.dnn.trainer.backward(ctx.saved, dfeature)
+        ctx.saved = None
+        out = []
+        for name, p in ctx.dnn.named_parameters():
+            g = grads.get(name)
+            out.append(g.view_as(p) if g is not None else None)
+        return (None, None) + tuple(out)
+
+
 class Darknet(nn.Module):
     def __init__(self, config_channels, anchors, num_cls, stride=2, ratio=1):
         nn.Module.__init__(self)
@@ -133,6 +154,7 @@ class Darknet(nn.Module):
 
         self.init()
         self._engine = None
+        self._trainer = None
 
     def init(self):
         """kaiming-normal conv weights, BN gamma = 1, beta = 0 (reference model/yolo2.py:117-123)."""
@@ -149,9 +171,16 @@ class Darknet(nn.Module):
             self._engine = _engine.DarknetEngine(self)
         return self._engine
 
+    @property
+    def trainer(self):
+        if self._trainer is None:
+            self._trainer = _train.DarknetTrainer(self.engine)
+        return self._trainer
+
     def forward(self, x):
         if self.training:
-            raise NotImplementedError('Darknet (B200): training-mode forward/backward is the next SURVEY 8 row; call .eval()')
+            # batch-statistics BatchNorm + autograd through the explicit backward chain
+            return _DarknetTrainFunction.apply(self, x, *[p for _, p in self.named_parameters()])
         return self.engine.forward(x).clone()
 
     def scope(self, name):
