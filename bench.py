@@ -376,6 +376,93 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def synth_targets(batch, height, width, slots, generator):
+    import torch
+    yx_min = torch.zeros(batch, slots, 2)
+    yx_max = torch.zeros(batch, slots, 2)
+    cls = torch.zeros(batch, slots, dtype=torch.long)
+    for b in range(batch):
+        n = int(torch.randint(1, slots + 1, (1,), generator=generator))
+        hw = torch.rand(n, 2, generator=generator) * torch.tensor([height / 2 - 16.0, width / 2 - 16.0]) + 16.0
+        lo, hi = hw / 2, torch.tensor([float(height), float(width)]) - hw / 2
+        c = lo + torch.rand(n, 2, generator=generator) * (hi - lo)
+        yx_min[b, :n], yx_max[b, :n] = c - hw / 2, c + hw / 2
+        cls[b, :n] = torch.randint(0, 20, (n,), generator=generator)
+    return yx_min, yx_max, cls
+
+
+def run_train(args):
+    """Secondary measurement (BASELINE configs[2]/[3]): 416x416 training step -- train-mode forward, region loss,
+    full backward, NCCL gradient all-reduce when N > 1, Adam step -- images/sec."""
+    import torch
+    import torch.distributed as dist
+    import train as yb_train
+    from b200 import ddp, ops
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=device)
+    config, dnn, inference = build_model(device)
+    config.read_dict({'hparam': {'foreground': '5', 'background': '1', 'center': '1', 'size': '1', 'cls': '1'},
+                      'train': {'cross_entropy': '1'}})
+    dnn.train(); inference.train()
+    anchors = torch.tensor(ANCHORS_HW, dtype=torch.float32)
+    optimizer = torch.optim.Adam(dnn.parameters(), 1e-5, betas=(0.9, 0.999), eps=1e-8)
+    B, H, W = args.batch, args.size, args.size
+    g = torch.Generator().manual_seed(200 + rank)
+    batches = []
+    for _ in range(2):
+        yx_min, yx_max, cls = synth_targets(B, H, W, 16, g)
+        batches.append(dict(tensor=torch.rand(B, 3, H, W, generator=g).to(device), yx_min=yx_min.to(device), yx_max=yx_max.to(device),
+                            cls=cls.to(device)))
+    reducer = ddp.GradientAllReducer() if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        yb_train.iterate(inference, optimizer, anchors, config, batches[i % 2], reducer)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = ops.launch_count
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for i in range(args.steps):
+        out = yb_train.iterate(inference, optimizer, anchors, config, batches[i % 2], reducer)
+    end.record()
+    torch.cuda.synchronize()
+    ms = start.elapsed_time(end)
+    launches = ops.launch_count - launches0
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if rank == 0:
+        value = world * B * args.steps / (ms / 1e3)
+        peaks = measured_peaks()
+        gflop_train = 3 * GFLOP_PER_IMAGE_416 - GFLOP_LAYER0_416          # SURVEY 8d: 87.78 GFLOP / image
+        line = dict(metric='416x416 training images/sec', value=value, unit='images/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f16', data='synthetic',
+                    config=dict(workload='Darknet-19 416x416 batch-%d training step: train-mode fwd + region loss + bwd%s + Adam (BASELINE configs[2])'
+                                % (B, ' + NCCL gradient all-reduce' if world > 1 else ''), global_batch=B * world, per_gpu_batch=B,
+                                parallelism='dp%d' % world, l2='0.6+ GB of activations per step (> L2)'),
+                    clocks=clocks, gpu_launches=launches, loss_total=float(out['loss_total'].item()),
+                    roofline=dict(bound='tensor', achieved=value * gflop_train / 1e3, peak=peaks['tflops'], unit='TFLOP/s',
+                                  frac=value * gflop_train / 1e3 / peaks['tflops'], traffic=None, kernel='whole training step',
+                                  peak_source=peaks['source']),
+                    allreduce_bytes_per_step=(reducer.bytes_reduced // max(1, args.steps + args.warmup)) if reducer else 0)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -385,12 +472,18 @@ def main():
     ap.add_argument('--batch', type=int, default=32)
     ap.add_argument('--size', type=int, default=416)
     ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--mode', default='infer', choices=['infer', 'train'], help='train: secondary measurement of the training step')
     ap.add_argument('--lanes', type=int, default=2, help='batches in flight per GPU (one CUDA stream + activation plan each)')
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
         args.warmup = max(args.warmup, 1)
         run_reference(args)
+    elif args.mode == 'train':
+        args.warmup = max(args.warmup, 3)
+        if args.batch == 32:
+            args.batch = 64
+        run_train(args)
     else:
         args.warmup = max(args.warmup, 3)
         run_b200(args)

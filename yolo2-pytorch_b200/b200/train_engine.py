@@ -30,8 +30,13 @@ class DarknetTrainer(object):
         self.grad_scale = float(grad_scale)
         self.sums = {}       # per-unit double[2C] accumulators (self-cleaning)
         self.wd_cache = {}   # dgrad weights per unit, keyed by parameter version
+        self.on_grad = None  # optional callback(name, grad) fired as soon as a parameter gradient is enqueued (DDP overlap)
 
     # ---- helpers -------------------------------------------------------------------------------------
+    def _emit(self, name, grads):
+        if self.on_grad is not None:
+            self.on_grad(name, grads[name])
+
     def _sums(self, key, channels, device):
         t = self.sums.get(key)
         if t is None or t.numel() != 2 * channels or t.device != device:
@@ -166,6 +171,7 @@ class DarknetTrainer(object):
         dw = torch.empty(cout, cin, k, k, dtype=torch.float32, device=dz.device)
         ops.call('yb_unpack_wgrad', dw_krsc, dw, cout, cin, k)
         grads[name + '.conv.weight'] = dw.mul_(1.0 / self.grad_scale)
+        self._emit(name + '.conv.weight', grads)
 
     def _unit_backward(self, key, s, b, grads, da=None, da_off=0, dap=None, dap_off=0, need_dgrad=True):
         """Backward of one BN unit; returns the gradient w.r.t. the unit's input activation (or None)."""
@@ -186,6 +192,8 @@ class DarknetTrainer(object):
         sums.zero_()
         grads[key + '.bn.weight'] = dgamma.mul_(1.0 / self.grad_scale)
         grads[key + '.bn.bias'] = dbeta.mul_(1.0 / self.grad_scale)
+        self._emit(key + '.bn.weight', grads)
+        self._emit(key + '.bn.bias', grads)
         if s.ain is None:
             return dz
         self._wgrad(u, s.ain, dz, b, s.h, s.w, grads, key)
@@ -210,6 +218,7 @@ class DarknetTrainer(object):
         scaled = (dfeature.contiguous().float() * self.grad_scale)
         ops.call('yb_head_grad_prepare', scaled, dzh, dbias, b, chead, cpad, h32 * w32)
         grads['layers3.1.conv.bias'] = dbias.mul_(1.0 / self.grad_scale)
+        self._emit('layers3.1.conv.bias', grads)
         self._wgrad(u31, saved.a30, dzh, b, h32, w32, grads, 'layers3.1', cout=chead)
         one, zero = self._ones(u31.cin, dev)
         da = ops.conv_bn_act(dzh, self._wd('layers3.1', u31, cpad), one, zero, 1.0)
@@ -241,4 +250,5 @@ class DarknetTrainer(object):
         dw0 = torch.empty_like(eng.units1[0].conv.weight, dtype=torch.float32)
         ops.call('yb_conv0_wgrad', saved.x, dz0, dw0, b, saved.h, saved.w)
         grads['layers1.0.conv.weight'] = dw0.mul_(1.0 / self.grad_scale)
+        self._emit('layers1.0.conv.weight', grads)
         return grads
