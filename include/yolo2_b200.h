@@ -168,6 +168,14 @@ int yb_conv_wgrad(const void* x, const void* dz, float* dw_krsc, int batch, int 
                   int dz_ld, yb_stream_t stream);
 int yb_unpack_wgrad(const float* dw_krsc, float* dw_oihw, int cout, int cin, int ksize, yb_stream_t stream);
 
+/* ---- MobileNet plugin (model/mobilenet.py:25-85), inference ------------------------------------------------- */
+/* conv_bn(3,32,stride 2) + BN + ReLU: x fp32 NCHW [B,3,H,W] -> y fp16 NHWC [B,H/2,W/2,32] (model/mobilenet.py:25-30). */
+int yb_mb_conv0_bn_relu_fwd(const float* x_nchw, const float* w_oihw, const float* scale, const float* shift, void* y_nhwc_f16, int batch,
+                            int height, int width, yb_stream_t stream);
+/* conv_dw: depthwise 3x3 (stride 1 or 2, pad 1) + BN + ReLU on fp16 NHWC; w fp32 [C][9] (model/mobilenet.py:33-38). */
+int yb_dwconv3x3_bn_relu_fwd(const void* x, const float* w_c9, const float* scale, const float* shift, void* y, int batch, int height,
+                             int width, int channels, int stride, yb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

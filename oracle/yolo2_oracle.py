@@ -455,3 +455,53 @@ def synth_boxes(n, seed=3, extent=13.0):
     s = torch.rand(n, 2, generator=g) * (extent / 3) + 0.2
     score = (torch.randperm(n, generator=g).float() + 0.5) / n
     return score, c - s / 2, c + s / 2
+
+
+# ----------------------------------------------------------------------------------------------
+# MobileNet backbone (model/mobilenet.py:25-85), eval mode -- BASELINE configs[4]
+# ----------------------------------------------------------------------------------------------
+MOBILENET_UNITS = [(64, 1), (128, 2), (128, 1), (256, 2), (256, 1), (512, 2), (512, 1), (512, 1), (512, 1), (512, 1), (512, 1), (1024, 2), (1024, 1)]
+
+
+def make_mobilenet_state_dict(seed=0, num_anchors=5, num_cls=20):
+    """Deterministic synthetic MobileNet state_dict with the reference's key names (model/mobilenet.py:59-75)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def bn(prefix, c):
+        sd[prefix + '.weight'] = torch.rand(c, generator=g) + 0.5
+        sd[prefix + '.bias'] = torch.randn(c, generator=g) * 0.1
+        sd[prefix + '.running_mean'] = torch.randn(c, generator=g) * 0.1
+        sd[prefix + '.running_var'] = torch.rand(c, generator=g) + 0.5
+
+    sd['layers.0.conv.weight'] = torch.randn(32, 3, 3, 3, generator=g) * math.sqrt(2.0 / 27)
+    bn('layers.0.bn', 32)
+    cin = 32
+    for i, (cout, _) in enumerate(MOBILENET_UNITS, 1):
+        sd['layers.%d.dw.conv.weight' % i] = torch.randn(cin, 1, 3, 3, generator=g) * math.sqrt(2.0 / 9)
+        bn('layers.%d.dw.bn' % i, cin)
+        sd['layers.%d.pw.conv.weight' % i] = torch.randn(cout, cin, 1, 1, generator=g) * math.sqrt(2.0 / cin)
+        bn('layers.%d.pw.bn' % i, cout)
+        cin = cout
+    ch = num_anchors * (5 + num_cls) if num_cls > 1 else num_anchors * 5
+    sd['layers.14.weight'] = torch.randn(ch, cin, 1, 1, generator=g) * math.sqrt(1.0 / cin)
+    sd['layers.14.bias'] = torch.randn(ch, generator=g) * 0.1
+    return sd
+
+
+def mobilenet_forward(sd, x, collect=None):
+    """model/mobilenet.py:84-85 in eval mode: conv_bn (:25-30) -> 13 x [conv_dw (:33-38), conv_pw (:41-46)] -> 1x1 head with bias."""
+    def bn_relu(y, prefix):
+        y = F.batch_norm(y, sd[prefix + '.running_mean'], sd[prefix + '.running_var'], sd[prefix + '.weight'], sd[prefix + '.bias'], False, 0.0, 1e-5)
+        return F.relu(y)
+
+    x = bn_relu(F.conv2d(x, sd['layers.0.conv.weight'], None, 2, 1), 'layers.0.bn')
+    if collect is not None:
+        collect['layers.0'] = x
+    for i, (_, stride) in enumerate(MOBILENET_UNITS, 1):
+        c = x.size(1)
+        x = bn_relu(F.conv2d(x, sd['layers.%d.dw.conv.weight' % i], None, stride, 1, groups=c), 'layers.%d.dw.bn' % i)
+        x = bn_relu(F.conv2d(x, sd['layers.%d.pw.conv.weight' % i]), 'layers.%d.pw.bn' % i)
+        if collect is not None:
+            collect['layers.%d' % i] = x
+    return F.conv2d(x, sd['layers.14.weight'], sd['layers.14.bias'])

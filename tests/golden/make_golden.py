@@ -46,6 +46,7 @@ def import_reference():
     exec(compile(src, mod.__file__, 'exec'), mod.__dict__)
     import model  # noqa
     import model.yolo2  # noqa
+    import model.mobilenet  # noqa
     import utils.postprocess  # noqa
     import utils.iou.torch  # noqa
     # detect.py pure functions
@@ -179,6 +180,23 @@ def main():
                         a_min=a_min.numpy(), a_max=a_max.numpy(), b_min=b_min.numpy(), b_max=b_max.numpy(), m1=m1.numpy(),
                         c_min=c_min.numpy(), c_max=c_max.numpy(), d_min=d_min.numpy(), d_max=d_max.numpy(), m0=m0.numpy(),
                         r_min=r_min.numpy(), r_max=r_max.numpy(), s_min=s_min.numpy(), s_max=s_max.numpy(), mb=mb.numpy())
+    # ---- 8. MobileNet plugin (BASELINE configs[4]): feature at 64x64 and 416x416 + per-unit checksums ----
+    msd = O.make_mobilenet_state_dict(seed=0)
+    mnet = model.mobilenet.MobileNet(model.ConfigChannels(config), anchors, 20)
+    res = mnet.load_state_dict(msd, strict=False)
+    assert not res.unexpected_keys and all(k.endswith('num_batches_tracked') for k in res.missing_keys), res
+    mnet.eval()
+    mouts = {}
+    hooks = [m.register_forward_hook(lambda mod, inp, out, name=name: mouts.__setitem__(name, out.detach().clone()))
+             for name, m in mnet.layers.named_children()]
+    with torch.no_grad():
+        mf64 = mnet(O.synth_images(1, 64, 64, seed=10))
+        acts64 = {'act_layers.' + k: v.numpy() for k, v in mouts.items() if k != '14'}
+        mf416 = mnet(O.synth_images(1, 416, 416, seed=0))
+    np.savez_compressed(os.path.join(HERE, 'mobilenet.npz'), feature64=mf64.numpy(), feature416=mf416.numpy(), **acts64,
+                        **{'absmean416_layers.' + k: np.float64(v.double().abs().mean().item()) for k, v in mouts.items()})
+    for h in hooks:
+        h.remove()
     for f in sorted(os.listdir(HERE)):
         if f.endswith('.npz'):
             print('%-20s %8.1f KB' % (f, os.path.getsize(os.path.join(HERE, f)) / 1024))

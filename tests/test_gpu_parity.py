@@ -567,3 +567,42 @@ def test_training_step_vs_oracle():
         rm = dict(dnn.named_buffers())[key + '.bn.running_mean'].cpu()
         exp = 0.99 * sd0[key + '.bn.running_mean'] + 0.01 * mean.detach()
         assert rel_err(rm, exp) <= 2e-2, key
+
+
+# ------------------------------------------------------------------------------------------------
+# MobileNet plugin (BASELINE configs[4])
+# ------------------------------------------------------------------------------------------------
+def test_mobilenet_plugin_vs_reference_golden(golden_dir):
+    import model
+    import model.mobilenet
+    import utils
+    g = np.load(os.path.join(golden_dir, 'mobilenet.npz'))
+    cfg = make_config(1)
+    cls = utils.parse_attr('model.mobilenet.MobileNet')
+    net = cls(model.ConfigChannels(cfg), O.anchors_yolo_voc(), 20)
+    res = net.load_state_dict(O.make_mobilenet_state_dict(0), strict=False)
+    assert not res.unexpected_keys and not res.missing_keys
+    net = net.to(DEV).eval()
+    f64 = net(O.synth_images(1, 64, 64, seed=10).to(DEV))
+    f416 = net(O.synth_images(1, 416, 416, seed=0).to(DEV))
+    e64, e416 = rel_err(f64, torch.from_numpy(g['feature64'])), rel_err(f416, torch.from_numpy(g['feature416']))
+    print('mobilenet feature rel: 64x64 %.3e, 416x416 %.3e' % (e64, e416))
+    assert f416.shape == (1, 125, 13, 13) and e64 <= 3e-3 and e416 <= 3e-3
+    # through the detection head: Inference + postprocess_batch run on any plugin backbone
+    import detect
+    inference = model.Inference(cfg, net, O.anchors_yolo_voc()).eval()
+    pred = model._inference(inference, O.synth_images(3, 416, 416, seed=2).to(DEV))
+    assert len(detect.postprocess_batch(cfg, pred)) == 3
+
+
+def test_mobilenet_depthwise_vs_torch(ops):
+    for (b, h, c, stride) in ((2, 26, 256, 1), (2, 26, 256, 2), (1, 104, 64, 2)):
+        gen = torch.Generator().manual_seed(c + stride)
+        x = torch.randn(b, c, h, h, generator=gen).half().float()
+        w = torch.randn(c, 1, 3, 3, generator=gen) * 0.4
+        scale, shift = torch.rand(c, generator=gen) + 0.5, torch.randn(c, generator=gen) * 0.1
+        ref = torch.relu(torch.nn.functional.conv2d(x, w, None, stride, 1, groups=c) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+        y = torch.empty(b, h // stride, h // stride, c, dtype=torch.float16, device=DEV)
+        ops.call('yb_dwconv3x3_bn_relu_fwd', x.to(DEV).permute(0, 2, 3, 1).contiguous().half(), w.to(DEV).view(c, 9).contiguous(), scale.to(DEV),
+                 shift.to(DEV), y, b, h, h, c, stride)
+        assert rel_err(y.permute(0, 3, 1, 2), ref) <= 1e-3

@@ -105,3 +105,17 @@ def test_plugin_surface_state_dict_and_channels():
     assert dnn2.layers1[4].conv.weight.shape[0] == 96 and dnn2.layers1[5].conv.weight.shape[1] == 96
     with pytest.raises(RuntimeError):
         dnn.train()(torch.zeros(1, 3, 32, 32))     # CPU tensor: no fallback in train mode either
+
+
+def test_mobilenet_plugin_surface():
+    import model
+    import model.mobilenet
+    from oracle import yolo2_oracle as O
+    config = load_config()
+    net = model.mobilenet.MobileNet(model.ConfigChannels(config), O.anchors_yolo_voc(), 20)
+    ref = O.make_mobilenet_state_dict(0)
+    sd = net.state_dict()
+    assert set(ref) == {k for k in sd if not k.endswith('num_batches_tracked')}
+    assert all(tuple(sd[k].shape) == tuple(ref[k].shape) for k in ref)
+    assert sum(p.numel() for p in net.parameters()) == 3335101
+    assert sd['layers.14.bias'].shape == (125,) and sd['layers.3.dw.conv.weight'].shape == (128, 1, 3, 3)

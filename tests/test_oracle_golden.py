@@ -140,3 +140,19 @@ def test_loss_restatement_self_consistency():
     gexp[..., 5:] = (torch.softmax(f[..., 5:], -1) - onehot) * p[..., None] / (pos.sum() * cnt)
     gexp = gexp.reshape(B, S, S, 125).permute(0, 3, 1, 2)
     np.testing.assert_allclose(feature.grad.numpy(), gexp.numpy(), rtol=1e-4, atol=1e-9)
+
+
+def test_mobilenet_oracle_matches_reference(golden_dir):
+    """BASELINE configs[4]: the MobileNet restatement vs the reference's own model.mobilenet.MobileNet outputs."""
+    g = load(golden_dir, 'mobilenet.npz')
+    sd = O.make_mobilenet_state_dict(0)
+    collect = {}
+    with torch.no_grad():
+        f64 = O.mobilenet_forward(sd, O.synth_images(1, 64, 64, seed=10), collect=collect)
+        f416 = O.mobilenet_forward(sd, O.synth_images(1, 416, 416, seed=0))
+    for k, v in collect.items():
+        ref = g['act_' + k]
+        assert np.abs(v.numpy() - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max()), k
+    assert np.abs(f64.numpy() - g['feature64']).max() <= 2e-5 * np.abs(g['feature64']).max()
+    assert np.abs(f416.numpy() - g['feature416']).max() <= 2e-5 * np.abs(g['feature416']).max()
+    assert sum(v.numel() for k, v in sd.items() if 'running' not in k) == 3335101          # SURVEY 8a row 23

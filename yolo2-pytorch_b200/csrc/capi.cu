@@ -90,6 +90,8 @@ int head_grad_prepare(const float*, void*, float*, int, int, int, int, cudaStrea
 int conv0_wgrad(const float*, const void*, float*, int, int, int, cudaStream_t);
 int unpack_wgrad(const float*, float*, int, int, int, cudaStream_t);
 int conv_wgrad_forward(const void*, const void*, float*, int, int, int, int, int, int, int, int, cudaStream_t);
+int mb_conv0(const float*, const float*, const float*, const float*, void*, int, int, int, cudaStream_t);
+int dwconv3x3(const void*, const float*, const float*, const float*, void*, int, int, int, int, int, cudaStream_t);
 
 }  // namespace yb
 
@@ -245,6 +247,16 @@ int yb_conv_wgrad(const void* x, const void* dz, float* dw_krsc, int batch, int 
 
 int yb_unpack_wgrad(const float* dw_krsc, float* dw_oihw, int cout, int cin, int ksize, yb_stream_t stream) {
   return yb::unpack_wgrad(dw_krsc, dw_oihw, cout, cin, ksize, S(stream));
+}
+
+int yb_mb_conv0_bn_relu_fwd(const float* x_nchw, const float* w_oihw, const float* scale, const float* shift, void* y_nhwc_f16, int batch,
+                            int height, int width, yb_stream_t stream) {
+  return yb::mb_conv0(x_nchw, w_oihw, scale, shift, y_nhwc_f16, batch, height, width, S(stream));
+}
+
+int yb_dwconv3x3_bn_relu_fwd(const void* x, const float* w_c9, const float* scale, const float* shift, void* y, int batch, int height,
+                             int width, int channels, int stride, yb_stream_t stream) {
+  return yb::dwconv3x3(x, w_c9, scale, shift, y, batch, height, width, channels, stride, S(stream));
 }
 
 }  // extern "C"

@@ -1,0 +1,123 @@
+"""model.mobilenet -- MobileNet backbone plugin on the B200 kernels (inference).
+
+Drop-in for the reference's `model/mobilenet.py` (file:line cited per item): same constructor contract
+`MobileNet(config_channels, anchors, num_cls)` (:56-77), same state_dict keys (`layers.0.conv.weight`,
+`layers.N.dw.conv.weight`, `layers.N.pw.bn.running_var`, `layers.14.weight`, `layers.14.bias`), same forward
+contract x[B,3,H,W] fp32 -> [B, A*(5+C), H/32, W/32] fp32 (:84-85).  Modules only hold parameters; the forward pass is:
+  conv_bn(3,32,s2)   -> yb_mb_conv0_bn_relu_fwd  (fp32 NCHW image in, fp16 NHWC out)
+  13 x conv_unit      -> yb_dwconv3x3_bn_relu_fwd (depthwise, HBM-bound) + tcgen05 1x1 conv with fused BN + ReLU
+  nn.Conv2d(1024, A*(5+C), 1) with bias -> tcgen05 1x1 conv writing fp32 NCHW.
+BatchNorm uses the PyTorch-default momentum 0.1 (unlike model.yolo2's 0.01) and the activation is ReLU (:28-29).
+"""
+import collections
+
+import torch
+import torch.nn as nn
+
+import model
+from b200 import ops as _ops
+
+
+def conv_bn(in_channels, out_channels, stride):
+    return nn.Sequential(collections.OrderedDict([
+        ('conv', nn.Conv2d(in_channels, out_channels, 3, stride, 1, bias=False)),
+        ('bn', nn.BatchNorm2d(out_channels)),
+        ('act', nn.ReLU(inplace=True)),
+    ]))
+
+
+def conv_dw(in_channels, stride):
+    return nn.Sequential(collections.OrderedDict([
+        ('conv', nn.Conv2d(in_channels, in_channels, 3, stride, 1, groups=in_channels, bias=False)),
+        ('bn', nn.BatchNorm2d(in_channels)),
+        ('act', nn.ReLU(inplace=True)),
+    ]))
+
+
+def conv_pw(in_channels, out_channels):
+    return nn.Sequential(collections.OrderedDict([
+        ('conv', nn.Conv2d(in_channels, out_channels, 1, 1, 0, bias=False)),
+        ('bn', nn.BatchNorm2d(out_channels)),
+        ('act', nn.ReLU(inplace=True)),
+    ]))
+
+
+def conv_unit(in_channels, out_channels, stride):
+    return nn.Sequential(collections.OrderedDict([
+        ('dw', conv_dw(in_channels, stride)),
+        ('pw', conv_pw(in_channels, out_channels)),
+    ]))
+
+
+UNITS = [(64, 1), (128, 2), (128, 1), (256, 2), (256, 1), (512, 2), (512, 1), (512, 1), (512, 1), (512, 1), (512, 1), (1024, 2), (1024, 1)]
+
+
+class MobileNet(nn.Module):
+    def __init__(self, config_channels, anchors, num_cls):
+        nn.Module.__init__(self)
+        cc = config_channels
+        layers = [conv_bn(cc.channels, cc(32, 'layers.0.conv.weight'), 2)]
+        for width, stride in UNITS:
+            layers.append(conv_unit(cc.channels, cc(width, 'layers.%d.pw.conv.weight' % len(layers)), stride))
+        layers.append(nn.Conv2d(cc.channels, model.output_channels(len(anchors), num_cls), 1))
+        self.layers = nn.Sequential(*layers)
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight)
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.ones_(m.weight)
+                nn.init.zeros_(m.bias)
+        self._cache = {}
+
+    # ---- operand preparation (cached per parameter version) ------------------------------------------
+    def _fold(self, key, bn):
+        ts = (bn.weight, bn.bias, bn.running_mean, bn.running_var)
+        ver = tuple((t.data_ptr(), t._version) for t in ts)
+        hit = self._cache.get(key)
+        if hit is None or hit[0] != ver:
+            hit = (ver, _ops.bn_fold(*(t.detach().contiguous() for t in ts), eps=bn.eps))
+            self._cache[key] = hit
+        return hit[1]
+
+    def _packed(self, key, w):
+        ver = (w.data_ptr(), w._version)
+        hit = self._cache.get(key)
+        if hit is None or hit[0] != ver:
+            hit = (ver, _ops.pack_weight_f16(w.detach().contiguous(), 0))
+            self._cache[key] = hit
+        return hit[1]
+
+    def forward(self, x):
+        if self.training:
+            raise NotImplementedError('MobileNet (B200): inference only (BASELINE configs[4]); call .eval()')
+        if not x.is_cuda:
+            raise RuntimeError('MobileNet (B200): input must be a CUDA tensor; there is no CPU fallback')
+        b, c, h, w = x.shape
+        if c != 3 or h % 32 or w % 32:
+            raise ValueError('MobileNet expects [B,3,H,W] with H, W multiples of 32')
+        x = x.contiguous().float()
+        first = self.layers[0]
+        scale, shift = self._fold('bn0', first.bn)
+        cur = torch.empty(b, h // 2, w // 2, first.conv.weight.shape[0], dtype=torch.float16, device=x.device)
+        if first.conv.weight.shape[0] != 32:
+            raise ValueError('MobileNet (B200): the first layer must have 32 output channels')
+        _ops.call('yb_mb_conv0_bn_relu_fwd', x, first.conv.weight.detach().contiguous(), scale, shift, cur, b, h, w)
+        hh, ww = h // 2, w // 2
+        for i, unit in enumerate(list(self.layers)[1:-1], 1):
+            dw, pw = unit.dw, unit.pw
+            ch = dw.conv.weight.shape[0]
+            stride = dw.conv.stride[0]
+            scale, shift = self._fold('dw%d' % i, dw.bn)
+            out = torch.empty(b, hh // stride, ww // stride, ch, dtype=torch.float16, device=x.device)
+            _ops.call('yb_dwconv3x3_bn_relu_fwd', cur, dw.conv.weight.detach().contiguous().view(ch, 9), scale, shift, out, b, hh, ww, ch, stride)
+            hh, ww = hh // stride, ww // stride
+            scale, shift = self._fold('pw%d' % i, pw.bn)
+            cur = _ops.conv_bn_act(out, self._packed('pww%d' % i, pw.conv.weight), scale, shift, 0.0)      # slope 0 == ReLU
+        head = self.layers[-1]
+        cout = head.weight.shape[0]
+        ones = self._cache.get('ones')
+        if ones is None or ones.numel() != cout or ones.device != x.device:
+            ones = torch.ones(cout, dtype=torch.float32, device=x.device)
+            self._cache['ones'] = ones
+        return _ops.conv_bn_act(cur, self._packed('head', head.weight), ones, head.bias.detach().float().contiguous(), 1.0,
+                                out_mode=_ops.OUT_F32_NCHW)
