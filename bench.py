@@ -350,7 +350,8 @@ def run_b200(args):
     achieved = prof['conv_flops'] / (prof['conv_ms'] / 1e3) / 1e12
     graph_step_ms = ms / args.steps
     roofline = dict(bound='tensor', achieved=achieved, peak=peaks['tflops'], unit='TFLOP/s', frac=achieved / peaks['tflops'],
-                    traffic=None, kernel='conv_igemm_kernel (22 launches/step)', peak_source=peaks['source'],
+                    traffic=38.7e6, traffic_source='profiles/r01_ncu_conv_full.md: (dram read 641.9 MB + write 208.8 MB) / 22 launches, B=32',
+                    kernel='conv_igemm_kernel (22 launches/step)', peak_source=peaks['source'],
                     flops_per_launch=prof['conv_flops'] / prof['launches'], us_per_launch=prof['conv_ms'] * 1e3 / prof['launches'],
                     share_of_step=prof['conv_ms'] / prof['eager_step_ms'],
                     whole_step_frac=(B * GFLOP_PER_IMAGE_416 / 1e3) / (graph_step_ms / 1e3) / peaks['tflops'])
@@ -466,8 +467,8 @@ def run_train(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=30)
-    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=300)
+    ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=32)
     ap.add_argument('--size', type=int, default=416)
