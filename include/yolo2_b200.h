@@ -38,6 +38,10 @@ typedef void* yb_stream_t; /* cudaStream_t */
 #define YB_CONV_A_TILED 1      /* 1x1 only: fetch A with a plain 2-D tiled TMA instead of im2col mode */
 #define YB_CONV_WIDE_N 2       /* allow the 128x256 tile when Cout % 256 == 0 */
 #define YB_CONV_FORCE_BN(bn) ((bn) << 8) /* testing: force BLOCK_N in {64,128,256} */
+#define YB_CONV_NO_STREAMK 8   /* never split tiles along K even when a workspace is supplied */
+#define YB_CONV_FORCE_STREAMK (1 << 30) /* testing: split along K whenever the shape allows it */
+#define YB_CONV_NO_SMALLK (1 << 28)     /* testing: route Cin=32 3x3 layers through the generic kernel */
+#define YB_CONV_PLAIN_STORE (1 << 29)   /* testing: small-K kernel writes with per-thread stores instead of a TMA store */
 /* yb_filter_nms mode */
 #define YB_FILTER_THRESHOLD 0  /* detect/fix = 0: iou > detect/threshold            (detect.py:56) */
 #define YB_FILTER_FIX 1        /* detect/fix = 1: iou * max prob > threshold_cls    (detect.py:54) */
@@ -48,6 +52,10 @@ const char* yb_last_error(void);
 /* Reads (and clears) the host-mapped debug word a kernel writes before it traps on a pipeline
  * time-out: out[0] = 0x0BADxxxx code, out[1] = block, out[2] = thread, out[3] = parity. */
 int yb_debug_read(int out[4]);
+/* Profiling aid (tools/conv_trace.py): when dev_buf (768 x uint64, device memory) is non-NULL, block 0 of the
+ * tcgen05 conv kernels records clock64() per pipeline event: [0,256) TMA producer, [256,512) MMA issuer,
+ * [512,768) epilogue.  NULL switches it off (the default). */
+int yb_conv_set_trace(void* dev_buf);
 
 /* ---- parameter preparation ---------------------------------------------------------------- */
 /* nn.Conv2d weight [Cout,Cin,k,k] fp32 (model/yolo2.py:57) -> fp16 [Cout][k][k][Cin] (mode 0), or
@@ -74,6 +82,14 @@ int yb_conv0_u8_bn_leaky_pool_fwd(const unsigned char* x_nhwc_u8, const float* w
 int yb_conv_bn_act_fwd(const void* x, const void* w, const float* scale, const float* shift, float slope, void* y, int batch,
                        int height, int width, int cin, int cout, int ksize, int x_ld, long long y_ld, int y_ch_off, int out_mode,
                        int flags, yb_stream_t stream);
+/* Same conv with a caller-owned scratch buffer (yb_conv_workspace_bytes() bytes, 256 B aligned, ZERO-FILLED ONCE when it
+ * is allocated; one per stream -- launches that may overlap must not share it).  With it the library may run the layer
+ * stream-K: tiles x K-blocks are divided evenly over all SMs and tiles cut by a boundary are summed through the buffer,
+ * which keeps every SM busy on the 13x13 / 26x26 layers whose tile count does not fill the GPU.  NULL = plain tiles. */
+long long yb_conv_workspace_bytes(void);
+int yb_conv_bn_act_fwd_ws(const void* x, const void* w, const float* scale, const float* shift, float slope, void* y, int batch,
+                          int height, int width, int cin, int cout, int ksize, int x_ld, long long y_ld, int y_ch_off, int out_mode,
+                          int flags, void* workspace, long long workspace_bytes, yb_stream_t stream);
 /* Same contract on CUDA cores (one thread per output): test/bisect utility, not a product path. */
 int yb_conv_ref_fwd(const void* x, const void* w, const float* scale, const float* shift, float slope, void* y, int batch, int height,
                     int width, int cin, int cout, int ksize, int x_ld, long long y_ld, int y_ch_off, int out_mode, yb_stream_t stream);

@@ -179,6 +179,10 @@ CONV_CASES = [
     (2, 26, 26, 128, 64, 3, ''),
     (2, 13, 13, 256, 512, 3, 'wide'),
     (1, 32, 32, 32, 64, 3, ''),
+    (3, 21, 19, 32, 64, 3, ''),            # small-K kernel, ragged last tile, tiles crossing image boundaries
+    (2, 20, 20, 32, 48, 3, ''),            # small-K kernel, Cout < 64 (TMA store clips the channel box)
+    (3, 21, 19, 32, 64, 3, 'plainstore'),  # small-K kernel with per-thread stores
+    (3, 21, 19, 32, 64, 3, 'generic'),     # same shape through the generic kernel
     (8, 52, 52, 128, 256, 3, ''),
     (32, 13, 13, 512, 1024, 3, ''),
     (2, 13, 13, 1280, 1024, 3, ''),
@@ -196,10 +200,59 @@ def test_conv_unit_vs_oracle(ops, case):
     ref = O.conv_unit(x, sd, 'u', k, True, True)                      # fp32 oracle on fp32 operands
     scale, shift = ops.bn_fold(*(sd['u.bn.' + n].to(DEV) for n in ('weight', 'bias', 'running_mean', 'running_var')))
     w16 = ops.pack_weight_f16(wt.to(DEV))
-    flags = {'tiled': ops.CONV_A_TILED, 'wide': ops.CONV_WIDE_N, '': 0}[fl]
+    flags = {'tiled': ops.CONV_A_TILED, 'wide': ops.CONV_WIDE_N, '': 0, 'plainstore': 1 << 29, 'generic': 1 << 28}[fl]
     y = ops.conv_bn_act(x.to(DEV).permute(0, 2, 3, 1).contiguous().half(), w16, scale, shift, 0.1, flags=flags)
     err = rel_err(y.permute(0, 3, 1, 2), ref)
     assert err <= 1e-3, 'rel err %.3e' % err
+
+
+SK_CASES = [
+    # b, h, w, cin, cout, k, bn, mt   (bn 0 = library's choice); every case is forced onto the stream-K path
+    (32, 13, 13, 512, 1024, 3, 0, 0),      # layers2.x: 88 tiles over 148 CTAs, every tile cut once or twice
+    (2, 13, 13, 1024, 1024, 3, 256, 2),    # 8 tiles x 144 K-blocks: each tile is summed from ~19 CTAs
+    (8, 26, 26, 256, 512, 3, 256, 1),      # two accumulator stages: dump / collect overlap the next segment
+    (4, 52, 52, 128, 256, 3, 128, 2),
+    (3, 13, 13, 1024, 512, 1, 0, 0),       # 1x1
+    (5, 19, 17, 64, 72, 3, 64, 1),         # ragged rows, Cout not a multiple of the tile, BK = 64 taps
+    (5, 19, 17, 96, 136, 3, 128, 1),       # BK = 32 path, two column tiles with a ragged second one
+]
+
+
+@pytest.mark.parametrize('case', SK_CASES)
+def test_conv_streamk_vs_oracle(ops, case):
+    b, h, w, cin, cout, k, bn, mt = case
+    gen = torch.Generator().manual_seed(cin * 3 + cout + h)
+    x = torch.randn(b, cin, h, w, generator=gen)
+    wt = torch.randn(cout, cin, k, k, generator=gen) * (2.0 / (cin * k * k)) ** 0.5
+    sd = {'u.conv.weight': wt, 'u.bn.weight': torch.rand(cout, generator=gen) + 0.5, 'u.bn.bias': torch.randn(cout, generator=gen) * 0.1,
+          'u.bn.running_mean': torch.randn(cout, generator=gen) * 0.1, 'u.bn.running_var': torch.rand(cout, generator=gen) + 0.5}
+    ref = O.conv_unit(x, sd, 'u', k, True, True)
+    scale, shift = ops.bn_fold(*(sd['u.bn.' + n].to(DEV) for n in ('weight', 'bias', 'running_mean', 'running_var')))
+    w16 = ops.pack_weight_f16(wt.to(DEV))
+    ws = ops.conv_workspace(DEV)
+    flags = ops.CONV_FORCE_STREAMK | (ops.conv_force_bn(bn) | ops.conv_force_mt(mt) | ops.conv_force_pair(1) if bn else 0)
+    x16 = x.to(DEV).permute(0, 2, 3, 1).contiguous().half()
+    for rep in range(3):      # repeated launches reuse the workspace: the flags must come back to zero every time
+        y = ops.conv_bn_act(x16, w16, scale, shift, 0.1, flags=flags, workspace=ws)
+        err = rel_err(y.permute(0, 3, 1, 2), ref)
+        assert err <= 1e-3, 'launch %d: rel err %.3e' % (rep, err)
+    assert int(ws[:4096].view(torch.int32).abs().sum().item()) == 0, 'stream-K flags not reset'
+    # and the split changes nothing beyond fp32 summation order
+    y0 = ops.conv_bn_act(x16, w16, scale, shift, 0.1, flags=ops.CONV_NO_STREAMK)
+    assert rel_err(y, y0) <= 2e-3
+
+
+def test_conv_streamk_head_fp32_nchw(ops):
+    gen = torch.Generator().manual_seed(11)
+    x = torch.randn(32, 1024, 13, 13, generator=gen)
+    wt = torch.randn(125, 1024, 1, 1, generator=gen) * (1.0 / 1024) ** 0.5
+    bias = torch.randn(125, generator=gen) * 0.1
+    ref = torch.nn.functional.conv2d(x, wt, bias)
+    w16 = ops.pack_weight_f16(wt.to(DEV))
+    ws = ops.conv_workspace(DEV)
+    y = ops.conv_bn_act(x.to(DEV).permute(0, 2, 3, 1).contiguous().half(), w16, torch.ones(125, device=DEV), bias.to(DEV), 1.0,
+                        out_mode=ops.OUT_F32_NCHW, flags=ops.CONV_FORCE_STREAMK, workspace=ws)
+    assert rel_err(y, ref) <= 1e-3
 
 
 def test_conv_head_fp32_nchw_and_slice(ops):

@@ -10,7 +10,8 @@ sys.path.insert(0, os.path.join(ROOT, 'yolo2-pytorch_b200'))
 import torch  # noqa: E402
 from b200 import ops  # noqa: E402
 
-CASES = [  # h, cin, cout, k, bn, mt, pair
+CASES = [  # h, cin, cout, k, bn, mt, pair  (bn 0 = no forcing: the small-K kernel for cin 32)
+    (208, 32, 64, 3, 0, 0, 0),
     (13, 1024, 1024, 3, 256, 2, 1), (13, 1024, 1024, 3, 256, 1, 1), (13, 1024, 1024, 3, 128, 1, 1),
     (52, 128, 256, 3, 256, 1, 1), (52, 128, 256, 3, 256, 1, 2), (52, 128, 256, 3, 128, 2, 1),
     (26, 256, 512, 3, 256, 1, 1), (104, 64, 128, 3, 128, 2, 1), (208, 32, 64, 3, 64, 2, 1),
@@ -28,7 +29,7 @@ def main():
         out = torch.empty(b, h, h, cout, device='cuda', dtype=torch.float16)
         line = '%3dx%-3d cin%-4d cout%-4d k%d bn%d mt%d p%d: ' % (h, h, cin, cout, k, bn, mt, pr)
         for code, name in ABL:
-            flags = ops.conv_force_bn(bn) | ops.conv_force_mt(mt) | ops.conv_force_pair(pr) | (code << 24)
+            flags = ((ops.conv_force_bn(bn) | ops.conv_force_mt(mt) | ops.conv_force_pair(pr)) if bn else 0) | (code << 24)
             for i in range(3):
                 ops.conv_bn_act(xs[i % 3], w, sc, sh, 0.1, out=out, flags=flags)
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

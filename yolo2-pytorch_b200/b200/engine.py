@@ -85,6 +85,8 @@ class DarknetPlan(object):
         self.l2 = [torch.empty(batch, h, w, u.cout, **f16) for u in units2[:-1]]
         self.l3 = torch.empty(batch, h, w, units3[0].cout, **f16)
         self.feature = torch.empty(batch, units3[1].cout, h, w, dtype=torch.float32, device=device)
+        # stream-K scratch (partial sums + flags): per plan, because plans are what run concurrently on different streams
+        self.workspace = ops.conv_workspace(device)
 
 
 class DarknetEngine(object):
@@ -143,7 +145,7 @@ class DarknetEngine(object):
         p = self.plan(b, h, w, x.device, plan_id)   # plan_id: independent buffer sets for concurrent streams
 
         def conv(u, src, dst, **kw):
-            return ops.conv_bn_act(src, u.w16, u.scale, u.shift, u.slope, out=dst, flags=conv_flags, ref=ref, **kw)
+            return ops.conv_bn_act(src, u.w16, u.scale, u.shift, u.slope, out=dst, flags=conv_flags, ref=ref, workspace=p.workspace, **kw)
 
         u0 = self.units1[0]
         conv0 = ops.conv0_u8_bn_leaky_pool if u8 else ops.conv0_bn_leaky_pool

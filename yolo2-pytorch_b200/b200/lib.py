@@ -4,7 +4,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), 'libyolo2_b200.so')
+# YB_LIB_PATH: A/B a differently-compiled build of the same library (tools/ only)
+LIB_PATH = os.environ.get('YB_LIB_PATH') or os.path.join(os.path.dirname(_HERE), 'libyolo2_b200.so')
 
 c_int, c_float, c_void_p, c_longlong = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_longlong
 P = c_void_p
@@ -13,11 +14,15 @@ P = c_void_p
 SIGNATURES = {
     'yb_version': [],
     'yb_debug_read': [ctypes.POINTER(c_int * 4)],
+    'yb_conv_set_trace': [P],
     'yb_pack_weight_f16': [P, P, c_int, c_int, c_int, c_int, P],
     'yb_bn_fold': [P, P, P, P, c_float, P, P, c_int, P],
     'yb_conv0_bn_leaky_pool_fwd': [P, P, P, P, c_float, P, c_int, c_int, c_int, c_int, P],
     'yb_conv0_u8_bn_leaky_pool_fwd': [P, P, P, P, c_float, P, c_int, c_int, c_int, c_int, P],
     'yb_conv_bn_act_fwd': [P, P, P, P, c_float, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_longlong, c_int, c_int, c_int, P],
+    'yb_conv_workspace_bytes': [],
+    'yb_conv_bn_act_fwd_ws': [P, P, P, P, c_float, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_longlong, c_int, c_int, c_int, P,
+                              c_longlong, P],
     'yb_conv_ref_fwd': [P, P, P, P, c_float, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_longlong, c_int, c_int, P],
     'yb_maxpool2x2_f16': [P, P, c_int, c_int, c_int, c_int, c_int, P],
     'yb_reorg_f16': [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P],
@@ -60,7 +65,7 @@ def load():
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.argtypes = argtypes
-        fn.restype = c_int
+        fn.restype = c_longlong if name == 'yb_conv_workspace_bytes' else c_int
     lib.yb_last_error.argtypes = []
     lib.yb_last_error.restype = ctypes.c_char_p
     _lib = lib

@@ -9,6 +9,7 @@ from . import lib as _l
 
 OUT_F16_NHWC, OUT_F32_NCHW = 0, 1
 CONV_A_TILED, CONV_WIDE_N = 1, 2
+CONV_NO_STREAMK, CONV_FORCE_STREAMK, CONV_NO_SMALLK, CONV_PLAIN_STORE = 8, 1 << 30, 1 << 28, 1 << 29
 FILTER_THRESHOLD, FILTER_FIX, FILTER_NONE = 0, 1, 2
 
 
@@ -105,16 +106,27 @@ def conv0_u8_bn_leaky_pool(x, w, scale, shift, slope, out=None):
     return out
 
 
-def _conv_common(fn_name, x, w, scale, shift, slope, out, batch, height, width, cin, cout, k, x_ld, y_ld, y_ch_off, out_mode, flags):
+def _conv_common(fn_name, x, w, scale, shift, slope, out, batch, height, width, cin, cout, k, x_ld, y_ld, y_ch_off, out_mode, flags,
+                 workspace=None):
+    if workspace is not None and fn_name == 'yb_conv_bn_act_fwd':
+        fn_name = 'yb_conv_bn_act_fwd_ws'
     fn = getattr(_l.load(), fn_name)
     args = [_p(x), _p(w), _p(scale), _p(shift), float(slope), _p(out), batch, height, width, cin, cout, k, x_ld, y_ld, y_ch_off, out_mode]
-    if fn_name == 'yb_conv_bn_act_fwd':
+    if fn_name != 'yb_conv_ref_fwd':
         args.append(flags)
+    if fn_name == 'yb_conv_bn_act_fwd_ws':
+        _req(workspace, torch.uint8, 'workspace')
+        args += [_p(workspace), workspace.numel()]
     args.append(_s())
     _ck(fn(*args), fn_name)
 
 
-def conv_bn_act(x, w, scale, shift, slope, out=None, out_mode=OUT_F16_NHWC, y_ch_off=0, cin=None, flags=0, ref=False):
+def conv_workspace(device='cuda'):
+    """Scratch buffer for stream-K convs (yb_conv_bn_act_fwd_ws): zero-filled once, one per stream / activation plan."""
+    return torch.zeros(int(_l.load().yb_conv_workspace_bytes()), dtype=torch.uint8, device=device)
+
+
+def conv_bn_act(x, w, scale, shift, slope, out=None, out_mode=OUT_F16_NHWC, y_ch_off=0, cin=None, flags=0, ref=False, workspace=None):
     """x: fp16 [B,H,W,x_ld] (uses the first `cin` channels, default all); w: fp16 [Cout,k,k,Cin].
     out (fp16): [B,H,W,y_ld] written at channels [y_ch_off, y_ch_off+Cout); out (fp32): [B,Cout,H,W]."""
     _req(x, torch.float16, 'x'); _req(w, torch.float16, 'w'); _req(scale, torch.float32, 'scale'); _req(shift, torch.float32, 'shift')
@@ -133,7 +145,7 @@ def conv_bn_act(x, w, scale, shift, slope, out=None, out_mode=OUT_F16_NHWC, y_ch
         _req(out, torch.float32, 'out')
         y_ld = 0
     _conv_common('yb_conv_ref_fwd' if ref else 'yb_conv_bn_act_fwd', x, w, scale, shift, slope, out, b, h, wd, cin, cout, k, x_ld, y_ld,
-                 y_ch_off, out_mode, flags)
+                 y_ch_off, out_mode, flags, workspace=None if ref else workspace)
     return out
 
 

@@ -60,11 +60,13 @@ int* debug_word_device() {
 }
 
 // implemented in the kernel translation units
+long long conv_workspace_bytes();
 int conv_igemm_forward(const void*, const void*, const float*, const float*, float, void*, int, int, int, int, int, int, int, long long,
-                       int, int, int, cudaStream_t);
+                       int, int, int, void*, long long, cudaStream_t);
 int conv_ref_forward(const void*, const void*, const float*, const float*, float, void*, int, int, int, int, int, int, int, long long,
                      int, int, cudaStream_t);
 int pack_weight(const float*, void*, int, int, int, int, int, cudaStream_t);
+void conv_set_trace(void*);
 int bn_fold(const float*, const float*, const float*, const float*, float, float*, float*, int, cudaStream_t);
 int conv0_tc_forward(const void*, int, const float*, const float*, const float*, float, void*, int, int, int, int, int, cudaStream_t);
 int maxpool2x2(const void*, void*, int, int, int, int, int, cudaStream_t);
@@ -110,6 +112,8 @@ int yb_debug_read(int out[4]) {
   return 0;
 }
 
+int yb_conv_set_trace(void* dev_buf) { yb::conv_set_trace(dev_buf); return 0; }
+
 int yb_pack_weight_f16(const float* w_oihw, void* w_f16, int cout, int cin, int ksize, int mode, yb_stream_t stream) {
   return yb::pack_weight(w_oihw, w_f16, cout, cin, ksize, mode, 0, S(stream));
 }
@@ -133,7 +137,16 @@ int yb_conv_bn_act_fwd(const void* x, const void* w, const float* scale, const f
                        int height, int width, int cin, int cout, int ksize, int x_ld, long long y_ld, int y_ch_off, int out_mode,
                        int flags, yb_stream_t stream) {
   return yb::conv_igemm_forward(x, w, scale, shift, slope, y, batch, height, width, cin, cout, ksize, x_ld, y_ld, y_ch_off, out_mode,
-                                flags, S(stream));
+                                flags, nullptr, 0, S(stream));
+}
+
+long long yb_conv_workspace_bytes(void) { return yb::conv_workspace_bytes(); }
+
+int yb_conv_bn_act_fwd_ws(const void* x, const void* w, const float* scale, const float* shift, float slope, void* y, int batch,
+                          int height, int width, int cin, int cout, int ksize, int x_ld, long long y_ld, int y_ch_off, int out_mode,
+                          int flags, void* workspace, long long workspace_bytes, yb_stream_t stream) {
+  return yb::conv_igemm_forward(x, w, scale, shift, slope, y, batch, height, width, cin, cout, ksize, x_ld, y_ld, y_ch_off, out_mode,
+                                flags, workspace, workspace_bytes, S(stream));
 }
 
 int yb_conv_ref_fwd(const void* x, const void* w, const float* scale, const float* shift, float slope, void* y, int batch, int height,

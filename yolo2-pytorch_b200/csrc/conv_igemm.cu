@@ -41,12 +41,68 @@ struct ConvParams {
   int hw;           // H*W
   int skip;         // profiling ablation (results are garbage): 1 = no A loads, 2 = no B loads, 4 = no MMA, 8 = no stores
   int* dbg;
+  // stream-K (streamk != 0): the tiles x K-blocks iteration space is cut into gridDim.x equal contiguous ranges, so a
+  // layer whose tile count does not fill the SMs (13x13: 88 tiles on 148 SMs) still keeps every SM busy.  A CTA
+  // whose range ends inside a tile dumps that partial fp32 accumulator to ws[blockIdx] and raises flags[blockIdx];
+  // the CTA that holds the tile's last K-block adds the partials of the (lower-numbered) CTAs and runs the epilogue.
+  int streamk;
+  int sk_base, sk_rem;         // units per CTA = sk_base (+1 for the first sk_rem CTAs)
+  float* ws;                   // [gridDim.x][MT][BN/32][128][32] fp32
+  unsigned* flags;             // [gridDim.x], 0 = empty, 1 = partial ready (reset by the consumer)
+  unsigned long long* trace;   // optional (tools/conv_trace.py): block 0 records clock64() per pipeline event, 3 roles x 256 slots
 };
 
+// role 0 = TMA producer, 1 = MMA issuer, 2 = epilogue thread 0; slot = running event index of that role
+#define YB_TRACE(role, slot) do { if (p.trace != nullptr && blockIdx.x == 0 && (slot) < 256) p.trace[(role) * 256 + (slot)] = clock64(); } while (0)
+
+
 constexpr int BM = 128;
+
 constexpr int UMMA_K = 16;
 constexpr int kNumThreads = 192;
 constexpr int kEpiThreads = 128;
+
+// Work iteration shared by the three warp roles.  Plain mode: whole tiles, strided over the CTAs.  Stream-K mode: the
+// CTA's unit range [s, e) (unit = one K-block of one tile) is walked from its END backwards, one tile segment at a
+// time, so that the only segment that can stop short of its tile's last K-block is the first one processed -- its
+// partial sums are needed by a HIGHER-numbered CTA, which reaches that tile last.  Waits therefore only ever point at
+// lower block ids and at work those CTAs do first.
+struct WorkIter {
+  int tile, kb0, kb1;
+  int streamk, num_kb, num_tiles, stride, s, cur_end;
+  __device__ __forceinline__ static int sk_start(int c, int base, int rem) { return c * base + (c < rem ? c : rem); }
+  __device__ __forceinline__ WorkIter(const ConvParams& p, int unit_id, int num_units, int ntiles) {
+    streamk = p.streamk; num_kb = p.num_kb; num_tiles = ntiles; stride = num_units;
+    if (streamk) {
+      s = sk_start(unit_id, p.sk_base, p.sk_rem);
+      cur_end = sk_start(unit_id + 1, p.sk_base, p.sk_rem);
+      tile = 0; kb0 = 0; kb1 = 0;
+      advance();
+    } else {
+      tile = unit_id; kb0 = 0; kb1 = num_kb; s = 0; cur_end = 0;
+    }
+  }
+  __device__ __forceinline__ void advance() {   // stream-K only
+    if (cur_end <= s) { tile = num_tiles; return; }
+    tile = (cur_end - 1) / num_kb;
+    const int tile_start = tile * num_kb;
+    const int seg_start = s > tile_start ? s : tile_start;
+    kb0 = seg_start - tile_start;
+    kb1 = cur_end - tile_start;
+    cur_end = seg_start;
+  }
+  __device__ __forceinline__ bool valid() const { return tile < num_tiles; }
+  __device__ __forceinline__ void next() { if (streamk) advance(); else tile += stride; }
+};
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
 
 // MT = number of 128-pixel M-subtiles per CTA tile (1 or 2).  MT = 2 makes the CTA tile 256 x BN: both
 // subtiles reuse the same weight (B) tile from shared memory, halving the L2->SM weight traffic per MAC.
@@ -127,7 +183,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = unit_id; tile < num_tiles; tile += num_units) {
+      int tr_p = 0;
+      for (WorkIter it(p, unit_id, num_units, num_tiles); it.valid(); it.next()) {
+        const int tile = it.tile;
         const int n_tile = tile % p.n_tiles;
         const int m_tile = tile / p.n_tiles;
         const int m_cta = m_tile * Cfg::kRowsPerTile + static_cast<int>(rank) * Cfg::kRowsPerCta;
@@ -154,12 +212,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           if (p.skip & 1) nsub_peer = 0;
           tx_bytes += nsub_peer * Cfg::kASubBytes + ((p.skip & 2) ? 0 : Cfg::kBBytes);     // (only used by rank 0, whose own nsub is MT here or the tile is the last one)
         }
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        for (int kb = it.kb0; kb < it.kb1; ++kb) {
           const int tap = kb / p.kb_per_tap;
           const int c0 = (kb - tap * p.kb_per_tap) * BK;
           const int r = tap / p.ksize;
           const int s = tap - r * p.ksize;
           mbar_wait(bar_empty + 8 * stage, phase ^ 1, p.dbg, 0x100 | stage);
+          YB_TRACE(0, tr_p); ++tr_p;
           const uint32_t full = kPair ? leader_addr(bar_full + 8 * stage) : (bar_full + 8 * stage);
           if (!kPair || rank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, tx_bytes);
           else mbar_arrive_remote(bar_full + 8 * stage, 0);
@@ -192,13 +251,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = unit_id; tile < num_tiles; tile += num_units) {
+      int tr_m = 0;
+      for (WorkIter it(p, unit_id, num_units, num_tiles); it.valid(); it.next()) {
         mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1, p.dbg, 0x200 | acc);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * Cfg::kAccCols;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        const int kb_first = it.kb0, kb_last = it.kb1 - 1;
+        for (int kb = kb_first; kb <= kb_last; ++kb) {
           mbar_wait(bar_full + 8 * stage, phase, p.dbg, 0x300 | stage);
           tc_fence_after();
+          YB_TRACE(1, tr_m); ++tr_m;
           const uint64_t bdesc = make_kmajor_desc<Cfg::kSwizzle>(smem_b + stage * Cfg::kBBytes);
 #pragma unroll
           for (int t = 0; t < MT; ++t) {
@@ -207,13 +269,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               // advance 16 fp16 = 32 bytes inside the swizzled row: +2 in the 16-byte address field
-              if (kPair) umma_f16_pair(d_tmem + t * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-              else umma_f16(d_tmem + t * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+              if (kPair) umma_f16_pair(d_tmem + t * BN, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb - kb_first) | k) != 0);
+              else umma_f16(d_tmem + t * BN, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb - kb_first) | k) != 0);
             }
           }
           // free the smem slot (in both CTAs of a pair) once these MMAs retire
           if (kPair) umma_commit_pair(bar_empty + 8 * stage); else umma_commit(bar_empty + 8 * stage);
-          if (kb == p.num_kb - 1) {
+          if (kb == kb_last) {
             if (kPair) umma_commit_pair(bar_tfull + 8 * acc); else umma_commit(bar_tfull + 8 * acc);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -228,10 +290,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     int acc = 0;
     uint32_t acc_phase = 0;
     int buf = 0;
-    for (int tile = unit_id; tile < num_tiles; tile += num_units) {
+    for (WorkIter it(p, unit_id, num_units, num_tiles); it.valid(); it.next()) {
+      const int tile = it.tile;
       const int n_tile = tile % p.n_tiles;
       const int m_tile = tile / p.n_tiles;
       const int n0 = n_tile * BN;
+      // stream-K roles of this segment: it either stops short of the tile's last K-block (dump the partial sums), or
+      // finishes a tile whose first K-blocks were summed by lower-numbered CTAs (collect their partials first)
+      const bool sk_dump = it.kb1 < p.num_kb;
+      const bool sk_collect = !sk_dump && it.kb0 > 0;
+      int sk_lo = 0;                           // partials come from CTAs [sk_lo, blockIdx.x)
       const int m_cta = m_tile * Cfg::kRowsPerTile + static_cast<int>(rank) * Cfg::kRowsPerCta;
       // stage this tile's per-channel scale/shift (double-buffered: a warp can be one tile ahead)
       float* sc = ep_scale + buf * BN;
@@ -242,9 +310,57 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         sc[i] = (c < p.cout) ? __ldg(p.scale + c) : 0.f;
         sh[i] = (c < p.cout) ? __ldg(p.shift + c) : 0.f;
       }
+      if (sk_collect) {
+        // the CTA whose range contains this tile's first unit, by inverting sk_start()
+        const int u = tile * p.num_kb;
+        const int wide = p.sk_rem * (p.sk_base + 1);
+        sk_lo = u < wide ? u / (p.sk_base + 1) : p.sk_rem + (u - wide) / p.sk_base;
+        if (et == 0) {
+          for (int j = sk_lo; j < static_cast<int>(blockIdx.x); ++j) {
+            uint32_t spins = 0;
+            uint64_t t0 = 0;
+            while (ld_acquire_gpu(p.flags + j) == 0u) {
+              if ((++spins & 0x3FFu) == 0) {
+                const uint64_t now = globaltimer_ns();
+                if (t0 == 0) t0 = now;
+                if (now - t0 > 4000000000ull) {
+                  if (p.dbg != nullptr) { p.dbg[0] = 0x0BAD0500; p.dbg[1] = static_cast<int>(blockIdx.x); p.dbg[2] = j; p.dbg[3] = tile; __threadfence_system(); }
+                  __trap();
+                }
+              }
+            }
+          }
+        }
+      }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       mbar_wait(bar_tfull + 8 * acc, acc_phase, p.dbg, 0x400 | acc);
       tc_fence_after();
+      if (sk_dump) {
+        float* wsp = p.ws + static_cast<size_t>(blockIdx.x) * (MT * BN * 128);
+#pragma unroll 1
+        for (int t = 0; t < MT; ++t) {
+          if (m_cta + t * BM >= p.m_total) break;
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * Cfg::kAccCols + t * BN;
+#pragma unroll 1
+          for (int cc = 0; cc < BN / 32; ++cc) {
+            if (n0 + cc * 32 >= p.cout) break;
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(taddr + cc * 32, v);
+            tmem_ld_wait();
+            float4* dst = reinterpret_cast<float4*>(wsp + (static_cast<size_t>(t * (BN / 32) + cc) * 128 + q * 32 + lane) * 32);
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              dst[g] = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
+          }
+        }
+        tc_fence_before();
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) st_release_gpu(p.flags + blockIdx.x, 1u);
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
 #pragma unroll 1
       for (int t = 0; t < MT; ++t) {
         if (m_cta + t * BM >= p.m_total) break;   // warp-uniform: subtile entirely past the end
@@ -260,6 +376,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           tmem_ld_wait();
           const int cbase = n0 + cc * 32;
           if (cbase >= p.cout) continue;           // warp-uniform
+          if (sk_collect) {
+            for (int j = sk_lo; j < static_cast<int>(blockIdx.x); ++j) {
+              const float4* src = reinterpret_cast<const float4*>(p.ws + static_cast<size_t>(j) * (MT * BN * 128) +
+                                                                  (static_cast<size_t>(t * (BN / 32) + cc) * 128 + q * 32 + lane) * 32);
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const float4 a = __ldcg(src + g);
+                v[4 * g] = __float_as_uint(__uint_as_float(v[4 * g]) + a.x);
+                v[4 * g + 1] = __float_as_uint(__uint_as_float(v[4 * g + 1]) + a.y);
+                v[4 * g + 2] = __float_as_uint(__uint_as_float(v[4 * g + 2]) + a.z);
+                v[4 * g + 3] = __float_as_uint(__uint_as_float(v[4 * g + 3]) + a.w);
+              }
+            }
+          }
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -304,6 +434,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         if (!kPair || rank == 0) mbar_arrive(bar_tempty + 8 * acc);
         else mbar_arrive_remote(bar_tempty + 8 * acc, 0);
       }
+      if (sk_collect) {
+        // every reader is done with the partials: hand the slots back (the next writer is a later launch)
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int j = sk_lo + et; j < static_cast<int>(blockIdx.x); j += kEpiThreads) p.flags[j] = 0u;
+      }
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -317,8 +452,215 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 }
 
 // ---------------------------------------------------------------------------------------------
+// Small-K variant for 3x3 convs with Cin = 32 (layers1.2: K = 288).  With the generic kernel every K-block is a
+// 32-channel sliver (2 MMAs), so the producer->MMA->commit hand-shake (~250 ns per K-block) dominates.  Here the
+// whole weight matrix (9 taps x [BN x 32]) stays resident in shared memory for the life of the CTA and one pipeline
+// stage carries ALL 9 taps of a 128-pixel tile: one barrier round trip and 18 MMAs per tile instead of 9 and 2.
+// ---------------------------------------------------------------------------------------------
+template <int BN>
+struct SmallKCfg {
+  static constexpr int kTaps = 9, BK = 32;
+  static constexpr int kATap = BM * BK * 2;            // 8 KB
+  static constexpr int kAStage = kTaps * kATap;        // 72 KB
+  static constexpr int kBTap = BN * BK * 2;            // 4 KB (BN = 64)
+  static constexpr int kBBytes = kTaps * kBTap;        // 36 KB, resident
+  static constexpr int kStages = 2;
+  static constexpr int kThreads = 64 + 256;            // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
+  static constexpr int kOutBytes = BM * BN * 2;       // 16 KB staging tile for the TMA-store epilogue (x2)
+  static constexpr int kSmemBytes = kStages * kAStage + kBBytes + 2 * kOutBytes + 1024 + 2 * 2 * BN * 4 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(SmallKCfg<BN>::kThreads, 1)
+conv_smallk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                   const __grid_constant__ CUtensorMap tmap_y, const ConvParams p, const int tma_store) {
+  using Cfg = SmallKCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_b = smem_base + kStages * Cfg::kAStage;
+  const uint32_t smem_o = smem_b + Cfg::kBBytes;       // 1024-aligned (72K, 36K are multiples of 1024)
+  float* ep_scale = reinterpret_cast<float*>(smem_gen + kStages * Cfg::kAStage + Cfg::kBBytes + 2 * Cfg::kOutBytes);
+  float* ep_shift = ep_scale + 2 * BN;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ep_shift + 2 * BN);
+  const uint32_t bar_full = smem_u32(bars);
+  const uint32_t bar_empty = bar_full + 8 * kStages;
+  const uint32_t bar_tfull = bar_empty + 8 * kStages;
+  const uint32_t bar_tempty = bar_tfull + 16;
+  const uint32_t bar_w = bar_tempty + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 5);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 8); }
+    mbar_init(bar_w, 1);
+    fence_mbar_init();
+    fence_proxy_async_smem();
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_y);
+  }
+  if (warp == 1) { tmem_alloc(smem_u32(tmem_slot), 2 * BN); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // resident weights: this CTA works on one column tile only when n_tiles == 1 (checked on the host)
+      mbar_arrive_expect_tx(bar_w, Cfg::kBBytes);
+      for (int t = 0; t < Cfg::kTaps; ++t) tma_load_2d(smem_b + t * Cfg::kBTap, &tmap_b, bar_w, t * p.cin, 0);
+      int stage = 0; uint32_t phase = 0; int tr = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = tile * BM;
+        const int img = m0 / p.hw;
+        const int rem = m0 - img * p.hw;
+        const int h0 = rem / p.width, w0 = rem - h0 * p.width;
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1, p.dbg, 0x900 | stage);
+        YB_TRACE(0, tr); ++tr;
+        if (p.skip & 1) { mbar_arrive(bar_full + 8 * stage); if (++stage == kStages) { stage = 0; phase ^= 1; } continue; }
+        mbar_arrive_expect_tx(bar_full + 8 * stage, Cfg::kAStage);
+        for (int t = 0; t < Cfg::kTaps; ++t)
+          tma_load_im2col_4d(smem_a + stage * Cfg::kAStage + t * Cfg::kATap, &tmap_a, bar_full + 8 * stage, 0, w0 - 1, h0 - 1, img,
+                             static_cast<uint16_t>(t % 3), static_cast<uint16_t>(t / 3));
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(BM, BN);
+      int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0; int tr = 0;
+      mbar_wait(bar_w, 0, p.dbg, 0xA00);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1, p.dbg, 0xA10 | acc);
+        YB_TRACE(1, tr); ++tr;
+        mbar_wait(bar_full + 8 * stage, phase, p.dbg, 0xA20 | stage);
+        tc_fence_after();
+        YB_TRACE(1, tr); ++tr;
+#pragma unroll
+        for (int t = 0; t < Cfg::kTaps; ++t) {
+          if (p.skip & 4) break;
+          const uint64_t adesc = make_kmajor_desc<64>(smem_a + stage * Cfg::kAStage + t * Cfg::kATap);
+          const uint64_t bdesc = make_kmajor_desc<64>(smem_b + t * Cfg::kBTap);
+          umma_f16(tmem_base + acc * BN, adesc, bdesc, idesc, t != 0);
+          umma_f16(tmem_base + acc * BN, adesc + 2, bdesc + 2, idesc, 1);
+        }
+        umma_commit(bar_empty + 8 * stage);
+        umma_commit(bar_tfull + 8 * acc);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;       // which 32-column half of the 64-wide tile this warp converts
+    const int et = threadIdx.x - 64;
+    int acc = 0; uint32_t acc_phase = 0; int tr = 0;
+    for (int i = et; i < BN; i += 256) {
+      ep_scale[i] = (i < p.cout) ? __ldg(p.scale + i) : 0.f;
+      ep_shift[i] = (i < p.cout) ? __ldg(p.shift + i) : 0.f;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(bar_tfull + 8 * acc, acc_phase, p.dbg, 0xA30 | acc);
+      tc_fence_after();
+      if (et == 0) { YB_TRACE(2, tr); ++tr; }
+      const int row = tile * BM + q * 32 + lane;
+      const bool row_ok = row < p.m_total;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      if (tma_store) {
+        // stage the 128 x 64 fp16 tile in shared memory (128 B rows, 128B-swizzled so the 16 B chunk writes of a
+        // quarter-warp hit distinct banks) and let one thread ship it with a single TMA store; the tensor map clips
+        // rows >= M and channels >= Cout.
+        const uint32_t obuf = smem_o + acc * Cfg::kOutBytes;
+        if (et == 0) tma_store_wait_read<1>();          // the store issued two tiles ago has finished reading this buffer
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (et == 0) { YB_TRACE(2, tr); ++tr; }
+        const int r = q * 32 + lane;
+        {
+          const int cc = half;
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr + cc * 32, v);
+          tmem_ld_wait();
+          const int cbase = cc * 32;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float x = __uint_as_float(v[g * 8 + j]) * ep_scale[cbase + g * 8 + j] + ep_shift[cbase + g * 8 + j];
+              f[j] = x > 0.f ? x : x * p.slope;
+            }
+            uint4 pk;
+            __half2 h0 = __floats2half2_rn(f[0], f[1]), h1 = __floats2half2_rn(f[2], f[3]), h2 = __floats2half2_rn(f[4], f[5]), h3 = __floats2half2_rn(f[6], f[7]);
+            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+            const int chunk = cc * 4 + g;
+            st_shared_v4(obuf + r * 128 + ((chunk ^ (r & 7)) << 4), pk);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+        if (et == 0) { YB_TRACE(2, tr); ++tr; }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (et == 0 && !(p.skip & 8)) { tma_store_2d(&tmap_y, obuf, 0, tile * BM); tma_store_commit(); }
+        if (et == 0) { YB_TRACE(2, tr); ++tr; }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
+      for (int cc = half; cc <= half; ++cc) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + cc * 32, v);
+        tmem_ld_wait();
+        const int cbase = cc * 32;
+        if (cbase >= p.cout || !row_ok || (p.skip & 8)) continue;
+        __half* dst = reinterpret_cast<__half*>(p.y) + static_cast<long long>(row) * p.y_ld + p.y_ch_off + cbase;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (cbase + g * 8 < p.cout) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float x = __uint_as_float(v[g * 8 + j]) * ep_scale[cbase + g * 8 + j] + ep_shift[cbase + g * 8 + j];
+              f[j] = x > 0.f ? x : x * p.slope;
+            }
+            uint4 pk;
+            __half2 h0 = __floats2half2_rn(f[0], f[1]), h1 = __floats2half2_rn(f[2], f[3]), h2 = __floats2half2_rn(f[4], f[5]), h3 = __floats2half2_rn(f[6], f[7]);
+            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(dst + g * 8) = pk;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (tma_store && et == 0) tma_store_wait<0>();      // all bulk stores complete before the CTA's smem goes away
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 2 * BN); }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Host side: tensor-map encoding through the driver entry points (no link-time libcuda dependency)
 // ---------------------------------------------------------------------------------------------
+constexpr long long kSkFlagBytes = 4096;          // room for 1024 CTA flags
+constexpr long long kSkSlotBytes = 512 * 128 * 4;  // one CTA's largest partial accumulator (MT*BN = 512 columns x 128 rows x fp32)
+long long conv_workspace_bytes() { return kSkFlagBytes + kSkSlotBytes * sm_count(); }
+
+static unsigned long long* g_conv_trace = nullptr;
+void conv_set_trace(void* dev_ptr) { g_conv_trace = static_cast<unsigned long long*>(dev_ptr); }
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -365,6 +707,8 @@ static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const ConvP
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
+  } else if (p.streamk) {
+    cfg.gridDim = dim3(sm_count());          // sk_base / sk_rem were computed for exactly this many CTAs
   } else {
     cfg.gridDim = dim3(tiles < sm_count() ? tiles : sm_count());
   }
@@ -389,7 +733,7 @@ static int dispatch_conv(int bn, int mt, const CUtensorMap& ta, const CUtensorMa
 
 int conv_igemm_forward(const void* x, const void* w, const float* scale, const float* shift, float slope, void* y, int batch,
                        int height, int width, int cin, int cout, int ksize, int x_ld, long long y_ld, int y_ch_off, int out_mode,
-                       int flags, cudaStream_t stream) {
+                       int flags, void* workspace, long long workspace_bytes, cudaStream_t stream) {
   YB_REQUIRE(x && w && scale && shift && y, "conv: null pointer");
   YB_REQUIRE(ksize == 1 || ksize == 3, "conv: ksize %d unsupported (1 or 3)", ksize);
   YB_REQUIRE(batch > 0 && height > 0 && width > 0, "conv: bad shape");
@@ -410,7 +754,11 @@ int conv_igemm_forward(const void* x, const void* w, const float* scale, const f
   // L2->SM operand feed (~95 B/ns per SM, ~11 TB/s chip-wide), a tile costs its operand bytes at
   // that rate (or its MMA time if larger), tiles run in ceil(tiles/SMs) rounds, and a CTA tile whose
   // accumulator fills all of TMEM (256x256) cannot overlap its epilogue with the next mainloop.
-  int bn = 0, mt = 0, pair = 0;
+  int bn = 0, mt = 0, pair = 0, streamk = 0;
+  // stream-K needs the caller's workspace (one per stream: partial sums + flags); flags bit 3 forbids, bit 30 forces it
+  const bool sk_possible = workspace != nullptr && workspace_bytes >= conv_workspace_bytes() && (flags & 8) == 0 &&
+                           (reinterpret_cast<uintptr_t>(workspace) & 255) == 0;
+  const bool sk_force = sk_possible && ((flags >> 30) & 1);
   const int force_bn = (flags >> 8) & 0x3FF;
   const int force_mt = (flags >> 20) & 0x3;
   const int force_pair = (flags >> 22) & 0x3;      // 0 = auto, 1 = single-CTA, 2 = CTA pair (cta_group::2)
@@ -438,13 +786,33 @@ int conv_igemm_forward(const void* x, const void* w, const float* scale, const f
           const double agg_ns = tiles * (cpair ? 2 : 1) * num_kb * bytes_kb / 11000.0;
           double t = rounds * tile_ns;
           if (agg_ns > t) t = agg_ns;
+          int csk = 0;
+          if (sk_possible && !cpair) {
+            // stream-K: every SM gets units/SMs K-blocks; on top, roughly one partial dump + one collecting epilogue
+            // per CTA (proportional to the accumulator size, not overlapped when it fills TMEM)
+            const double units = tiles * num_kb;
+            const double per_cta = static_cast<double>((static_cast<long long>(units) + sms - 1) / sms);
+            const double epi_ns = 8000.0 * (cmt * cbn / 512.0);
+            double tsk = per_cta * kb_ns + (single_acc ? 2.0 : 1.0) * epi_ns + 1500.0;
+            if (agg_ns > tsk) tsk = agg_ns;
+            // Measured (tools/conv_sweep_sk.py, profiles/r01_conv_sweep_sk.md): at batch 32 the 13x13 / 26x26 layers are
+            // already limited chip-wide (L2 -> SM operand bandwidth, board power), so spreading them over all SMs gains
+            // nothing; stream-K pays when the layer leaves most of the GPU idle (single images, small batches).
+            const bool ok = per_cta >= 4.0 && num_kb >= 2;
+            const bool idle = tiles <= sms / 2;
+            if (ok && (sk_force || (idle && tsk < 0.93 * t))) { t = tsk; csk = 1; }
+          }
+          if (sk_force && !csk) continue;
           // ties (e.g. 256x128 vs 128x256, same operand bytes) go to the wider-N shape, which measured ~8% faster
-          if (t < best * 0.9999 || (t <= best * 1.0001 && cbn > bn)) { best = t; bn = cbn; mt = cmt; pair = cpair; }
+          if (t < best * 0.9999 || (t <= best * 1.0001 && cbn > bn)) { best = t; bn = cbn; mt = cmt; pair = cpair; streamk = csk; }
         }
       }
     }
-    if (bn == 0) { bn = force_bn ? force_bn : 128; mt = force_mt ? force_mt : 1; pair = force_pair == 2; }
+    if (bn == 0) { bn = force_bn ? force_bn : 128; mt = force_mt ? force_mt : 1; pair = force_pair == 2; streamk = 0; }
   }
+  // small-K specialisation (Cin = 32, 3x3, Cout <= 64, fp16 NHWC out): all 9 taps per stage, resident weights
+  const bool smallk = (cin == 32 && ksize == 3 && cout <= 64 && out_mode == 0 && !force_bn && !force_mt && !force_pair && ((flags >> 28) & 1) == 0);
+  if (smallk) { bn = 64; mt = 1; pair = 0; streamk = 0; }
   YB_REQUIRE(bn == 64 || bn == 128 || bn == 256, "conv: BN=%d", bn);
   YB_REQUIRE(mt == 1 || mt == 2, "conv: MT=%d", mt);
   const int a_im2col = (ksize == 3) ? 1 : ((flags & 1) ? 0 : 1);
@@ -467,7 +835,18 @@ int conv_igemm_forward(const void* x, const void* w, const float* scale, const f
   p.y = y; p.y_ld = y_ld; p.y_ch_off = y_ch_off; p.out_mode = out_mode;
   p.hw = height * width;
   p.dbg = debug_word_device();
+  p.trace = g_conv_trace;
   p.skip = (flags >> 24) & 0xF;
+  p.streamk = streamk;
+  p.sk_base = 0; p.sk_rem = 0; p.ws = nullptr; p.flags = nullptr;
+  if (streamk) {
+    const long long units = static_cast<long long>(p.m_tiles) * p.n_tiles * p.num_kb;
+    YB_REQUIRE(units < (1ll << 31), "conv: stream-K unit count overflows");
+    p.sk_base = static_cast<int>(units / sm_count());
+    p.sk_rem = static_cast<int>(units % sm_count());
+    p.flags = static_cast<unsigned*>(workspace);
+    p.ws = reinterpret_cast<float*>(static_cast<char*>(workspace) + kSkFlagBytes);
+  }
 
   const CUtensorMapSwizzle swz = (bk == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   alignas(64) CUtensorMap ta, tb;
@@ -510,6 +889,29 @@ int conv_igemm_forward(const void* x, const void* w, const float* scale, const f
     if (cr != CUDA_SUCCESS) return fail(YB_ERR_DRIVER, "cuTensorMapEncodeTiled(W) failed (%d)", static_cast<int>(cr));
   }
 
+  if (smallk) {
+    using Cfg = SmallKCfg<64>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      YB_CUDA(cudaFuncSetAttribute(conv_smallk_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+      attr_set = true;
+    }
+    const int tiles = p.m_tiles;
+    const int grid = tiles < sm_count() ? tiles : sm_count();
+    alignas(64) CUtensorMap ty;
+    {
+      const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cout), static_cast<cuuint64_t>(p.m_total)};
+      const cuuint64_t strides[1] = {static_cast<cuuint64_t>(y_ld) * 2};
+      const cuuint32_t box[2] = {64, BM};
+      const cuuint32_t estr[2] = {1, 1};
+      cr = enc_tiled(&ty, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, static_cast<__half*>(y) + y_ch_off, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (cr != CUDA_SUCCESS) return fail(YB_ERR_DRIVER, "cuTensorMapEncodeTiled(Y) failed (%d)", static_cast<int>(cr));
+    }
+    const int tma_store = ((flags >> 29) & 1) ? 0 : 1;     // bit 29: plain per-thread stores (A/B switch)
+    conv_smallk_kernel<64><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, ty, p, tma_store);
+    return check_launch("conv_smallk_kernel");
+  }
   if (pair) {
     if (bk == 64) return dispatch_conv<64, true>(bn, mt, ta, tb, p, stream);
     return dispatch_conv<32, true>(bn, mt, ta, tb, p, stream);

@@ -41,7 +41,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
+#ifdef YB_MBAR_POLL
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+#else
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+#endif
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(bar), "r"(parity)
@@ -53,18 +57,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 // was stuck into a host-mapped debug word (if provided) and traps, which fails the launch.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, volatile int* dbg = nullptr, int code = 0) {
   if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = globaltimer_ns();
+  // The common case resolves within a few polls: keep %globaltimer (a slow read) off that path and only start the
+  // clock once the wait is clearly long.
   uint32_t spins = 0;
+  uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3FFu) == 0 && globaltimer_ns() - t0 > 4000000000ull) {
-      if (dbg != nullptr) {
-        dbg[0] = 0x0BAD0000 | code;
-        dbg[1] = static_cast<int>(blockIdx.x);
-        dbg[2] = static_cast<int>(threadIdx.x);
-        dbg[3] = static_cast<int>(parity);
-        __threadfence_system();
+    if ((++spins & 0xFFFu) == 0) {
+      const uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 4000000000ull) {
+        if (dbg != nullptr) {
+          dbg[0] = 0x0BAD0000 | code;
+          dbg[1] = static_cast<int>(blockIdx.x);
+          dbg[2] = static_cast<int>(threadIdx.x);
+          dbg[3] = static_cast<int>(parity);
+          __threadfence_system();
+        }
+        __trap();
       }
-      __trap();
     }
   }
 }
@@ -96,6 +106,20 @@ __device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorM
 // ---------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, MMA, commit, TMEM loads
 // ---------------------------------------------------------------------------------------------
+// TMA store (shared -> global, bulk-group completion): the epilogue stages a tile in shared memory and one thread ships it.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               :: "l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait() { asm volatile("cp.async.bulk.wait_group %0;" :: "n"(N) : "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {  // whole warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
 }
