@@ -183,6 +183,9 @@ CONV_CASES = [
     (2, 20, 20, 32, 48, 3, ''),            # small-K kernel, Cout < 64 (TMA store clips the channel box)
     (3, 21, 19, 32, 64, 3, 'plainstore'),  # small-K kernel with per-thread stores
     (3, 21, 19, 32, 64, 3, 'generic'),     # same shape through the generic kernel
+    (3, 21, 19, 32, 64, 3, 'im2col'),      # small-K im2col kernel (the default for this shape is the halo-tile kernel)
+    (2, 20, 20, 32, 48, 3, 'im2col'),
+    (2, 48, 40, 32, 64, 3, ''),            # halo-tile kernel, several full tiles per image
     (8, 52, 52, 128, 256, 3, ''),
     (32, 13, 13, 512, 1024, 3, ''),
     (2, 13, 13, 1280, 1024, 3, ''),
@@ -200,7 +203,8 @@ def test_conv_unit_vs_oracle(ops, case):
     ref = O.conv_unit(x, sd, 'u', k, True, True)                      # fp32 oracle on fp32 operands
     scale, shift = ops.bn_fold(*(sd['u.bn.' + n].to(DEV) for n in ('weight', 'bias', 'running_mean', 'running_var')))
     w16 = ops.pack_weight_f16(wt.to(DEV))
-    flags = {'tiled': ops.CONV_A_TILED, 'wide': ops.CONV_WIDE_N, '': 0, 'plainstore': 1 << 29, 'generic': 1 << 28}[fl]
+    flags = {'tiled': ops.CONV_A_TILED, 'wide': ops.CONV_WIDE_N, '': 0, 'plainstore': ops.CONV_C32_IM2COL | ops.CONV_PLAIN_STORE,
+             'generic': ops.CONV_NO_SMALLK, 'im2col': ops.CONV_C32_IM2COL}[fl]
     y = ops.conv_bn_act(x.to(DEV).permute(0, 2, 3, 1).contiguous().half(), w16, scale, shift, 0.1, flags=flags)
     err = rel_err(y.permute(0, 3, 1, 2), ref)
     assert err <= 1e-3, 'rel err %.3e' % err
@@ -253,6 +257,26 @@ def test_conv_streamk_head_fp32_nchw(ops):
     y = ops.conv_bn_act(x.to(DEV).permute(0, 2, 3, 1).contiguous().half(), w16, torch.ones(125, device=DEV), bias.to(DEV), 1.0,
                         out_mode=ops.OUT_F32_NCHW, flags=ops.CONV_FORCE_STREAMK, workspace=ws)
     assert rel_err(y, ref) <= 1e-3
+
+
+@pytest.mark.parametrize('shape', [(2, 32, 24), (3, 22, 18), (1, 208, 208)])
+def test_conv_c32_fused_maxpool(ops, shape):
+    """layers1.2 + the MaxPool2d after it in one launch == the two separate kernels, bit for bit (max of fp16 values)."""
+    b, h, w = shape
+    gen = torch.Generator().manual_seed(h)
+    x16 = torch.randn(b, h, w, 32, generator=gen).half().to(DEV)
+    wt = torch.randn(64, 32, 3, 3, generator=gen) * (2.0 / 288) ** 0.5
+    w16 = ops.pack_weight_f16(wt.to(DEV))
+    scale, shift = (torch.rand(64, generator=gen) + 0.5).to(DEV), (torch.randn(64, generator=gen) * 0.1).to(DEV)
+    full = ops.conv_bn_act(x16, w16, scale, shift, 0.1)
+    two_step = ops.maxpool2x2(full)
+    fused = ops.conv_bn_act(x16, w16, scale, shift, 0.1, flags=ops.CONV_POOL2X2)
+    assert fused.shape == two_step.shape
+    assert torch.equal(fused, two_step)
+    ref = torch.nn.functional.max_pool2d(torch.nn.functional.leaky_relu(
+        torch.nn.functional.conv2d(x16.float().permute(0, 3, 1, 2).cpu(), wt.half().float(), padding=1) * scale.cpu()[None, :, None, None]
+        + shift.cpu()[None, :, None, None], 0.1), 2)
+    assert rel_err(fused.permute(0, 3, 1, 2), ref) <= 1e-3
 
 
 def test_conv_head_fp32_nchw_and_slice(ops):

@@ -153,7 +153,16 @@ class DarknetEngine(object):
         if collect is not None:
             collect['layers1.0(pooled)'] = cur
         x1 = None
+        last1 = self.units1[-1]
         for u, (out, pooled), key in zip(self.units1[1:], p.l1, self._k1[1:]):
+            # layers1.2 (3x3, Cin = 32) has a kernel whose epilogue applies the MaxPool2d that follows it, so the
+            # 208x208x64 activation never goes to HBM; tests that inspect every layer (collect / ref) keep the two steps
+            fuse_pool = (pooled is not None and u is not last1 and collect is None and not ref and u.cin == 32 and u.ksize == 3
+                         and u.cout <= 64 and (conv_flags & (ops.CONV_NO_SMALLK | ops.CONV_C32_IM2COL)) == 0 and conv_flags < 256)
+            if fuse_pool:
+                ops.conv_bn_act(cur, u.w16, u.scale, u.shift, u.slope, out=pooled, flags=conv_flags | ops.CONV_POOL2X2)
+                cur = pooled
+                continue
             conv(u, cur, out)
             if collect is not None:
                 collect[key] = out

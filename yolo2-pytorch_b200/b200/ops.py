@@ -10,6 +10,7 @@ from . import lib as _l
 OUT_F16_NHWC, OUT_F32_NCHW = 0, 1
 CONV_A_TILED, CONV_WIDE_N = 1, 2
 CONV_NO_STREAMK, CONV_FORCE_STREAMK, CONV_NO_SMALLK, CONV_PLAIN_STORE = 8, 1 << 30, 1 << 28, 1 << 29
+CONV_POOL2X2, CONV_C32_IM2COL, CONV_C32_SWAP = 16, 32, 64
 FILTER_THRESHOLD, FILTER_FIX, FILTER_NONE = 0, 1, 2
 
 
@@ -136,7 +137,8 @@ def conv_bn_act(x, w, scale, shift, slope, out=None, out_mode=OUT_F16_NHWC, y_ch
     if cin != wcin:
         raise ValueError('weight Cin %d != %d' % (wcin, cin))
     if out is None:
-        out = (torch.empty(b, h, wd, cout, dtype=torch.float16, device=x.device) if out_mode == OUT_F16_NHWC
+        oh, ow = (h // 2, wd // 2) if (flags & CONV_POOL2X2) else (h, wd)
+        out = (torch.empty(b, oh, ow, cout, dtype=torch.float16, device=x.device) if out_mode == OUT_F16_NHWC
                else torch.empty(b, cout, h, wd, dtype=torch.float32, device=x.device))
     if out_mode == OUT_F16_NHWC:
         _req(out, torch.float16, 'out')

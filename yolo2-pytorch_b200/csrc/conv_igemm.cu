@@ -652,6 +652,228 @@ conv_smallk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 }
 
 // ---------------------------------------------------------------------------------------------
+// Halo-tile kernel for 3x3, Cin = 32 (layers1.2).  The im2col formulations above pull every input pixel through the
+// L2 -> SM path nine times (once per tap) -- 779 MB for 88 MB of input at batch 32, and the clock64 trace
+// (profiles/r01_conv_trace.txt) shows the MMA warp waiting on exactly that.  Here an output tile is a 16 x 8 pixel
+// rectangle and its 18 x 10 x 32ch input halo is fetched ONCE (11.5 KB instead of 72 KB) as four 8-channel planes
+// [pixel][16 B].  In that layout a 3x3 tap is just a shifted window: 8 consecutive pixels of a halo row form one 8 x 16 B
+// core matrix of the un-swizzled K-major operand format, the next output row is +10 pixels (SBO = 160 B) and the second
+// K chunk is the next plane (LBO), so tcgen05.mma reads all nine taps straight out of the halo tile by moving the
+// descriptor's start address by (r * 10 + s) * 16 B.  Weights stay resident (as in the small-K kernel); the epilogue can
+// apply the 2x2 max-pool that follows this layer (lane ^ 1 and lane ^ 8 hold the horizontal / vertical neighbours) and
+// ships the tile with one TMA store, so the un-pooled activation never reaches HBM in inference.
+// ---------------------------------------------------------------------------------------------
+struct C32Params {
+  int batch, height, width, cout;
+  int tiles_w, tiles_h, num_tiles;
+  const float* scale;
+  const float* shift;
+  float slope;
+  int pool;
+  int swap_lbo;   // testing: exchange LBO / SBO in the A descriptor
+  int skip;
+  int* dbg;
+  unsigned long long* trace;
+};
+
+struct C32Cfg {
+  static constexpr int TH = 16, TW = 8, HH = TH + 2, HW = TW + 2;
+  static constexpr int kPlaneData = HH * HW * 16;                 // 2880 B written by one TMA box
+  static constexpr int kPlane = (kPlaneData + 127) / 128 * 128;   // 2944: TMA destinations are 128 B aligned
+  static constexpr int kHalo = 4 * kPlane;                        // 11776
+  static constexpr int kStages = 6;
+  static constexpr int BN = 64;
+  static constexpr int kBTap = BN * 32 * 2;                       // 4 KB
+  static constexpr int kBBytes = 9 * kBTap;                       // 36 KB resident
+  static constexpr int kOutBytes = 128 * 128;                     // staging tile for the TMA store (2 per epilogue group)
+  static constexpr int kAccStages = 4;
+  static constexpr int kThreads = 64 + 256;
+  static constexpr int kSmemBytes = 1024 + kBBytes + 4 * kOutBytes + kStages * kHalo + 2 * BN * 4 + 256;
+};
+
+__global__ void __launch_bounds__(C32Cfg::kThreads, 1)
+conv_c32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                const __grid_constant__ CUtensorMap tmap_y, const C32Params p) {
+  using Cfg = C32Cfg;
+  constexpr int BN = Cfg::BN;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t smem_b = smem_base;
+  const uint32_t smem_o = smem_b + Cfg::kBBytes;
+  const uint32_t smem_h = smem_o + 4 * Cfg::kOutBytes;
+  float* ep_scale = reinterpret_cast<float*>(smem_gen + Cfg::kBBytes + 4 * Cfg::kOutBytes + Cfg::kStages * Cfg::kHalo);
+  float* ep_shift = ep_scale + BN;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ep_shift + BN);
+  const uint32_t bar_full = smem_u32(bars);
+  const uint32_t bar_empty = bar_full + 8 * Cfg::kStages;
+  const uint32_t bar_tfull = bar_empty + 8 * Cfg::kStages;
+  const uint32_t bar_tempty = bar_tfull + 8 * Cfg::kAccStages;
+  const uint32_t bar_w = bar_tempty + 8 * Cfg::kAccStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 2 * Cfg::kAccStages + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < Cfg::kAccStages; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 4); }
+    mbar_init(bar_w, 1);
+    fence_mbar_init();
+    fence_proxy_async_smem();
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_w);
+    tma_prefetch_desc(&tmap_y);
+  }
+  if (warp == 1) { tmem_alloc(smem_u32(tmem_slot), Cfg::kAccStages * BN); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_w, Cfg::kBBytes);
+      for (int t = 0; t < 9; ++t) tma_load_2d(smem_b + t * Cfg::kBTap, &tmap_w, bar_w, t * 32, 0);
+      int stage = 0; uint32_t phase = 0; int tr = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int tw = tile % p.tiles_w;
+        const int rest = tile / p.tiles_w;
+        const int th = rest % p.tiles_h;
+        const int n = rest / p.tiles_h;
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1, p.dbg, 0xB00 | stage);
+        YB_TRACE(0, tr); ++tr;
+        if (p.skip & 1) {
+          mbar_arrive(bar_full + 8 * stage);
+        } else {
+          mbar_arrive_expect_tx(bar_full + 8 * stage, 4 * Cfg::kPlaneData);
+          for (int c = 0; c < 4; ++c)
+            tma_load_4d(smem_h + stage * Cfg::kHalo + c * Cfg::kPlane, &tmap_x, bar_full + 8 * stage, c * 8, tw * Cfg::TW - 1, th * Cfg::TH - 1, n);
+        }
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(BM, BN);
+      const uint32_t lbo = p.swap_lbo ? Cfg::HW * 16 : Cfg::kPlane;
+      const uint32_t sbo = p.swap_lbo ? Cfg::kPlane : Cfg::HW * 16;
+      int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0; int tr = 0;
+      mbar_wait(bar_w, 0, p.dbg, 0xB10);
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1, p.dbg, 0xB20 | acc);
+        YB_TRACE(1, tr); ++tr;
+        mbar_wait(bar_full + 8 * stage, phase, p.dbg, 0xB30 | stage);
+        tc_fence_after();
+        YB_TRACE(1, tr); ++tr;
+        const uint32_t halo = smem_h + stage * Cfg::kHalo;
+        if (!(p.skip & 4)) {
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            const uint32_t win = halo + ((t / 3) * Cfg::HW + (t % 3)) * 16;      // tap (r, s): window shifted by r rows, s pixels
+            const uint64_t bdesc = make_kmajor_desc<64>(smem_b + t * Cfg::kBTap);
+            umma_f16(tmem_base + acc * BN, make_kmajor_desc_noswz(win, lbo, sbo), bdesc, idesc, t != 0);
+            umma_f16(tmem_base + acc * BN, make_kmajor_desc_noswz(win + 2 * Cfg::kPlane, lbo, sbo), bdesc + 2, idesc, 1);
+          }
+        }
+        umma_commit(bar_empty + 8 * stage);
+        umma_commit(bar_tfull + 8 * acc);
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        if (++acc == Cfg::kAccStages) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // Two independent epilogue groups of four warps take alternate tiles: one tile's epilogue is a chain of latencies
+    // (tcgen05.ld, two named barriers, the async-proxy fence, the TMA store issue -- ~1300 cycles even with nothing else
+    // running, see profiles/r01_conv_trace.txt), so two of them in flight roughly double the tile rate.
+    const int q = warp & 3;                 // TMEM lane quarter: tile rows 4q .. 4q+3
+    const int grp = (warp - 2) >> 2;
+    const int gt = (threadIdx.x - 64) & 127;
+    const int et = threadIdx.x - 64;
+    int tr = 0;
+    for (int i = et; i < BN; i += 256) {
+      ep_scale[i] = (i < p.cout) ? __ldg(p.scale + i) : 0.f;
+      ep_shift[i] = (i < p.cout) ? __ldg(p.shift + i) : 0.f;
+    }
+    asm volatile("bar.sync 3, 256;" ::: "memory");
+    const int m = q * 32 + lane;            // tile-local pixel: row m >> 3, column m & 7
+    int srow = m;
+    bool writer = true;
+    if (p.pool) {
+      writer = ((lane & 1) == 0) && ((lane & 8) == 0);
+      srow = (q * 2 + (lane >> 4)) * 4 + ((lane & 7) >> 1);       // pooled pixel: row (m >> 3) / 2, column (m & 7) / 2
+    }
+    int local = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
+      if ((local & 1) != grp) continue;
+      const int acc = local & 3;
+      const uint32_t acc_phase = (local >> 2) & 1;
+      const int tw = tile % p.tiles_w;
+      const int rest = tile / p.tiles_w;
+      const int th = rest % p.tiles_h;
+      const int n = rest / p.tiles_h;
+      mbar_wait(bar_tfull + 8 * acc, acc_phase, p.dbg, 0xB40 | acc);
+      tc_fence_after();
+      if (et == 0) { YB_TRACE(2, tr); ++tr; }
+      uint4 pk[8];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + half * 32, v);
+        tmem_ld_wait();
+        if (half == 1) {                      // both halves are in registers: hand the accumulator back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+        }
+        float f[32];
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 s4 = *reinterpret_cast<const float4*>(ep_scale + half * 32 + j4 * 4);
+          const float4 h4 = *reinterpret_cast<const float4*>(ep_shift + half * 32 + j4 * 4);
+          const float x0 = __uint_as_float(v[j4 * 4 + 0]) * s4.x + h4.x, x1 = __uint_as_float(v[j4 * 4 + 1]) * s4.y + h4.y;
+          const float x2 = __uint_as_float(v[j4 * 4 + 2]) * s4.z + h4.z, x3 = __uint_as_float(v[j4 * 4 + 3]) * s4.w + h4.w;
+          f[j4 * 4 + 0] = x0 > 0.f ? x0 : x0 * p.slope; f[j4 * 4 + 1] = x1 > 0.f ? x1 : x1 * p.slope;
+          f[j4 * 4 + 2] = x2 > 0.f ? x2 : x2 * p.slope; f[j4 * 4 + 3] = x3 > 0.f ? x3 : x3 * p.slope;
+        }
+        if (p.pool) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            f[j] = fmaxf(f[j], __shfl_xor_sync(0xffffffffu, f[j], 1));
+            f[j] = fmaxf(f[j], __shfl_xor_sync(0xffffffffu, f[j], 8));
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          __half2 h0 = __floats2half2_rn(f[g * 8 + 0], f[g * 8 + 1]), h1 = __floats2half2_rn(f[g * 8 + 2], f[g * 8 + 3]);
+          __half2 h2 = __floats2half2_rn(f[g * 8 + 4], f[g * 8 + 5]), h3 = __floats2half2_rn(f[g * 8 + 6], f[g * 8 + 7]);
+          pk[half * 4 + g].x = *reinterpret_cast<uint32_t*>(&h0); pk[half * 4 + g].y = *reinterpret_cast<uint32_t*>(&h1);
+          pk[half * 4 + g].z = *reinterpret_cast<uint32_t*>(&h2); pk[half * 4 + g].w = *reinterpret_cast<uint32_t*>(&h3);
+        }
+      }
+      const uint32_t obuf = smem_o + (grp * 2 + ((local >> 1) & 1)) * Cfg::kOutBytes;
+      if (gt == 0) tma_store_wait_read<1>();      // this group's store from two of its tiles ago has drained the buffer
+      if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (et == 0) { YB_TRACE(2, tr); ++tr; }
+      if (writer) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) st_shared_v4(obuf + srow * 128 + ((c ^ (srow & 7)) << 4), pk[c]);
+      }
+      fence_proxy_async_smem();
+      if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (gt == 0 && !(p.skip & 8)) {
+        if (p.pool) tma_store_4d(&tmap_y, obuf, 0, tw * (Cfg::TW / 2), th * (Cfg::TH / 2), n);
+        else tma_store_4d(&tmap_y, obuf, 0, tw * Cfg::TW, th * Cfg::TH, n);
+        tma_store_commit();
+      }
+      if (et == 0) { YB_TRACE(2, tr); ++tr; }
+    }
+    if (gt == 0) tma_store_wait<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::kAccStages * BN); }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Host side: tensor-map encoding through the driver entry points (no link-time libcuda dependency)
 // ---------------------------------------------------------------------------------------------
 constexpr long long kSkFlagBytes = 4096;          // room for 1024 CTA flags
@@ -731,6 +953,68 @@ static int dispatch_conv(int bn, int mt, const CUtensorMap& ta, const CUtensorMa
   return launch_conv<256, BK, 2, kPair>(ta, tb, p, stream);
 }
 
+static int conv_c32_forward(const void* x, const void* w, const float* scale, const float* shift, float slope, void* y, int batch,
+                            int height, int width, int cout, int x_ld, long long y_ld, int y_ch_off, int pool, int flags, cudaStream_t stream) {
+  using Cfg = C32Cfg;
+  EncodeTiledFn enc_tiled;
+  EncodeIm2colFn enc_im2col;
+  int rc = get_encoders(&enc_tiled, &enc_im2col);
+  if (rc) return rc;
+  YB_REQUIRE(!pool || (height % 2 == 0 && width % 2 == 0), "conv: fused 2x2 max-pool needs even H and W");
+  C32Params p;
+  p.batch = batch; p.height = height; p.width = width; p.cout = cout;
+  p.tiles_w = (width + Cfg::TW - 1) / Cfg::TW;
+  p.tiles_h = (height + Cfg::TH - 1) / Cfg::TH;
+  const long long nt = static_cast<long long>(batch) * p.tiles_w * p.tiles_h;
+  YB_REQUIRE(nt < (1ll << 31), "conv: too many tiles");
+  p.num_tiles = static_cast<int>(nt);
+  p.scale = scale; p.shift = shift; p.slope = slope;
+  p.pool = pool;
+  p.swap_lbo = (flags >> 6) & 1;
+  p.skip = (flags >> 24) & 0xF;
+  p.dbg = debug_word_device();
+  p.trace = g_conv_trace;
+  alignas(64) CUtensorMap tx, tw, ty;
+  CUresult cr;
+  {
+    const cuuint64_t dims[4] = {32, static_cast<cuuint64_t>(width), static_cast<cuuint64_t>(height), static_cast<cuuint64_t>(batch)};
+    const cuuint64_t strides[3] = {static_cast<cuuint64_t>(x_ld) * 2, static_cast<cuuint64_t>(x_ld) * 2 * width,
+                                   static_cast<cuuint64_t>(x_ld) * 2 * width * height};
+    const cuuint32_t box[4] = {8, Cfg::HW, Cfg::HH, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    cr = enc_tiled(&tx, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(YB_ERR_DRIVER, "cuTensorMapEncodeTiled(halo) failed (%d)", static_cast<int>(cr));
+  }
+  {
+    const cuuint64_t dims[2] = {9 * 32, static_cast<cuuint64_t>(cout)};
+    const cuuint64_t strides[1] = {9 * 32 * 2};
+    const cuuint32_t box[2] = {32, 64};
+    const cuuint32_t estr[2] = {1, 1};
+    cr = enc_tiled(&tw, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(YB_ERR_DRIVER, "cuTensorMapEncodeTiled(W) failed (%d)", static_cast<int>(cr));
+  }
+  {
+    const int oh = pool ? height / 2 : height, ow = pool ? width / 2 : width;
+    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(cout), static_cast<cuuint64_t>(ow), static_cast<cuuint64_t>(oh), static_cast<cuuint64_t>(batch)};
+    const cuuint64_t strides[3] = {static_cast<cuuint64_t>(y_ld) * 2, static_cast<cuuint64_t>(y_ld) * 2 * ow, static_cast<cuuint64_t>(y_ld) * 2 * ow * oh};
+    const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(pool ? Cfg::TW / 2 : Cfg::TW), static_cast<cuuint32_t>(pool ? Cfg::TH / 2 : Cfg::TH), 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    cr = enc_tiled(&ty, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, static_cast<__half*>(y) + y_ch_off, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(YB_ERR_DRIVER, "cuTensorMapEncodeTiled(Y) failed (%d)", static_cast<int>(cr));
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    YB_CUDA(cudaFuncSetAttribute(conv_c32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  conv_c32_kernel<<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(tx, tw, ty, p);
+  return check_launch("conv_c32_kernel");
+}
+
 int conv_igemm_forward(const void* x, const void* w, const float* scale, const float* shift, float slope, void* y, int batch,
                        int height, int width, int cin, int cout, int ksize, int x_ld, long long y_ld, int y_ch_off, int out_mode,
                        int flags, void* workspace, long long workspace_bytes, cudaStream_t stream) {
@@ -747,6 +1031,11 @@ int conv_igemm_forward(const void* x, const void* w, const float* scale, const f
   }
   const long long m_total_ll = static_cast<long long>(batch) * height * width;
   YB_REQUIRE(m_total_ll < (1ll << 31) - BM, "conv: too many pixels");
+  const int pool = (flags >> 4) & 1;        // YB_CONV_POOL2X2
+  // 3x3, Cin = 32, Cout <= 64 (layers1.2): halo-tile kernel unless a test asks for one of the im2col kernels
+  if (cin == 32 && ksize == 3 && cout <= 64 && out_mode == 0 && ((flags >> 28) & 1) == 0 && ((flags >> 5) & 1) == 0 && ((flags >> 8) & 0xFFFF) == 0)
+    return conv_c32_forward(x, w, scale, shift, slope, y, batch, height, width, cout, x_ld, y_ld, y_ch_off, pool, flags, stream);
+  if (pool) return fail(YB_ERR_UNSUPPORTED, "conv: YB_CONV_POOL2X2 is only implemented for the Cin = 32 3x3 layer");
   const int bk = (cin % 64 == 0) ? 64 : 32;
   // tile shape: flags may force BLOCK_N (bits 8..17) and the number of M-subtiles (bits 20..21);
   // otherwise pick the (BLOCK_N, M-subtiles) pair with the lowest modelled time.  The model was

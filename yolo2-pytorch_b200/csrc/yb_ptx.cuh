@@ -106,6 +106,15 @@ __device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorM
 // ---------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, MMA, commit, TMEM loads
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      :: "r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               :: "l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 // TMA store (shared -> global, bulk-group completion): the epilogue stages a tile in shared memory and one thread ships it.
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -237,6 +246,13 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
   constexpr uint64_t layout = (kSwizzleBytes == 128) ? 2ull : 4ull;
   constexpr uint64_t sbo = (8ull * kSwizzleBytes) >> 4;
   return static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+// K-major operand WITHOUT swizzle: 8-row x 16-byte core matrices, rows of a core matrix 16 B apart; `lbo_bytes` is the
+// distance between the two 16-byte K chunks of one K = 16 step, `sbo_bytes` the distance between 8-row groups.  Start
+// addresses only need 16 B alignment, which is what lets a 3x3 tap be addressed as a shifted window of a halo tile.
+__device__ __forceinline__ uint64_t make_kmajor_desc_noswz(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(lbo_bytes >> 4) << 16) |
+         (static_cast<uint64_t>(sbo_bytes >> 4) << 32) | (1ull << 46);
 }
 // Instruction descriptor for kind::f16, A/B = fp16 K-major, D = fp32, shape M x N (K = 16).
 __host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n) {
