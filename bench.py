@@ -411,7 +411,8 @@ def run_train(args):
                       'train': {'cross_entropy': '1'}})
     dnn.train(); inference.train()
     anchors = torch.tensor(ANCHORS_HW, dtype=torch.float32)
-    optimizer = torch.optim.Adam(dnn.parameters(), 1e-5, betas=(0.9, 0.999), eps=1e-8)
+    use_graph = (not args.no_graph) and (world == 1 or args.graph_ddp)
+    optimizer = torch.optim.Adam(dnn.parameters(), 1e-5, betas=(0.9, 0.999), eps=1e-8, capturable=use_graph)
     B, H, W = args.batch, args.size, args.size
     g = torch.Generator().manual_seed(200 + rank)
     batches = []
@@ -426,19 +427,31 @@ def run_train(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if use_graph:
+        # the whole iteration (fwd, loss, bwd, all-reduce, optimizer) replayed as one CUDA graph; the batch is copied
+        # into the graph's static input buffers inside the timed region
+        graphed = yb_train.GraphedStep(inference, optimizer, anchors, config, reducer)
+
+        def step(batch):
+            return graphed(batch)
+    else:
+        graphed = None
+
+        def step(batch):
+            return yb_train.iterate(inference, optimizer, anchors, config, batch, reducer)
     for i in range(args.warmup):
-        yb_train.iterate(inference, optimizer, anchors, config, batches[i % 2], reducer)
+        step(batches[i % 2])
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
-    launches0 = ops.launch_count
+    launches0 = graphed.launches if graphed else ops.launch_count
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
     for i in range(args.steps):
-        out = yb_train.iterate(inference, optimizer, anchors, config, batches[i % 2], reducer)
+        out = step(batches[i % 2])
     end.record()
     torch.cuda.synchronize()
     ms = start.elapsed_time(end)
-    launches = ops.launch_count - launches0
+    launches = (graphed.launches if graphed else ops.launch_count) - launches0
     barrier()
     clocks = sampler.stop() if sampler else None
     if world > 1:
@@ -453,7 +466,7 @@ def run_train(args):
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f16', data='synthetic',
                     config=dict(workload='Darknet-19 416x416 batch-%d training step: train-mode fwd + region loss + bwd%s + Adam (BASELINE configs[2])'
                                 % (B, ' + NCCL gradient all-reduce' if world > 1 else ''), global_batch=B * world, per_gpu_batch=B,
-                                parallelism='dp%d' % world, l2='0.6+ GB of activations per step (> L2)'),
+                                parallelism='dp%d' % world, l2='0.6+ GB of activations per step (> L2)', cuda_graph=bool(use_graph)),
                     clocks=clocks, gpu_launches=launches, loss_total=float(out['loss_total'].item()),
                     roofline=dict(bound='tensor', achieved=value * gflop_train / 1e3, peak=peaks['tflops'], unit='TFLOP/s',
                                   frac=value * gflop_train / 1e3 / peaks['tflops'], traffic=None, kernel='whole training step',
@@ -476,6 +489,7 @@ def main():
     ap.add_argument('--mode', default='infer', choices=['infer', 'train'], help='train: secondary measurement of the training step')
     ap.add_argument('--lanes', type=int, default=2, help='batches in flight per GPU (one CUDA stream + activation plan each)')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--graph-ddp', action='store_true', help='train mode, N > 1: capture the step (incl. the NCCL all-reduce) into a CUDA graph too')
     args = ap.parse_args()
     if args.impl == 'reference':
         args.warmup = max(args.warmup, 1)

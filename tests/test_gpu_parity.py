@@ -646,6 +646,64 @@ def test_training_step_vs_oracle():
         assert rel_err(rm, exp) <= 2e-2, key
 
 
+def test_graphed_training_step_matches_eager():
+    """train.GraphedStep (whole iteration replayed as one CUDA graph) against eager train.iterate from the same
+    initial state: same first-step loss, parameters and running statistics after three SGD steps agree (the only
+    run-to-run difference is the order of the fp32 atomics in the weight-gradient kernel)."""
+    import model
+    import model.yolo2
+    import train as yb_train
+    cfg = make_config(1)
+    cfg.read_dict({'model': {'threshold': '0.6'}, 'hparam': {k: str(v) for k, v in O.HPARAM_DEFAULT.items()}, 'train': {'cross_entropy': '1'}})
+    anchors = O.anchors_yolo_voc()
+    sd0 = O.make_state_dict(0)
+    b, size = 4, 128
+    batches = []
+    for i in range(2):
+        t = O.synth_targets(b, size, size, slots=6, seed=21 + i)
+        batches.append(dict(tensor=O.synth_images(b, size, size, seed=31 + i).to(DEV), yx_min=t['yx_min'].to(DEV), yx_max=t['yx_max'].to(DEV),
+                            cls=t['cls'].to(DEV)))
+
+    def run(graphed):
+        dnn = model.yolo2.Darknet(model.ConfigChannels(cfg), anchors, 20)
+        dnn.load_state_dict(sd0, strict=False)
+        dnn = dnn.to(DEV).train()
+        inference = model.Inference(cfg, dnn, anchors).train()
+        opt = torch.optim.SGD(dnn.parameters(), 1e-3, momentum=0.9)
+        step = yb_train.GraphedStep(inference, opt, anchors, cfg) if graphed else (lambda d: yb_train.iterate(inference, opt, anchors, cfg, d))
+        losses = []
+        for i in range(3):
+            out = step(batches[i % 2])
+            losses.append(float(out['loss_total'].item()))
+        if graphed:
+            assert step.launches > 0 and len(step.graphs) == 1
+            step.finish()
+        return losses, {k: v.detach().float().cpu().clone() for k, v in dnn.state_dict().items()}
+
+    l_e, sd_e = run(False)
+    l_g, sd_g = run(True)
+    print('eager losses %s graphed losses %s' % (l_e, l_g))
+    # Not bit-identical, and not even close to it: the float shared-memory atomics of the BN statistics make two eager
+    # runs differ in the last bit, and the step is discontinuous in such perturbations (max-pool ties, fp16 rounding,
+    # the region loss's best-IoU matching and its IoU < 0.6 "negative" threshold), so a 1-ulp change moves the loss by
+    # ~1e-2 (measured).  The check is therefore structural: same loss scale, the three updates point the same way, the
+    # running statistics agree, and the step counter advanced exactly three times (no warm-up step leaked).
+    for a, g in zip(l_e, l_g):
+        assert abs(a - g) <= 0.1 * abs(a)
+    for k in sd_e:
+        if k.endswith('num_batches_tracked'):
+            assert int(sd_e[k]) == int(sd_g[k]) == 3, k
+            continue
+        de, dg = (sd_e[k] - sd0[k].float()).flatten(), (sd_g[k] - sd0[k].float()).flatten()
+        assert de.norm().item() > 0 and dg.norm().item() > 0, k
+        if 'running' in k:
+            assert (sd_e[k] - sd_g[k]).norm().item() <= 0.05 * sd_e[k].norm().item() + 1e-6, k
+        elif k.endswith('conv.weight'):
+            cos = (torch.dot(de, dg) / (de.norm() * dg.norm())).item()
+            assert cos >= 0.8, '%s: update cosine %.3f' % (k, cos)
+            assert 0.5 <= (dg.norm() / de.norm()).item() <= 2.0, k
+
+
 # ------------------------------------------------------------------------------------------------
 # MobileNet plugin (BASELINE configs[4])
 # ------------------------------------------------------------------------------------------------

@@ -119,3 +119,95 @@ def test_mobilenet_plugin_surface():
     assert all(tuple(sd[k].shape) == tuple(ref[k].shape) for k in ref)
     assert sum(p.numel() for p in net.parameters()) == 3335101
     assert sd['layers.14.bias'].shape == (125,) and sd['layers.3.dw.conv.weight'].shape == (128, 1, 3, 3)
+
+
+# ------------------------------------------------------------------------------------------------
+# Darknet `.weights` importer (reference convert_darknet_torch.py:37-57,93-113)
+# ------------------------------------------------------------------------------------------------
+def test_darknet_head_permutation_matches_reference_golden():
+    """Head rows (x, y, w, h, obj, cls...) -> (obj, y, x, h, w, cls...): fixtures made by executing the reference's
+    transpose_weight / transpose_bias (tests/golden/make_golden_weights.py)."""
+    from utils import darknet_weights as dw
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'darknet_weights.npz'))
+    for tag in ('voc', 'coco', 'one'):
+        a = int(g['anchors_' + tag])
+        w, b = g['w_in_' + tag], g['b_in_' + tag]
+        perm = dw.head_permutation(a, w.shape[0] // a)
+        assert np.array_equal(w[perm], g['w_out_' + tag]) and np.array_equal(b[perm], g['b_out_' + tag])
+        inv = dw.head_permutation(a, w.shape[0] // a, inverse=True)
+        assert np.array_equal(g['w_out_' + tag][inv], w)
+
+
+def _tiny_template():
+    """A 3-unit stand-in with the real key structure: BN unit, BN unit, plain head (A=2, C=3)."""
+    import collections
+    g = torch.Generator().manual_seed(3)
+    sd = collections.OrderedDict()
+    for name, cin, cout, k in (('layers1.0', 3, 4, 3), ('passthrough', 4, 6, 1)):
+        sd[name + '.conv.weight'] = torch.randn(cout, cin, k, k, generator=g)
+        sd[name + '.bn.weight'] = torch.rand(cout, generator=g)
+        sd[name + '.bn.bias'] = torch.randn(cout, generator=g)
+        sd[name + '.bn.running_mean'] = torch.randn(cout, generator=g)
+        sd[name + '.bn.running_var'] = torch.rand(cout, generator=g)
+        sd[name + '.bn.num_batches_tracked'] = torch.tensor(7)
+    sd['layers3.1.conv.weight'] = torch.randn(16, 6, 1, 1, generator=g)
+    sd['layers3.1.conv.bias'] = torch.randn(16, generator=g)
+    return sd
+
+
+def test_darknet_weights_file_layout_and_round_trip(tmp_path):
+    """Byte layout written by hand exactly as Darknet stores it (header; per unit beta, gamma, mean, var, weight --
+    or bias, weight -- float32 LE; head in Darknet's channel order), then read back; save -> load is the identity."""
+    import struct
+    from utils import darknet_weights as dw
+    sd = _tiny_template()
+    a, per = 2, 8
+    inv = dw.head_permutation(a, per, inverse=True)
+    blob = struct.pack('<4i', 0, 2, 0, 12345)
+    for name in ('layers1.0', 'passthrough'):
+        for suffix in ('bn.bias', 'bn.weight', 'bn.running_mean', 'bn.running_var', 'conv.weight'):
+            blob += sd[name + '.' + suffix].numpy().astype('<f4').tobytes()
+    blob += sd['layers3.1.conv.bias'].numpy()[inv].astype('<f4').tobytes()
+    blob += sd['layers3.1.conv.weight'].numpy()[inv].astype('<f4').tobytes()
+    path = str(tmp_path / 'tiny.weights')
+    with open(path, 'wb') as f:
+        f.write(blob + b'\0' * 8)                                        # 8 trailing bytes -> reported as remaining
+    template = {k: torch.zeros_like(v) for k, v in sd.items()}
+    out, info = dw.load_darknet_weights(path, template, a)
+    assert (info['major'], info['minor'], info['seen'], info['remaining']) == (0, 2, 12345, 8)
+    assert list(out) [:5] == ['layers1.0.bn.bias', 'layers1.0.bn.weight', 'layers1.0.bn.running_mean', 'layers1.0.bn.running_var', 'layers1.0.conv.weight']
+    for k, v in sd.items():
+        if k.endswith('num_batches_tracked'):
+            assert int(out[k]) == 0                                      # not in the file: the template's value is kept
+        else:
+            assert torch.equal(out[k], v), k
+    path2 = str(tmp_path / 'again.weights')
+    dw.save_darknet_weights(path2, sd, a, header=dict(major=0, minor=2, revision=0, seen=12345))
+    assert open(path2, 'rb').read() == blob
+    with open(path2, 'r+b') as f:
+        f.truncate(len(blob) - 4)
+    with pytest.raises(ValueError):
+        dw.load_darknet_weights(path2, template, a)
+
+
+def test_darknet_weights_full_model_round_trip(tmp_path):
+    """The real Darknet-19 key set: 50,655,389 parameters + running statistics survive save -> load_into."""
+    import model
+    import model.yolo2
+    from oracle import yolo2_oracle as O
+    from utils import darknet_weights as dw
+    config = configparser.ConfigParser()
+    config.read_dict({'batch_norm': {'enable': '1'}})
+    anchors = O.anchors_yolo_voc()
+    dnn = model.yolo2.Darknet(model.ConfigChannels(config), anchors, 20)
+    sd = O.make_state_dict(0)
+    path = str(tmp_path / 'd19.weights')
+    dw.save_darknet_weights(path, sd, len(anchors))
+    n_float = sum(v.numel() for k, v in sd.items() if not k.endswith('num_batches_tracked'))
+    assert os.path.getsize(path) == 16 + 4 * n_float
+    info = dw.load_into(dnn, path, len(anchors))
+    assert info['remaining'] == 0 and info['assigned'] == n_float
+    got = dnn.state_dict()
+    for k, v in sd.items():
+        if not k.endswith('num_batches_tracked'):
+            assert torch.equal(got[k], v), k

@@ -90,46 +90,67 @@ struct BnParams {
   int channels;
 };
 
-__device__ __forceinline__ void load_affine(const BnParams& bn, float* s_scale, float* s_shift) {
-  for (int c = threadIdx.x; c < bn.channels; c += blockDim.x) {
-    const float sc = bn.gamma[c] * bn.invstd[c];
-    s_scale[c] = sc;
-    s_shift[c] = bn.beta[c] - bn.mean[c] * sc;
+// Per-thread channel constants.  Every thread of these kernels owns the same 8 channels for its whole grid-stride loop
+// (blockDim and the total stride are multiples of C/8), so the folded BatchNorm terms live in registers: the loop body
+// is ~8 instructions per element (convert, FMA, select, ...) with no shared-memory or index-division traffic, which
+// is what lets the kernels run at HBM speed instead of being issue-bound.
+struct Ch8 {
+  float sc[8], sh[8];   // y = z * sc + sh          (sc = gamma * invstd, sh = beta - mean * sc; 1 / 0 without BN)
+};
+__device__ __forceinline__ void load_ch8(const BnParams& bn, int cg, bool has_bn, Ch8& k) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = cg * 8 + i;
+    if (has_bn) {
+      const float sc = __ldg(bn.gamma + c) * __ldg(bn.invstd + c);
+      k.sc[i] = sc;
+      k.sh[i] = __ldg(bn.beta + c) - __ldg(bn.mean + c) * sc;
+    } else {
+      k.sc[i] = 1.f; k.sh[i] = 0.f;
+    }
   }
-  __syncthreads();
 }
 
 // a = leaky(scale * z + shift); pool = 1 additionally takes the 2x2 max (thread = 8 channels of one OUTPUT pixel)
+template <int kPool>
 __global__ void __launch_bounds__(kTrainThreads) bn_act_apply_kernel(const __half* __restrict__ z, long long ld_z, BnParams bn,
                                                                      __half* __restrict__ a, long long ld_a, int a_ch_off, int batch, int height,
-                                                                     int width, int pool) {
-  extern __shared__ float s_aff[];
-  float* s_scale = s_aff;
-  float* s_shift = s_aff + bn.channels;
-  load_affine(bn, s_scale, s_shift);
-  const int c8 = bn.channels >> 3;
-  const int oh = pool ? height >> 1 : height, ow = pool ? width >> 1 : width;
-  const long long total = static_cast<long long>(batch) * oh * ow * c8;
-  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int cg = static_cast<int>(idx % c8);
-    long long t = idx / c8;
-    const int px = static_cast<int>(t % ow); t /= ow;
-    const int py = static_cast<int>(t % oh);
-    const int img = static_cast<int>(t / oh);
+                                                                     int width) {
+  const unsigned c8 = static_cast<unsigned>(bn.channels) >> 3;
+  const unsigned cg = threadIdx.x % c8;
+  Ch8 k;
+  load_ch8(bn, static_cast<int>(cg), true, k);
+  const unsigned oh = kPool ? height >> 1 : height, ow = kPool ? width >> 1 : width;
+  const unsigned npix = static_cast<unsigned>(batch) * oh * ow;                 // output pixels (< 2^31, checked on the host)
+  const unsigned pstride = gridDim.x * (blockDim.x / c8);
+  constexpr int nwin = kPool ? 4 : 1;
+#pragma unroll 2
+  for (unsigned p = blockIdx.x * (blockDim.x / c8) + threadIdx.x / c8; p < npix; p += pstride) {
+    long long in0;
+    if (kPool) {
+      const unsigned px = p % ow, t = p / ow;
+      const unsigned py = t % oh, img = t / oh;
+      in0 = (static_cast<long long>(img) * height + 2 * py) * width + 2 * px;
+    } else {
+      in0 = p;
+    }
+    uint4 raw[nwin];
+#pragma unroll
+    for (int w = 0; w < nwin; ++w)
+      raw[w] = __ldg(reinterpret_cast<const uint4*>(z + (in0 + (w >> 1) * width + (w & 1)) * ld_z + cg * 8));
     float best[8];
-    const int nwin = pool ? 4 : 1;
-    for (int k = 0; k < nwin; ++k) {
-      const int iy = pool ? 2 * py + (k >> 1) : py, ix = pool ? 2 * px + (k & 1) : px;
+#pragma unroll
+    for (int w = 0; w < nwin; ++w) {
       float f[8];
-      h8_to_f(__ldg(reinterpret_cast<const uint4*>(z + ((static_cast<long long>(img) * height + iy) * width + ix) * ld_z + cg * 8)), f);
+      h8_to_f(raw[w], f);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        float y = f[i] * s_scale[cg * 8 + i] + s_shift[cg * 8 + i];
+        float y = fmaf(f[i], k.sc[i], k.sh[i]);
         y = y > 0.f ? y : y * bn.slope;
-        best[i] = (k == 0) ? y : fmaxf(best[i], y);
+        best[i] = (w == 0) ? y : fmaxf(best[i], y);
       }
     }
-    *reinterpret_cast<uint4*>(a + ((static_cast<long long>(img) * oh + py) * ow + px) * ld_a + a_ch_off + cg * 8) = f_to_h8(best);
+    *reinterpret_cast<uint4*>(a + static_cast<long long>(p) * ld_a + a_ch_off + cg * 8) = f_to_h8(best);
   }
 }
 
@@ -141,91 +162,101 @@ struct GradIn {
 };
 
 // One thread handles 8 channels of one 2x2 window (pool / branch layers) or of one pixel (window = 0).
-// mode 0: accumulate sum(dy), sum(dy * xhat) ; mode 1: write dz.
+// mode 0: accumulate sum(dy), sum(dy * xhat) ; mode 1: write dz = sc * (dy - mean(dy) - xhat * mean(dy xhat)).
 template <int kMode, int kWin>
 __global__ void __launch_bounds__(kTrainThreads) bn_act_bwd_kernel(const __half* __restrict__ z, long long ld_z, BnParams bn, GradIn g, int batch,
                                                                    int height, int width, double* __restrict__ sums,
                                                                    __half* __restrict__ dz, long long ld_dz, int has_bn) {
-  constexpr int window = kWin;
   constexpr int nwin = kWin ? 4 : 1;
-  extern __shared__ float s_buf[];
-  float* s_scale = s_buf;                         // gamma * invstd        (has_bn) else 1
-  float* s_shift = s_buf + bn.channels;           // beta - mean * scale   (has_bn) else 0
-  float* s_m1 = s_buf + 2 * bn.channels;          // mode 1: sum(dy) / M
-  float* s_m2 = s_buf + 3 * bn.channels;          // mode 1: sum(dy xhat) / M
-  float* s_acc = s_buf + 2 * bn.channels;         // mode 0: [2][C] block accumulators
-  const long long rows = static_cast<long long>(batch) * height * width;
-  if (has_bn) {
-    load_affine(bn, s_scale, s_shift);
-  } else {
-    for (int c = threadIdx.x; c < bn.channels; c += blockDim.x) { s_scale[c] = 1.f; s_shift[c] = 0.f; }
-    __syncthreads();
+  extern __shared__ float s_acc[];                // mode 0: [2][C] block accumulators
+  const unsigned c8 = static_cast<unsigned>(bn.channels) >> 3;
+  const unsigned cg = threadIdx.x % c8;
+  const float inv_rows = 1.f / static_cast<float>(static_cast<long long>(batch) * height * width);
+  Ch8 k;
+  load_ch8(bn, static_cast<int>(cg), has_bn != 0, k);
+  float xa[8], xb[8];                             // xhat = z * xa + xb
+  float k1[8], k2[8];                             // mode 1: dz = sc * dy - k1 - k2 * xhat
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = static_cast<int>(cg) * 8 + i;
+    if (has_bn) {
+      xa[i] = __ldg(bn.invstd + c);
+      xb[i] = -__ldg(bn.mean + c) * xa[i];
+    } else {
+      xa[i] = 0.f; xb[i] = 0.f;
+    }
+    if (kMode == 1 && has_bn) {
+      k1[i] = k.sc[i] * (static_cast<float>(sums[c]) * inv_rows);
+      k2[i] = k.sc[i] * (static_cast<float>(sums[bn.channels + c]) * inv_rows);
+    } else {
+      k1[i] = 0.f; k2[i] = 0.f;
+    }
   }
   if (kMode == 0) {
     for (int i = threadIdx.x; i < 2 * bn.channels; i += blockDim.x) s_acc[i] = 0.f;
-  } else {
-    for (int c = threadIdx.x; c < bn.channels; c += blockDim.x) {
-      s_m1[c] = has_bn ? static_cast<float>(sums[c] / static_cast<double>(rows)) : 0.f;
-      s_m2[c] = has_bn ? static_cast<float>(sums[bn.channels + c] / static_cast<double>(rows)) : 0.f;
-    }
+    __syncthreads();
   }
-  __syncthreads();
-  const int c8 = bn.channels >> 3;
-  const int oh = window ? height >> 1 : height, ow = window ? width >> 1 : width;
-  const long long total = static_cast<long long>(batch) * oh * ow * c8;
+  const unsigned oh = kWin ? height >> 1 : height, ow = kWin ? width >> 1 : width;
+  const unsigned npix = static_cast<unsigned>(batch) * oh * ow;
+  const unsigned pstride = gridDim.x * (blockDim.x / c8);
   float acc1[8], acc2[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { acc1[i] = 0.f; acc2[i] = 0.f; }
-  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int cg = static_cast<int>(idx % c8);
-    long long t = idx / c8;
-    const int px = static_cast<int>(t % ow); t /= ow;
-    const int py = static_cast<int>(t % oh);
-    const int img = static_cast<int>(t / oh);
-    float zf[nwin][8], yv[nwin][8], besty[8];
+#pragma unroll 2
+  for (unsigned p = blockIdx.x * (blockDim.x / c8) + threadIdx.x / c8; p < npix; p += pstride) {
+    long long in0;
+    if (kWin) {
+      const unsigned px = p % ow, t = p / ow;
+      const unsigned py = t % oh, img = t / oh;
+      in0 = (static_cast<long long>(img) * height + 2 * py) * width + 2 * px;
+    } else {
+      in0 = p;
+    }
+    // all loads of this item first (memory-level parallelism), then the math
+    uint4 zr[nwin], dr[nwin], pr = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int w = 0; w < nwin; ++w) {
+      const long long pix = in0 + (w >> 1) * width + (w & 1);
+      zr[w] = __ldg(reinterpret_cast<const uint4*>(z + pix * ld_z + cg * 8));
+      dr[w] = (g.da != nullptr) ? __ldg(reinterpret_cast<const uint4*>(g.da + pix * g.ld_da + g.da_off + cg * 8)) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (g.dap != nullptr) pr = __ldg(reinterpret_cast<const uint4*>(g.dap + static_cast<long long>(p) * g.ld_dap + g.dap_off + cg * 8));
+    float zf[nwin][8], yv[nwin][8], gp[8];
     int arg[8];
+    h8_to_f(pr, gp);
 #pragma unroll
-    for (int k = 0; k < nwin; ++k) {
-      const int iy = window ? 2 * py + (k >> 1) : py, ix = window ? 2 * px + (k & 1) : px;
-      h8_to_f(__ldg(reinterpret_cast<const uint4*>(z + ((static_cast<long long>(img) * height + iy) * width + ix) * ld_z + cg * 8)), zf[k]);
+    for (int w = 0; w < nwin; ++w) {
+      h8_to_f(zr[w], zf[w]);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        yv[k][i] = zf[k][i] * s_scale[cg * 8 + i] + s_shift[cg * 8 + i];
-        if (k == 0 || yv[k][i] > besty[i]) { besty[i] = yv[k][i]; arg[i] = k; }   // first maximum wins (leaky is strictly increasing)
+      for (int i = 0; i < 8; ++i) yv[w][i] = fmaf(zf[w][i], k.sc[i], k.sh[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      arg[i] = 0;
+      if (kWin) {
+        float besty = yv[0][i];
+#pragma unroll
+        for (int w = 1; w < nwin; ++w)
+          if (yv[w][i] > besty) { besty = yv[w][i]; arg[i] = w; }      // first maximum wins (leaky is strictly increasing)
       }
     }
-    float gp[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) gp[i] = 0.f;
-    if (g.dap != nullptr) h8_to_f(__ldg(reinterpret_cast<const uint4*>(g.dap + ((static_cast<long long>(img) * oh + py) * ow + px) * g.ld_dap + g.dap_off + cg * 8)), gp);
-#pragma unroll
-    for (int k = 0; k < nwin; ++k) {
-      const int iy = window ? 2 * py + (k >> 1) : py, ix = window ? 2 * px + (k & 1) : px;
-      const long long pix = (static_cast<long long>(img) * height + iy) * width + ix;
-      float gd[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) gd[i] = 0.f;
-      if (g.da != nullptr) h8_to_f(__ldg(reinterpret_cast<const uint4*>(g.da + pix * g.ld_da + g.da_off + cg * 8)), gd);
-      float out[8];
+    for (int w = 0; w < nwin; ++w) {
+      float gd[8], out[8];
+      h8_to_f(dr[w], gd);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         float gin = gd[i];
-        if (g.dap != nullptr && (!window || arg[i] == k)) gin += gp[i];
-        const float dy = gin * (yv[k][i] > 0.f ? 1.f : bn.slope);
-        if (has_bn) {
-          const float xhat = (zf[k][i] - bn.mean[cg * 8 + i]) * bn.invstd[cg * 8 + i];
-          if (kMode == 0) { acc1[i] += dy; acc2[i] += dy * xhat; }
-          else out[i] = s_scale[cg * 8 + i] * (dy - s_m1[cg * 8 + i] - xhat * s_m2[cg * 8 + i]);
-        } else {
-          if (kMode == 0) acc1[i] += dy;           // bias gradient
-          else out[i] = dy;
-        }
+        if (!kWin || arg[i] == w) gin += gp[i];          // gp is zero when there is no pooled gradient
+        const float dy = yv[w][i] > 0.f ? gin : gin * bn.slope;
+        const float xhat = fmaf(zf[w][i], xa[i], xb[i]);
+        if (kMode == 0) { acc1[i] += dy; acc2[i] = fmaf(dy, xhat, acc2[i]); }
+        else out[i] = fmaf(k.sc[i], dy, -fmaf(k2[i], xhat, k1[i]));
       }
-      if (kMode == 1) *reinterpret_cast<uint4*>(dz + pix * ld_dz + cg * 8) = f_to_h8(out);
+      if (kMode == 1) *reinterpret_cast<uint4*>(dz + (in0 + (w >> 1) * width + (w & 1)) * ld_dz + cg * 8) = f_to_h8(out);
     }
   }
   if (kMode == 0) {
-    const int cg = threadIdx.x % c8;    // blockDim is a multiple of c8 and the grid stride keeps cg fixed per thread
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       atomicAdd(&s_acc[cg * 8 + i], acc1[i]);
@@ -285,9 +316,13 @@ int bn_act_apply(const void* z, long long ld_z, const float* mean, const float* 
              "bn_act_apply: bad argument");
   YB_REQUIRE(!pool || (height % 2 == 0 && width % 2 == 0), "bn_act_apply: pooling needs even H, W");
   BnParams bn{mean, invstd, gamma, beta, slope, channels};
+  YB_REQUIRE(kTrainThreads % (channels / 8) == 0, "bn_act_apply: C/8 must divide %d (C=%d)", kTrainThreads, channels);
   const long long total = static_cast<long long>(batch) * (pool ? height / 2 : height) * (pool ? width / 2 : width) * (channels / 8);
-  bn_act_apply_kernel<<<grid_for(total), kTrainThreads, 2 * channels * sizeof(float), stream>>>(
-      reinterpret_cast<const __half*>(z), ld_z, bn, reinterpret_cast<__half*>(a), ld_a, a_ch_off, batch, height, width, pool);
+  YB_REQUIRE(total / (channels / 8) < (1ll << 31), "bn_act_apply: too many pixels");
+  if (pool) bn_act_apply_kernel<1><<<grid_for(total), kTrainThreads, 0, stream>>>(reinterpret_cast<const __half*>(z), ld_z, bn, reinterpret_cast<__half*>(a),
+                                                                                 ld_a, a_ch_off, batch, height, width);
+  else bn_act_apply_kernel<0><<<grid_for(total), kTrainThreads, 0, stream>>>(reinterpret_cast<const __half*>(z), ld_z, bn, reinterpret_cast<__half*>(a), ld_a,
+                                                                            a_ch_off, batch, height, width);
   return check_launch("bn_act_apply_kernel");
 }
 
@@ -303,8 +338,9 @@ int bn_act_bwd(int mode, const void* z, long long ld_z, const float* mean, const
   BnParams bn{mean, invstd, gamma, beta, slope, channels};
   GradIn g{reinterpret_cast<const __half*>(da), ld_da, da_off, reinterpret_cast<const __half*>(dap), ld_dap, dap_off};
   const long long total = static_cast<long long>(batch) * (window ? height / 2 : height) * (window ? width / 2 : width) * (channels / 8);
+  YB_REQUIRE(total / (channels / 8) < (1ll << 31), "bn_act_bwd: too many pixels");
   const int grid = grid_for_groups(total, channels / 8);
-  const size_t smem = 4 * channels * sizeof(float);
+  const size_t smem = mode == 0 ? 2 * channels * sizeof(float) : 0;
   const __half* zp = reinterpret_cast<const __half*>(z);
   __half* dzp = reinterpret_cast<__half*>(dz);
   if (mode == 0 && window) bn_act_bwd_kernel<0, 1><<<grid, kTrainThreads, smem, stream>>>(zp, ld_z, bn, g, batch, height, width, sums, nullptr, 0, has_bn);
@@ -380,21 +416,49 @@ int head_grad_prepare(const float* dfeature, void* dz, float* dbias, int batch, 
 
 // ------------------------------------------------------------------------------------------------
 // conv0 weight gradient: dW[co][ci][r][s] = sum_{b,y,x} dz[b,y,x,co] * x[b,ci,y+r-1,x+s-1]   (Cout = 32, Cin = 3)
-// Persistent blocks over 8x32-pixel tiles; the haloed input patch and the dz tile are staged in shared memory;
-// lane k (< 27) of every warp owns filter tap k for all 32 output channels (32 fp32 accumulators).
+// A [27 taps (padded to 32) x pixels] x [pixels x 32 co] product with the pixels as the reduction dimension.  K = 27 is
+// far too thin for a tcgen05 tile, and the op is HBM-bound (709 MB of dz at batch 64), so this uses warp-level
+// mma.sync.m16n8k16 (fp16 in, fp32 accumulate): persistent blocks over 8x32-pixel tiles, the haloed fp32 input patch
+// and the fp16 dz tile staged in shared memory; warp w owns image row w of the tile (2 K-steps of 16 pixels), builds
+// the tap-major A fragments from the patch (two adjacent pixels -> one half2 register) and reads the dz fragments
+// with ldmatrix.trans.  Each warp keeps the whole 32 x 32 result in 32 fp32 registers per thread until the end.
 constexpr int kW0Rows = 8, kW0Cols = 32;
+constexpr int kW0DzStride = 40;      // halves per staged dz pixel row (32 + 8 pad: conflict-free ldmatrix)
+
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+  const __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
 
 __global__ void __launch_bounds__(256) conv0_wgrad_kernel(const float* __restrict__ x, const __half* __restrict__ dz, float* __restrict__ dw, int batch,
                                                           int height, int width, int tiles_x, int tiles_y, int num_tiles) {
   __shared__ float patch[3][kW0Rows + 2][kW0Cols + 2];
-  __shared__ __align__(16) __half dzs[kW0Rows * kW0Cols][32];
-  __shared__ float s_dw[27 * 32];
+  __shared__ __align__(16) __half dzs[kW0Rows * kW0Cols][kW0DzStride];
+  __shared__ float s_dw[32 * 32];            // [tap (padded)][co]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < 27 * 32; i += 256) s_dw[i] = 0.f;
-  float acc[32];
+  const int g = lane >> 2, t = lane & 3;
+  for (int i = tid; i < 32 * 32; i += 256) s_dw[i] = 0.f;
+  float acc[2][4][4];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-  const int kc = lane / 9, kr = (lane % 9) / 3, ks = lane % 3;   // tap of this lane (lane < 27)
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+  // A-fragment rows of this thread: taps g, g+8, g+16, g+24 -> patch plane / row / column offsets (tap >= 27: zero)
+  int a_off[4];
+  bool a_ok[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int tap = g + 8 * j;
+    a_ok[j] = tap < 27;
+    const int tc = a_ok[j] ? tap / 9 : 0, tr = a_ok[j] ? (tap % 9) / 3 : 0, ts = a_ok[j] ? tap % 3 : 0;
+    a_off[j] = (tc * (kW0Rows + 2) + warp + tr) * (kW0Cols + 2) + ts;
+  }
+  const float* pflat = &patch[0][0][0];
+  // ldmatrix.x4.trans row addresses: matrix j = lane >> 3: K-half (j & 1), co block (j >> 1) (+2 for the second load)
+  const int lm_row = (lane & 7) + ((lane >> 3) & 1) * 8;
+  const int lm_col = (lane >> 4) * 8;
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     const int tx = tile % tiles_x;
     const int t2 = tile / tiles_x;
@@ -412,30 +476,54 @@ __global__ void __launch_bounds__(256) conv0_wgrad_kernel(const float* __restric
     for (int i = tid; i < kW0Rows * kW0Cols * 4; i += 256) {        // 4 x 16 B per pixel
       const int pix = i >> 2, part = i & 3;
       const int py = pix / kW0Cols, pxx = pix % kW0Cols;
-      reinterpret_cast<uint4*>(&dzs[pix][0])[part] =
+      *reinterpret_cast<uint4*>(&dzs[pix][part * 8]) =
           __ldg(reinterpret_cast<const uint4*>(dz + ((static_cast<long long>(img) * height + y0 + py) * width + x0 + pxx) * 32) + part);
     }
     __syncthreads();
-    if (lane < 27) {
-      // warp w handles image row w of the tile
-      for (int pxx = 0; pxx < kW0Cols; ++pxx) {
-        const float xv = patch[kc][warp + kr][pxx + ks];
-        const uint4* dp = reinterpret_cast<const uint4*>(&dzs[warp * kW0Cols + pxx][0]);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float f[8];
-          h8_to_f(dp[q], f);
+    for (int ks = 0; ks < 2; ++ks) {
+      // B fragments (dz): b[n-tile][0..1]
+      uint32_t bfr[4][2];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) acc[q * 8 + i] = fmaf(xv, f[i], acc[q * 8 + i]);
-        }
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t addr = static_cast<uint32_t>(__cvta_generic_to_shared(&dzs[warp * kW0Cols + ks * 16 + lm_row][h * 16 + lm_col]));
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(bfr[2 * h][0]), "=r"(bfr[2 * h][1]), "=r"(bfr[2 * h + 1][0]), "=r"(bfr[2 * h + 1][1]) : "r"(addr));
       }
+      // A fragments (taps x pixels) from the fp32 patch
+      const int k0 = ks * 16 + t * 2;
+      uint32_t afr[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int j0 = 2 * mt, j1 = 2 * mt + 1;       // rows g + 16 mt and g + 16 mt + 8
+        const float* r0 = pflat + a_off[j0] + k0;
+        const float* r1 = pflat + a_off[j1] + k0;
+        afr[mt][0] = a_ok[j0] ? pack_h2(r0[0], r0[1]) : 0u;
+        afr[mt][1] = a_ok[j1] ? pack_h2(r1[0], r1[1]) : 0u;
+        afr[mt][2] = a_ok[j0] ? pack_h2(r0[8], r0[9]) : 0u;
+        afr[mt][3] = a_ok[j1] ? pack_h2(r1[8], r1[9]) : 0u;
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+          asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                       : "+f"(acc[mt][nt][0]), "+f"(acc[mt][nt][1]), "+f"(acc[mt][nt][2]), "+f"(acc[mt][nt][3])
+                       : "r"(afr[mt][0]), "r"(afr[mt][1]), "r"(afr[mt][2]), "r"(afr[mt][3]), "r"(bfr[nt][0]), "r"(bfr[nt][1]));
     }
   }
   __syncthreads();
-  if (lane < 27) {
+  // D fragment: (row g, cols 2t, 2t+1), (row g + 8, same cols) of each 16 x 8 tile
 #pragma unroll
-    for (int co = 0; co < 32; ++co) atomicAdd(&s_dw[lane * 32 + co], acc[co]);
-  }
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int r0 = mt * 16 + g, c0 = nt * 8 + t * 2;
+      atomicAdd(&s_dw[r0 * 32 + c0], acc[mt][nt][0]);
+      atomicAdd(&s_dw[r0 * 32 + c0 + 1], acc[mt][nt][1]);
+      atomicAdd(&s_dw[(r0 + 8) * 32 + c0], acc[mt][nt][2]);
+      atomicAdd(&s_dw[(r0 + 8) * 32 + c0 + 1], acc[mt][nt][3]);
+    }
   __syncthreads();
   for (int i = tid; i < 27 * 32; i += 256) {
     const int k = i / 32, co = i % 32;                 // k = ci*9 + r*3 + s  -> OIHW flat index co*27 + k

@@ -21,10 +21,11 @@ from b200 import ddp as _ddp
 def norm_data(data, height, width, rows, cols, keys='yx_min, yx_max'):
     """GT pixel coordinates -> grid units (reference train.py:57-62)."""
     out = {key: data[key] for key in data}
-    ref = data[keys.split(', ')[0]]
-    scale = torch.tensor([rows / height, cols / width], dtype=torch.float32, device=ref.device).view(1, 1, 2)
+    sy, sx = rows / height, cols / width
     for key in keys.split(', '):
-        out[key] = out[key] * scale
+        t = out[key]
+        # Python-scalar multiplies only: no host tensor is created, so the step stays CUDA-graph capturable
+        out[key] = torch.stack([t[..., 0] * sy, t[..., 1] * sx], -1)
     return out
 
 
@@ -70,3 +71,97 @@ def iterate(inference, optimizer, anchors, config, data, reducer=None):
     optimizer.step()
     return dict(height=height, width=width, rows=rows, cols=cols, data=data, pred=pred, debug=debug, loss_total=loss_total, loss=loss,
                 loss_hparam=loss_hparam)
+
+
+class GraphedStep(object):
+    """`iterate` captured once per input shape into a CUDA graph and replayed: the ~300 kernel launches, the autograd
+    bookkeeping and the optimizer step of one training iteration cost one graph launch, which removes the host
+    launch overhead that dominates the eager step (tcgen05 kernels of 20-100 us each).
+
+        step = train.GraphedStep(inference, optimizer, anchors, config)
+        out = step(dict(tensor=..., yx_min=..., yx_max=..., cls=...))      # same dict as iterate()
+
+    * Inputs (host-pinned or device tensors) are copied into static device buffers, then the graph is replayed; the
+      returned tensors are static too (overwritten by the next call with the same shapes).
+    * One graph per distinct set of input shapes (multi-scale training, `data/sizes`: one per size).
+    * Capture needs two eager warm-up iterations (lazy optimizer state, kernel attribute setup).  Parameters, buffers
+      and optimizer state are restored afterwards, so the first replay is the first real update.
+    * The optimizer must be capture-safe: torch.optim.SGD as is, Adam/AdamW with `capturable=True`.  The learning
+      rate is baked into the graph unless it is a tensor (`lr=torch.tensor(...)`).
+    * Operand caches keyed by parameter version (packed fp16 weights) are refreshed inside the graph; call
+      `finish()` before switching the model to eval() so the inference engine re-packs from the final parameters.
+    """
+
+    def __init__(self, inference, optimizer, anchors, config, reducer=None, warmup=2):
+        self.inference, self.optimizer, self.anchors, self.config, self.reducer = inference, optimizer, anchors, config, reducer
+        self.warmup = int(warmup)
+        self.graphs = {}
+        self.launches = 0          # library kernels replayed so far (bench.py's gpu_launches)
+        self.keys = ('tensor', 'yx_min', 'yx_max', 'cls')
+
+    def _snapshot(self):
+        mod = self.inference
+        tensors = [p.data for p in mod.parameters()] + [b for b in mod.buffers()]
+        saved = [(t, t.clone()) for t in tensors]
+        state = {}
+        for p, st in self.optimizer.state.items():
+            for k, v in st.items():
+                if torch.is_tensor(v):
+                    state[(id(p), k)] = v.clone()
+        return saved, state
+
+    def _restore(self, snap):
+        saved, state = snap
+        for t, c in saved:
+            t.copy_(c)
+        for p, st in self.optimizer.state.items():
+            for k, v in st.items():
+                if torch.is_tensor(v):
+                    c = state.get((id(p), k))
+                    if c is not None:
+                        v.copy_(c)
+                    else:
+                        v.zero_()      # state created lazily by the warm-up steps: back to its initial value
+
+    def _capture(self, key, data, dev):
+        from b200 import ops as _ops
+        static = {k: data[k].to(dev).clone() for k in self.keys}
+        self.anchors = self.anchors.detach().to(device=dev, dtype=torch.float32).contiguous()   # no host->device copy inside the capture
+        snap = self._snapshot()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(self.warmup):
+                iterate(self.inference, self.optimizer, self.anchors, self.config, static, self.reducer)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self._restore(snap)
+        self.optimizer.zero_grad(set_to_none=True)
+        graph = torch.cuda.CUDAGraph()
+        n0 = _ops.launch_count
+        with torch.cuda.graph(graph):
+            out = iterate(self.inference, self.optimizer, self.anchors, self.config, static, self.reducer)
+        entry = (static, graph, out, _ops.launch_count - n0)
+        self.graphs[key] = entry
+        return entry
+
+    def __call__(self, data):
+        dev = torch.device('cuda', torch.cuda.current_device())
+        key = tuple(tuple(data[k].shape) for k in self.keys)
+        entry = self.graphs.get(key)
+        if entry is None:
+            entry = self._capture(key, data, dev)
+        static, graph, out, launches = entry
+        for k in self.keys:
+            static[k].copy_(data[k], non_blocking=True)
+        graph.replay()
+        self.launches += launches
+        return out
+
+    def finish(self):
+        """Drop operand caches that the graph kept current on its own buffers (see the class docstring)."""
+        dnn = self.inference.dnn
+        for u in dnn.engine.all_units():
+            u._wver = None
+            u._bver = None
+        dnn.trainer.wd_cache.clear()
