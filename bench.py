@@ -230,7 +230,7 @@ def profile_layers(pipe, steps):
     step_events = []
     try:
         for _ in range(steps):
-            torch.cuda._sleep(int(8e6))
+            torch.cuda._sleep(int(6e7))   # ~30 ms head start: the host enqueues the whole eager step while the GPU spins
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
             pipe._forward(pipe.x[0])
@@ -254,7 +254,8 @@ def profile_layers(pipe, steps):
     conv_ms = sum(l['us'] for l in layers) / 1e3
     conv_flops = sum(records[i][2] for i in range(per_step))
     step_ms = sum(s.elapsed_time(e) for s, e in step_events) / steps
-    return dict(layers=layers, others=others, conv_ms=conv_ms, conv_flops=conv_flops, eager_step_ms=step_ms, launches=per_step)
+    kernels_ms = conv_ms + sum(v['us_per_step'] for v in others.values()) / 1e3
+    return dict(layers=layers, others=others, conv_ms=conv_ms, conv_flops=conv_flops, eager_step_ms=step_ms, kernels_ms=kernels_ms, launches=per_step)
 
 
 def run_b200(args):
@@ -315,29 +316,41 @@ def run_b200(args):
     value = world * B * args.steps / (ms / 1e3)
 
     # ---- end to end through the serving API: pinned host batches in, detection arrays out ----
-    for i in range(max(4, args.warmup)):
-        pipe.load(i % slots, host[i % 2]); pipe.run(i % slots, fetch=True)
-    barrier()
-    s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s2.record(cur)
-    pipe.start_after(s2)
-    pipe.load(0, host[0])
-    for i in range(args.steps):
-        if i + 1 < args.steps:
-            pipe.load((i + 1) % slots, host[(i + 1) % 2])
-        pipe.run(i % slots, fetch=True)
-    pipe.wait_all(cur)
-    e2.record(cur)
-    torch.cuda.synchronize()
-    ms_e2e = s2.elapsed_time(e2)
-    barrier()
-    if world > 1:
-        t = torch.tensor([ms_e2e], device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t.item())
+    def measure_e2e(pp, host_batches):
+        for i in range(max(4, args.warmup)):
+            pp.load(i % slots, host_batches[i % 2]); pp.run(i % slots, fetch=True)
+        barrier()
+        s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s2.record(cur)
+        pp.start_after(s2)
+        pp.load(0, host_batches[0])
+        for i in range(args.steps):
+            if i + 1 < args.steps:
+                pp.load((i + 1) % slots, host_batches[(i + 1) % 2])
+            pp.run(i % slots, fetch=True)
+        pp.wait_all(cur)
+        e2.record(cur)
+        torch.cuda.synchronize()
+        t_ms = s2.elapsed_time(e2)
+        barrier()
+        if world > 1:
+            t = torch.tensor([t_ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_ms = float(t.item())
+        return t_ms
+
+    ms_e2e = measure_e2e(pipe, host)
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
     h2d = B * 3 * H * W * 4
     d2h = pipe.result_bytes()
+    # same call with the frames as the reference's data loader holds them before ToTensor (uint8 HWC, detect.py:142-146):
+    # the first conv kernel applies the 1/255 and the layout change, so the host->device copy is 4x smaller
+    pipe_u8 = DetectPipeline(inference, config, B, H, W, slots=slots, lanes=args.lanes, use_graph=not args.no_graph, uint8_input=True).prepare()
+    host_u8 = [torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, generator=g).pin_memory() for _ in range(2)]
+    ms_e2e_u8 = measure_e2e(pipe_u8, host_u8)
+    e2e_u8 = dict(value=world * B * args.steps / (ms_e2e_u8 / 1e3), unit='images/s', h2d_bytes_per_step=B * 3 * H * W, d2h_bytes_per_step=d2h,
+                  ms_per_step=ms_e2e_u8 / args.steps, input='uint8 NHWC frames (ToTensor fused into the first conv kernel)')
+    del pipe_u8
 
     if rank != 0:
         if world > 1:
@@ -353,7 +366,7 @@ def run_b200(args):
                     traffic=38.7e6, traffic_source='profiles/r01_ncu_conv_full.md: (dram read 641.9 MB + write 208.8 MB) / 22 launches, B=32',
                     kernel='conv_igemm_kernel (22 launches/step)', peak_source=peaks['source'],
                     flops_per_launch=prof['conv_flops'] / prof['launches'], us_per_launch=prof['conv_ms'] * 1e3 / prof['launches'],
-                    share_of_step=prof['conv_ms'] / prof['eager_step_ms'],
+                    share_of_step=prof['conv_ms'] / prof['kernels_ms'],
                     whole_step_frac=(B * GFLOP_PER_IMAGE_416 / 1e3) / (graph_step_ms / 1e3) / peaks['tflops'])
     os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
     with open(os.path.join(ROOT, 'gpurun_out', 'bench_layers.json'), 'w') as f:
@@ -370,7 +383,9 @@ def run_b200(args):
                             global_batch=B * world, per_gpu_batch=B, parallelism='replicas x%d (images shard, no collective)' % world,
                             l2='inputs rotate over %d resident batches (%.0f MB > 126 MB L2); ~0.6 GB of activations streamed per step' % (slots, slots * h2d / 1e6),
                             cuda_graph=not args.no_graph, lanes=pipe.lanes, weights='random-init (kaiming) + random BN statistics'),
-                clocks=clocks, e2e=dict(value=e2e_value, unit='images/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=ms_e2e / args.steps),
+                clocks=clocks, e2e=dict(value=e2e_value, unit='images/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=ms_e2e / args.steps,
+                         input='fp32 NCHW tensors (the reference forward() signature)'),
+                e2e_u8=e2e_u8,
                 gpu_launches=graph_launches, roofline=roofline, cpu_baseline=cpu, wall_ms=wall_ms)
     print(json.dumps(line))
     if world > 1:
@@ -412,7 +427,7 @@ def run_train(args):
     dnn.train(); inference.train()
     anchors = torch.tensor(ANCHORS_HW, dtype=torch.float32)
     use_graph = (not args.no_graph) and (world == 1 or args.graph_ddp)
-    optimizer = torch.optim.Adam(dnn.parameters(), 1e-5, betas=(0.9, 0.999), eps=1e-8, capturable=use_graph)
+    optimizer = torch.optim.Adam(dnn.parameters(), 1e-5, betas=(0.9, 0.999), eps=1e-8, capturable=use_graph, fused=True)
     B, H, W = args.batch, args.size, args.size
     g = torch.Generator().manual_seed(200 + rank)
     batches = []

@@ -492,7 +492,7 @@ def test_conv_wgrad_vs_torch(ops, case):
     dw_krsc = torch.empty(cout, k, k, cin, dtype=torch.float32, device=DEV)
     ops.call('yb_conv_wgrad', x.to(DEV), dz.to(DEV), dw_krsc, b, h, h, cin, cout, k, cin, dz_ld)
     dw = torch.empty(cout, cin, k, k, dtype=torch.float32, device=DEV)
-    ops.call('yb_unpack_wgrad', dw_krsc, dw, cout, cin, k)
+    ops.call('yb_unpack_wgrad', dw_krsc, dw, cout, cin, k, 1.0)
     err = rel_err(dw, ref)
     assert err <= 2e-3, 'rel err %.3e' % err
 
@@ -565,14 +565,14 @@ def test_training_unit_forward_backward(ops, case):
     args = (zd, cout, mean, invstd, gd, bd, 0.1, da, 0 if da is None else cout, 0, dap, 0 if dap is None else cout, 0, b, h, h, cout, window, sums)
     ops.call('yb_bn_act_bwd', 0, *args, None, 0, 1)
     dgamma, dbeta = torch.empty(cout, device=DEV), torch.empty(cout, device=DEV)
-    ops.call('yb_bn_param_grad', sums, cout, dgamma, dbeta, 0)
+    ops.call('yb_bn_param_grad', sums, cout, dgamma, dbeta, 0, 1.0)
     dz = torch.empty(b, h, h, cout, dtype=torch.float16, device=DEV)
     ops.call('yb_bn_act_bwd', 1, *args, dz, cout, 1)
     assert rel_err(dgamma, gr.grad) <= 5e-3 and rel_err(dbeta, br.grad) <= 5e-3
     dw_krsc = torch.empty(cout, k, k, cin, dtype=torch.float32, device=DEV)
     ops.call('yb_conv_wgrad', xd, dz, dw_krsc, b, h, h, cin, cout, k, cin, cout)
     dw = torch.empty(cout, cin, k, k, dtype=torch.float32, device=DEV)
-    ops.call('yb_unpack_wgrad', dw_krsc, dw, cout, cin, k)
+    ops.call('yb_unpack_wgrad', dw_krsc, dw, cout, cin, k, 1.0)
     # gradients downstream of the leaky kink: an activation within fp16 rounding of 0 flips its slope (1 vs 0.1) for that
     # single element, so dW / dx are compared in relative L2 (robust to isolated flips) with a loose max-norm bound
     assert rel_l2(dw, wr.grad) <= 5e-3 and rel_err(dw, wr.grad) <= 5e-2

@@ -39,12 +39,12 @@ SIGNATURES = {
     'yb_bn_act_apply': [P, c_longlong, P, P, P, P, c_float, P, c_longlong, c_int, c_int, c_int, c_int, c_int, c_int, P],
     'yb_bn_act_bwd': [c_int, P, c_longlong, P, P, P, P, c_float, P, c_longlong, c_int, P, c_longlong, c_int, c_int, c_int, c_int, c_int, c_int,
                       P, P, c_longlong, c_int, P],
-    'yb_bn_param_grad': [P, c_int, P, P, c_int, P],
+    'yb_bn_param_grad': [P, c_int, P, P, c_int, c_float, P],
     'yb_reorg_bwd_f16': [P, c_longlong, c_int, P, c_int, c_int, c_int, c_int, P],
     'yb_head_grad_prepare': [P, P, P, c_int, c_int, c_int, c_int, P],
     'yb_conv0_wgrad': [P, P, P, c_int, c_int, c_int, P],
     'yb_conv_wgrad': [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P],
-    'yb_unpack_wgrad': [P, P, c_int, c_int, c_int, P],
+    'yb_unpack_wgrad': [P, P, c_int, c_int, c_int, c_float, P],
     'yb_mb_conv0_bn_relu_fwd': [P, P, P, P, P, c_int, c_int, c_int, P],
     'yb_dwconv3x3_bn_relu_fwd': [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P],
 }

@@ -169,8 +169,8 @@ class DarknetTrainer(object):
         dw_krsc = torch.empty(cout, k, k, cin, dtype=torch.float32, device=dz.device)
         ops.call('yb_conv_wgrad', ain, dz, dw_krsc, b, hh, ww, cin, cout, k, ain.shape[-1], dz.shape[-1])
         dw = torch.empty(cout, cin, k, k, dtype=torch.float32, device=dz.device)
-        ops.call('yb_unpack_wgrad', dw_krsc, dw, cout, cin, k)
-        grads[name + '.conv.weight'] = dw.mul_(1.0 / self.grad_scale)
+        ops.call('yb_unpack_wgrad', dw_krsc, dw, cout, cin, k, 1.0 / self.grad_scale)      # layout change + inverse loss scale
+        grads[name + '.conv.weight'] = dw
         self._emit(name + '.conv.weight', grads)
 
     def _unit_backward(self, key, s, b, grads, da=None, da_off=0, dap=None, dap_off=0, need_dgrad=True):
@@ -186,12 +186,11 @@ class DarknetTrainer(object):
         ops.call('yb_bn_act_bwd', 0, *args, None, 0, 1)
         dgamma = torch.empty(c, dtype=torch.float32, device=dev)
         dbeta = torch.empty(c, dtype=torch.float32, device=dev)
-        ops.call('yb_bn_param_grad', sums, c, dgamma, dbeta, 0)
         dz = torch.empty(b, s.h, s.w, c, dtype=torch.float16, device=dev)
         ops.call('yb_bn_act_bwd', 1, *args, dz, c, 1)
-        sums.zero_()
-        grads[key + '.bn.weight'] = dgamma.mul_(1.0 / self.grad_scale)
-        grads[key + '.bn.bias'] = dbeta.mul_(1.0 / self.grad_scale)
+        ops.call('yb_bn_param_grad', sums, c, dgamma, dbeta, 1, 1.0 / self.grad_scale)     # un-scales, then clears the accumulators
+        grads[key + '.bn.weight'] = dgamma
+        grads[key + '.bn.bias'] = dbeta
         self._emit(key + '.bn.weight', grads)
         self._emit(key + '.bn.bias', grads)
         if s.ain is None:

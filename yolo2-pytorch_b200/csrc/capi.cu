@@ -86,11 +86,11 @@ int bn_act_apply(const void*, long long, const float*, const float*, const float
                  int, cudaStream_t);
 int bn_act_bwd(int, const void*, long long, const float*, const float*, const float*, const float*, float, const void*, long long, int,
                const void*, long long, int, int, int, int, int, int, double*, void*, long long, int, cudaStream_t);
-int bn_param_grad(double*, int, float*, float*, int, cudaStream_t);
+int bn_param_grad(double*, int, float*, float*, int, float, cudaStream_t);
 int reorg_bwd(const void*, long long, int, void*, int, int, int, int, cudaStream_t);
 int head_grad_prepare(const float*, void*, float*, int, int, int, int, cudaStream_t);
 int conv0_wgrad(const float*, const void*, float*, int, int, int, cudaStream_t);
-int unpack_wgrad(const float*, float*, int, int, int, cudaStream_t);
+int unpack_wgrad(const float*, float*, int, int, int, float, cudaStream_t);
 int conv_wgrad_forward(const void*, const void*, float*, int, int, int, int, int, int, int, int, cudaStream_t);
 int mb_conv0(const float*, const float*, const float*, const float*, void*, int, int, int, cudaStream_t);
 int dwconv3x3(const void*, const float*, const float*, const float*, void*, int, int, int, int, int, cudaStream_t);
@@ -235,8 +235,8 @@ int yb_bn_act_bwd(int mode, const void* z, long long ld_z, const float* mean, co
                         channels, window, sums, dz, ld_dz, has_bn, S(stream));
 }
 
-int yb_bn_param_grad(double* sums, int channels, float* dgamma, float* dbeta, int reset, yb_stream_t stream) {
-  return yb::bn_param_grad(sums, channels, dgamma, dbeta, reset, S(stream));
+int yb_bn_param_grad(double* sums, int channels, float* dgamma, float* dbeta, int reset, float scale, yb_stream_t stream) {
+  return yb::bn_param_grad(sums, channels, dgamma, dbeta, reset, scale, S(stream));
 }
 
 int yb_reorg_bwd_f16(const void* dy, long long ld_dy, int dy_off, void* dx, int batch, int height, int width, int channels,
@@ -258,8 +258,8 @@ int yb_conv_wgrad(const void* x, const void* dz, float* dw_krsc, int batch, int 
   return yb::conv_wgrad_forward(x, dz, dw_krsc, batch, height, width, cin, cout, ksize, x_ld, dz_ld, S(stream));
 }
 
-int yb_unpack_wgrad(const float* dw_krsc, float* dw_oihw, int cout, int cin, int ksize, yb_stream_t stream) {
-  return yb::unpack_wgrad(dw_krsc, dw_oihw, cout, cin, ksize, S(stream));
+int yb_unpack_wgrad(const float* dw_krsc, float* dw_oihw, int cout, int cin, int ksize, float scale, yb_stream_t stream) {
+  return yb::unpack_wgrad(dw_krsc, dw_oihw, cout, cin, ksize, scale, S(stream));
 }
 
 int yb_mb_conv0_bn_relu_fwd(const float* x_nchw, const float* w_oihw, const float* scale, const float* shift, void* y_nhwc_f16, int batch,

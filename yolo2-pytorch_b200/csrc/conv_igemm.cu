@@ -122,6 +122,7 @@ struct ConvCfg {
   static constexpr int kAccStages = (2 * kAccCols <= 512) ? 2 : 1;
   static constexpr int kTmemCols = kAccStages * kAccCols;       // power of two in [64, 512]
   static constexpr int kRowsPerCta = BM * MT;
+  static constexpr bool kMergedA = (MT == 2 && !kPair);        // A tile fetched by one 256-pixel TMA box
   static constexpr int kRowsPerTile = kRowsPerCta * (kPair ? 2 : 1);
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 2 * 2 * BN * 4 /*scale/shift x2*/ + 256 /*barriers*/;
   static_assert(kAccCols <= 512, "accumulator does not fit TMEM");
@@ -133,6 +134,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   using Cfg = ConvCfg<BN, BK, MT, kPair>;
   constexpr int kAccStages = Cfg::kAccStages;
   constexpr int kStages = Cfg::kStages;
+  constexpr bool kMergedA = Cfg::kMergedA;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the swizzle atoms (identical offsets in both CTAs of a pair)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -201,6 +203,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           w0[t] = rem - h0[t] * p.width;
         }
         if (p.skip & 1) nsub = 0;
+        if (kMergedA && nsub) nsub = MT;      // the merged box always transfers (and zero-fills) both subtiles
         uint32_t tx_bytes = nsub * Cfg::kASubBytes + ((p.skip & 2) ? 0 : Cfg::kBBytes);
         if (kPair) {
           // the leader's barrier also counts the peer's bytes: recompute the peer's live subtiles
@@ -222,6 +225,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           const uint32_t full = kPair ? leader_addr(bar_full + 8 * stage) : (bar_full + 8 * stage);
           if (!kPair || rank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, tx_bytes);
           else mbar_arrive_remote(bar_full + 8 * stage, 0);
+          if (kMergedA) {
+            // one TMA box covers both 128-pixel subtiles (the tensor map's box is BM * MT pixels): the im2col-mode TMA has
+            // a large per-instruction cost (profiles/r01_wgrad_variants.txt), rows past the tensor end are zero-filled
+            if (!(p.skip & 1)) {
+              const uint32_t dst = smem_a + stage * Cfg::kABytes;
+              if (p.a_im2col) tma_load_im2col_4d(dst, &tmap_a, full, c0, w0[0] - p.pad, h0[0] - p.pad, img[0], static_cast<uint16_t>(s), static_cast<uint16_t>(r));
+              else tma_load_2d(dst, &tmap_a, full, c0, m_cta);
+            }
+          } else {
 #pragma unroll
           for (int t = 0; t < MT; ++t) {
             if (t < nsub) {
@@ -234,6 +246,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 else tma_load_2d(dst, &tmap_a, full, c0, m_cta + t * BM);
               }
             }
+          }
           }
           const int brow = n_tile * BN + static_cast<int>(rank) * Cfg::kBRows;
           if (p.skip & 2) { /* ablation: weights not fetched */ }
@@ -1140,6 +1153,7 @@ int conv_igemm_forward(const void* x, const void* w, const float* scale, const f
   const CUtensorMapSwizzle swz = (bk == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   alignas(64) CUtensorMap ta, tb;
   CUresult cr;
+  const int a_rows = (mt == 2 && !pair && !smallk) ? 2 * BM : BM;   // pixels per A box (ConvCfg::kMergedA)
   if (a_im2col) {
     const cuuint64_t dims[4] = {static_cast<cuuint64_t>(cin), static_cast<cuuint64_t>(width), static_cast<cuuint64_t>(height),
                                 static_cast<cuuint64_t>(batch)};
@@ -1149,7 +1163,7 @@ int conv_igemm_forward(const void* x, const void* w, const float* scale, const f
     const int upper[2] = {p.pad - (ksize - 1), p.pad - (ksize - 1)};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     cr = enc_im2col(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(x), dims, strides, lower, upper,
-                    static_cast<cuuint32_t>(bk), BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    static_cast<cuuint32_t>(bk), static_cast<cuuint32_t>(a_rows), estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return fail(YB_ERR_DRIVER, "cuTensorMapEncodeIm2col failed (%d)", static_cast<int>(cr));
     // Driver workaround (same one CUTLASS carries, cute/atom/copy_traits_sm90_im2col.hpp): for
@@ -1161,7 +1175,7 @@ int conv_igemm_forward(const void* x, const void* w, const float* scale, const f
   } else {
     const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cin), static_cast<cuuint64_t>(p.m_total)};
     const cuuint64_t strides[1] = {static_cast<cuuint64_t>(x_ld) * 2};
-    const cuuint32_t box[2] = {static_cast<cuuint32_t>(bk), BM};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(bk), static_cast<cuuint32_t>(a_rows)};
     const cuuint32_t estr[2] = {1, 1};
     cr = enc_tiled(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(x), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

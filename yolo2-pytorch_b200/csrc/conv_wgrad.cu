@@ -146,21 +146,24 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
       }
     } else if (warp == 1) {
       if (lane == 0) {
-        // M = 128, N = n_per_group, A and B MN-major (bits 15, 16)
-        const uint32_t idesc = make_idesc_f16(128, p.n_per_group) | (1u << 15) | (1u << 16);
+        // M = 128, A and B MN-major (bits 15, 16).  The (tap, ci-chunk) groups of this CTA are consecutive TMA boxes in
+        // shared memory and consecutive accumulator columns, so one MMA covers all of them (N = groups x n_per_group,
+        // up to 256 columns per instruction): far fewer, larger MMAs than one per group.
+        const int n_total = ngroups * p.n_per_group;
         int stage = 0; uint32_t phase = 0;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(bar_full + 8 * stage, phase, p.dbg, 0x700 | stage);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * kStageBytes;
           const uint64_t adesc = make_mnmajor_desc<128>(sa, kABox);
-          for (int g = 0; g < ((p.skip & 4) ? 0 : ngroups); ++g) {
-            const uint64_t bdesc = make_mnmajor_desc<kBRow>(sa + kABytes + g * boxes_per_group * kBBox, kBBox);
+          for (int c0 = (p.skip & 4) ? n_total : 0; c0 < n_total; c0 += 256) {
+            const int n = n_total - c0 < 256 ? n_total - c0 : 256;
+            const uint32_t idesc = make_idesc_f16(128, n) | (1u << 15) | (1u << 16);
+            const uint64_t bdesc = make_mnmajor_desc<kBRow>(sa + kABytes + (c0 / kBCh) * kBBox, kBBox);
 #pragma unroll
             for (int ks = 0; ks < WG_KP / 16; ++ks) {
               // advance 16 pixel rows: 16 * rowbytes, in 16-byte units
-              umma_f16(tmem_base + g * p.n_per_group, adesc + ks * (16 * 128 / 16), bdesc + ks * (16 * kBRow / 16), idesc,
-                       (kb > kb0 || ks > 0) ? 1u : 0u);
+              umma_f16(tmem_base + c0, adesc + ks * (16 * 128 / 16), bdesc + ks * (16 * kBRow / 16), idesc, (kb > kb0 || ks > 0) ? 1u : 0u);
             }
           }
           umma_commit(bar_empty + 8 * stage);

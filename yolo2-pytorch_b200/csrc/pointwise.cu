@@ -10,35 +10,57 @@
 namespace yb {
 
 // ------------------------------------------------------------------------------------------
-__global__ void pack_weight_kernel(const float* __restrict__ w, __half* __restrict__ out, int cout, int cin, int k, int mode, int cout_pad) {
-  const long long total = static_cast<long long>(mode == 0 ? cout : cout_pad) * cin * k * k;
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  if (mode == 0) {
-    // out[co][r][s][ci] = w[co][ci][r][s]
-    const int ci = static_cast<int>(idx % cin);
-    long long t = idx / cin;
-    const int s = static_cast<int>(t % k); t /= k;
-    const int r = static_cast<int>(t % k);
-    const int co = static_cast<int>(t / k);
-    out[idx] = __float2half_rn(w[((static_cast<long long>(co) * cin + ci) * k + r) * k + s]);
-  } else {
-    // data-gradient operand: out[ci][r][s][co] = w[co][ci][k-1-r][k-1-s]  (rotated, in/out swapped)
-    // (the reduction dimension Cout may be zero-padded to cout_pad so that it is a multiple of 32)
-    const int co = static_cast<int>(idx % cout_pad);
-    long long t = idx / cout_pad;
-    const int s = static_cast<int>(t % k); t /= k;
-    const int r = static_cast<int>(t % k);
-    const int ci = static_cast<int>(t / k);
-    out[idx] = co < cout ? __float2half_rn(w[((static_cast<long long>(co) * cin + ci) * k + (k - 1 - r)) * k + (k - 1 - s)]) : __float2half_rn(0.f);
+// mode 0: out[co][r][s][ci] = w[co][ci][r][s].  One block per (Cout row, 128-channel chunk): the [128][k*k] input run is read
+// coalesced into shared memory and written back as k*k coalesced fp16 rows.
+__global__ void __launch_bounds__(128) pack_weight_fwd_kernel(const float* __restrict__ w, __half* __restrict__ out, int cin, int k) {
+  __shared__ float tile[128 * 9 + 8];
+  const int k2 = k * k;
+  const int co = blockIdx.y, ci0 = blockIdx.x * 128, t = threadIdx.x;
+  const int nci = cin - ci0 < 128 ? cin - ci0 : 128;
+  const float* src = w + (static_cast<long long>(co) * cin + ci0) * k2;
+  for (int j = t; j < nci * k2; j += 128) tile[j] = src[j];
+  __syncthreads();
+  if (t < nci)
+    for (int tap = 0; tap < k2; ++tap) out[(static_cast<long long>(co) * k2 + tap) * cin + ci0 + t] = __float2half_rn(tile[t * k2 + tap]);
+}
+
+// mode 1 (data-gradient operand): out[ci][r][s][co] = w[co][ci][k-1-r][k-1-s]  (rotated, in/out swapped; the reduction
+// dimension Cout may be zero-padded to cout_pad).  32 x 32 tiles of the [Cout] x [Cin*k*k] matrix through shared memory:
+// rows of w are read along (ci, tap), rows of out are written along co.
+__global__ void __launch_bounds__(256) pack_weight_dgrad_kernel(const float* __restrict__ w, __half* __restrict__ out, int cout, int cin, int k, int cout_pad) {
+  __shared__ float tile[32][33];
+  const int k2 = k * k;
+  const long long cols = static_cast<long long>(cin) * k2;
+  const long long j0 = static_cast<long long>(blockIdx.x) * 32;
+  const int co0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int co = co0 + r;
+    const long long j = j0 + tx;
+    tile[r][tx] = (co < cout && j < cols) ? w[static_cast<long long>(co) * cols + j] : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const long long j = j0 + r;
+    const int co = co0 + tx;
+    if (j < cols && co < cout_pad) {
+      const long long ci = j / k2;
+      const int tap = static_cast<int>(j - ci * k2);
+      out[(ci * k2 + (k2 - 1 - tap)) * cout_pad + co] = __float2half_rn(tile[tx][r]);
+    }
   }
 }
 
 int pack_weight(const float* w, void* out, int cout, int cin, int k, int mode, int cout_pad, cudaStream_t stream) {
   YB_REQUIRE(w && out && cout > 0 && cin > 0 && (k == 1 || k == 3) && (mode == 0 || mode == 1), "pack_weight: bad argument");
   if (cout_pad < cout) cout_pad = cout;
-  const long long total = static_cast<long long>(mode == 0 ? cout : cout_pad) * cin * k * k;
-  pack_weight_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(w, reinterpret_cast<__half*>(out), cout, cin, k, mode, cout_pad);
+  if (mode == 0) {
+    pack_weight_fwd_kernel<<<dim3((cin + 127) / 128, cout), 128, 0, stream>>>(w, reinterpret_cast<__half*>(out), cin, k);
+  } else {
+    const long long cols = static_cast<long long>(cin) * k * k;
+    pack_weight_dgrad_kernel<<<dim3(static_cast<unsigned>((cols + 31) / 32), (cout_pad + 31) / 32), 256, 0, stream>>>(
+        w, reinterpret_cast<__half*>(out), cout, cin, k, cout_pad);
+  }
   return check_launch("pack_weight_kernel");
 }
 

@@ -163,7 +163,10 @@ struct GradIn {
 
 // One thread handles 8 channels of one 2x2 window (pool / branch layers) or of one pixel (window = 0).
 // mode 0: accumulate sum(dy), sum(dy * xhat) ; mode 1: write dz = sc * (dy - mean(dy) - xhat * mean(dy xhat)).
-template <int kMode, int kWin>
+// kHasDa = 0 (only valid with kWin = 1): the gradient arrives through the max-pool alone, so exactly one pixel of the
+// window (the first maximum) has a non-zero dy -- the reduction touches one element per window and the dz of the
+// other three is just -(k1 + k2 * xhat): about a third of the instructions of the general path.
+template <int kMode, int kWin, int kHasDa>
 __global__ void __launch_bounds__(kTrainThreads) bn_act_bwd_kernel(const __half* __restrict__ z, long long ld_z, BnParams bn, GradIn g, int batch,
                                                                    int height, int width, double* __restrict__ sums,
                                                                    __half* __restrict__ dz, long long ld_dz, int has_bn) {
@@ -202,7 +205,7 @@ __global__ void __launch_bounds__(kTrainThreads) bn_act_bwd_kernel(const __half*
   float acc1[8], acc2[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { acc1[i] = 0.f; acc2[i] = 0.f; }
-#pragma unroll 2
+#pragma unroll(kWin ? 1 : 2)
   for (unsigned p = blockIdx.x * (blockDim.x / c8) + threadIdx.x / c8; p < npix; p += pstride) {
     long long in0;
     if (kWin) {
@@ -218,12 +221,49 @@ __global__ void __launch_bounds__(kTrainThreads) bn_act_bwd_kernel(const __half*
     for (int w = 0; w < nwin; ++w) {
       const long long pix = in0 + (w >> 1) * width + (w & 1);
       zr[w] = __ldg(reinterpret_cast<const uint4*>(z + pix * ld_z + cg * 8));
-      dr[w] = (g.da != nullptr) ? __ldg(reinterpret_cast<const uint4*>(g.da + pix * g.ld_da + g.da_off + cg * 8)) : make_uint4(0u, 0u, 0u, 0u);
+      if (kHasDa) dr[w] = (g.da != nullptr) ? __ldg(reinterpret_cast<const uint4*>(g.da + pix * g.ld_da + g.da_off + cg * 8)) : make_uint4(0u, 0u, 0u, 0u);
     }
     if (g.dap != nullptr) pr = __ldg(reinterpret_cast<const uint4*>(g.dap + static_cast<long long>(p) * g.ld_dap + g.dap_off + cg * 8));
-    float zf[nwin][8], yv[nwin][8], gp[8];
-    int arg[8];
+    float gp[8];
     h8_to_f(pr, gp);
+    if constexpr (!kHasDa) {
+      // ---- pooled gradient only: one live element per window and channel ----
+      float zf[nwin][8];
+#pragma unroll
+      for (int w = 0; w < nwin; ++w) h8_to_f(zr[w], zf[w]);
+      float dyb[8];
+      int arg[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float besty = fmaf(zf[0][i], k.sc[i], k.sh[i]);
+        float bestz = zf[0][i];
+        arg[i] = 0;
+#pragma unroll
+        for (int w = 1; w < nwin; ++w) {
+          const float y = fmaf(zf[w][i], k.sc[i], k.sh[i]);
+          if (y > besty) { besty = y; bestz = zf[w][i]; arg[i] = w; }   // first maximum wins (leaky is strictly increasing)
+        }
+        dyb[i] = besty > 0.f ? gp[i] : gp[i] * bn.slope;
+        if (kMode == 0) {
+          acc1[i] += dyb[i];
+          acc2[i] = fmaf(dyb[i], fmaf(bestz, xa[i], xb[i]), acc2[i]);
+        }
+      }
+      if (kMode == 1) {
+#pragma unroll
+        for (int w = 0; w < nwin; ++w) {
+          float out[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float base = -fmaf(k2[i], fmaf(zf[w][i], xa[i], xb[i]), k1[i]);
+            out[i] = arg[i] == w ? fmaf(k.sc[i], dyb[i], base) : base;
+          }
+          *reinterpret_cast<uint4*>(dz + (in0 + (w >> 1) * width + (w & 1)) * ld_dz + cg * 8) = f_to_h8(out);
+        }
+      }
+    } else {
+    float zf[nwin][8], yv[nwin][8];
+    int arg[8];
 #pragma unroll
     for (int w = 0; w < nwin; ++w) {
       h8_to_f(zr[w], zf[w]);
@@ -255,6 +295,7 @@ __global__ void __launch_bounds__(kTrainThreads) bn_act_bwd_kernel(const __half*
       }
       if (kMode == 1) *reinterpret_cast<uint4*>(dz + (in0 + (w >> 1) * width + (w & 1)) * ld_dz + cg * 8) = f_to_h8(out);
     }
+    }
   }
   if (kMode == 0) {
 #pragma unroll
@@ -267,17 +308,18 @@ __global__ void __launch_bounds__(kTrainThreads) bn_act_bwd_kernel(const __half*
   }
 }
 
-// dgamma = sum(dy xhat), dbeta = sum(dy)  (fp32 parameter gradients) ; optionally reset the accumulators
-__global__ void bn_param_grad_kernel(double* __restrict__ sums, int channels, float* __restrict__ dgamma, float* __restrict__ dbeta, int reset) {
+// dgamma = scale * sum(dy xhat), dbeta = scale * sum(dy)  (fp32 parameter gradients; scale = 1 / loss scale) ; optionally reset the accumulators
+__global__ void bn_param_grad_kernel(double* __restrict__ sums, int channels, float* __restrict__ dgamma, float* __restrict__ dbeta, int reset,
+                                     float scale) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= channels) return;
-  if (dbeta) dbeta[c] = static_cast<float>(sums[c]);
-  if (dgamma) dgamma[c] = static_cast<float>(sums[channels + c]);
+  if (dbeta) dbeta[c] = static_cast<float>(sums[c] * static_cast<double>(scale));
+  if (dgamma) dgamma[c] = static_cast<float>(sums[channels + c] * static_cast<double>(scale));
   if (reset) { sums[c] = 0.0; sums[channels + c] = 0.0; }
 }
 
-static int grid_for(long long work_items) {
-  long long blocks = (work_items + kTrainThreads - 1) / kTrainThreads;
+static int grid_for(long long work_items, int items_per_thread = 1) {
+  long long blocks = (work_items + static_cast<long long>(kTrainThreads) * items_per_thread - 1) / (static_cast<long long>(kTrainThreads) * items_per_thread);
   const long long cap = static_cast<long long>(sm_count()) * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
@@ -286,7 +328,7 @@ static int grid_for(long long work_items) {
 
 // keep cg = threadIdx % c8 constant along the grid stride: total stride must be a multiple of c8
 static int grid_for_groups(long long work_items, int c8) {
-  int g = grid_for(work_items);
+  int g = grid_for(work_items, 16);    // every block pays ~50 parameter loads per thread and 2C global double atomics
   (void)c8;  // blockDim (256) is a multiple of every supported c8 (4..128), so any grid size works
   return g;
 }
@@ -295,7 +337,7 @@ int bn_stats(const void* z, long long ld, long long rows, int channels, double* 
   YB_REQUIRE(z && sums && rows > 0 && channels >= 32 && channels % 8 == 0 && channels <= 2048 && kTrainThreads % (channels / 8) == 0 && ld % 8 == 0,
              "bn_stats: unsupported shape (C=%d)", channels);
   const int rpi = kTrainThreads / (channels / 8);
-  long long blocks = (rows + rpi - 1) / rpi;
+  long long blocks = (rows + static_cast<long long>(rpi) * 16 - 1) / (static_cast<long long>(rpi) * 16);   // >= 16 rows per thread: 2C double atomics per block
   const long long cap = static_cast<long long>(sm_count()) * 8;
   if (blocks > cap) blocks = cap;
   bn_stats_kernel<<<static_cast<int>(blocks), kTrainThreads, 2 * channels * sizeof(float), stream>>>(reinterpret_cast<const __half*>(z), ld, rows,
@@ -343,16 +385,19 @@ int bn_act_bwd(int mode, const void* z, long long ld_z, const float* mean, const
   const size_t smem = mode == 0 ? 2 * channels * sizeof(float) : 0;
   const __half* zp = reinterpret_cast<const __half*>(z);
   __half* dzp = reinterpret_cast<__half*>(dz);
-  if (mode == 0 && window) bn_act_bwd_kernel<0, 1><<<grid, kTrainThreads, smem, stream>>>(zp, ld_z, bn, g, batch, height, width, sums, nullptr, 0, has_bn);
-  else if (mode == 0) bn_act_bwd_kernel<0, 0><<<grid, kTrainThreads, smem, stream>>>(zp, ld_z, bn, g, batch, height, width, sums, nullptr, 0, has_bn);
-  else if (window) bn_act_bwd_kernel<1, 1><<<grid, kTrainThreads, smem, stream>>>(zp, ld_z, bn, g, batch, height, width, sums, dzp, ld_dz, has_bn);
-  else bn_act_bwd_kernel<1, 0><<<grid, kTrainThreads, smem, stream>>>(zp, ld_z, bn, g, batch, height, width, sums, dzp, ld_dz, has_bn);
+  const bool pooled_only = window && da == nullptr;
+  if (mode == 0 && pooled_only) bn_act_bwd_kernel<0, 1, 0><<<grid, kTrainThreads, smem, stream>>>(zp, ld_z, bn, g, batch, height, width, sums, nullptr, 0, has_bn);
+  else if (mode == 0 && window) bn_act_bwd_kernel<0, 1, 1><<<grid, kTrainThreads, smem, stream>>>(zp, ld_z, bn, g, batch, height, width, sums, nullptr, 0, has_bn);
+  else if (mode == 0) bn_act_bwd_kernel<0, 0, 1><<<grid, kTrainThreads, smem, stream>>>(zp, ld_z, bn, g, batch, height, width, sums, nullptr, 0, has_bn);
+  else if (pooled_only) bn_act_bwd_kernel<1, 1, 0><<<grid, kTrainThreads, smem, stream>>>(zp, ld_z, bn, g, batch, height, width, sums, dzp, ld_dz, has_bn);
+  else if (window) bn_act_bwd_kernel<1, 1, 1><<<grid, kTrainThreads, smem, stream>>>(zp, ld_z, bn, g, batch, height, width, sums, dzp, ld_dz, has_bn);
+  else bn_act_bwd_kernel<1, 0, 1><<<grid, kTrainThreads, smem, stream>>>(zp, ld_z, bn, g, batch, height, width, sums, dzp, ld_dz, has_bn);
   return check_launch("bn_act_bwd_kernel");
 }
 
-int bn_param_grad(double* sums, int channels, float* dgamma, float* dbeta, int reset, cudaStream_t stream) {
+int bn_param_grad(double* sums, int channels, float* dgamma, float* dbeta, int reset, float scale, cudaStream_t stream) {
   YB_REQUIRE(sums && channels > 0, "bn_param_grad: bad argument");
-  bn_param_grad_kernel<<<(channels + 127) / 128, 128, 0, stream>>>(sums, channels, dgamma, dbeta, reset);
+  bn_param_grad_kernel<<<(channels + 127) / 128, 128, 0, stream>>>(sums, channels, dgamma, dbeta, reset, scale);
   return check_launch("bn_param_grad_kernel");
 }
 
@@ -536,7 +581,12 @@ int conv0_wgrad(const float* x, const void* dz, float* dw, int batch, int height
   YB_CUDA(cudaMemsetAsync(dw, 0, 27 * 32 * sizeof(float), stream));
   const int tiles_x = width / kW0Cols, tiles_y = height / kW0Rows;
   const long long tiles = static_cast<long long>(tiles_x) * tiles_y * batch;
-  const int cap = sm_count() * 4;
+  static int resident = 0;                       // persistent blocks: exactly what fits (a partial second wave would double the time)
+  if (resident == 0) {
+    YB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, conv0_wgrad_kernel, 256, 0));
+    if (resident < 1) resident = 1;
+  }
+  const int cap = sm_count() * resident;
   const int grid = tiles < cap ? static_cast<int>(tiles) : cap;
   conv0_wgrad_kernel<<<grid, 256, 0, stream>>>(x, reinterpret_cast<const __half*>(dz), dw, batch, height, width, tiles_x, tiles_y,
                                                static_cast<int>(tiles));
@@ -544,23 +594,24 @@ int conv0_wgrad(const float* x, const void* dz, float* dw, int batch, int height
 }
 
 // ------------------------------------------------------------------------------------------------
-// fp32 [Cout][k][k][Cin] (the wgrad kernel's accumulation layout) -> fp32 OIHW parameter gradient
-__global__ void unpack_wgrad_kernel(const float* __restrict__ g, float* __restrict__ out, int cout, int cin, int k) {
-  const long long total = static_cast<long long>(cout) * cin * k * k;
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int s = static_cast<int>(idx % k);
-  long long t = idx / k;
-  const int r = static_cast<int>(t % k); t /= k;
-  const int ci = static_cast<int>(t % cin);
-  const int co = static_cast<int>(t / cin);
-  out[idx] = g[((static_cast<long long>(co) * k + r) * k + s) * cin + ci];
+// fp32 [Cout][k][k][Cin] (the wgrad kernel's accumulation layout) -> fp32 OIHW parameter gradient, times `scale`
+// (the inverse loss scale).  One block per (Cout row, 128-channel chunk): coalesced reads of the k*k tap rows into
+// shared memory, coalesced writes of the [128][k*k] output run.
+__global__ void __launch_bounds__(128) unpack_wgrad_kernel(const float* __restrict__ g, float* __restrict__ out, int cout, int cin, int k, float scale) {
+  __shared__ float tile[9][129];
+  const int k2 = k * k;
+  const int co = blockIdx.y, ci0 = blockIdx.x * 128, t = threadIdx.x;
+  const int nci = cin - ci0 < 128 ? cin - ci0 : 128;
+  if (t < nci)
+    for (int tap = 0; tap < k2; ++tap) tile[tap][t] = g[(static_cast<long long>(co) * k2 + tap) * cin + ci0 + t];
+  __syncthreads();
+  float* dst = out + (static_cast<long long>(co) * cin + ci0) * k2;
+  for (int j = t; j < nci * k2; j += 128) dst[j] = tile[j % k2][j / k2] * scale;
 }
 
-int unpack_wgrad(const float* g_krsc, float* out_oihw, int cout, int cin, int k, cudaStream_t stream) {
-  YB_REQUIRE(g_krsc && out_oihw && cout > 0 && cin > 0 && k > 0, "unpack_wgrad: bad argument");
-  const long long total = static_cast<long long>(cout) * cin * k * k;
-  unpack_wgrad_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(g_krsc, out_oihw, cout, cin, k);
+int unpack_wgrad(const float* g_krsc, float* out_oihw, int cout, int cin, int k, float scale, cudaStream_t stream) {
+  YB_REQUIRE(g_krsc && out_oihw && cout > 0 && cin > 0 && (k == 1 || k == 3), "unpack_wgrad: bad argument");
+  unpack_wgrad_kernel<<<dim3((cin + 127) / 128, cout), 128, 0, stream>>>(g_krsc, out_oihw, cout, cin, k, scale);
   return check_launch("unpack_wgrad_kernel");
 }
 
