@@ -427,7 +427,7 @@ def run_train(args):
     dnn.train(); inference.train()
     anchors = torch.tensor(ANCHORS_HW, dtype=torch.float32)
     use_graph = (not args.no_graph) and (world == 1 or args.graph_ddp)
-    optimizer = torch.optim.Adam(dnn.parameters(), 1e-5, betas=(0.9, 0.999), eps=1e-8, capturable=use_graph, fused=True)
+    optimizer = torch.optim.Adam(dnn.parameters(), 1e-5, betas=(0.9, 0.999), eps=1e-8, capturable=use_graph, fused=os.environ.get('YB_ADAM_FUSED', '1') != '0')
     B, H, W = args.batch, args.size, args.size
     g = torch.Generator().manual_seed(200 + rank)
     batches = []

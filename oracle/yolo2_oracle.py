@@ -505,3 +505,60 @@ def mobilenet_forward(sd, x, collect=None):
         if collect is not None:
             collect['layers.%d' % i] = x
     return F.conv2d(x, sd['layers.14.weight'], sd['layers.14.bias'])
+
+
+# ----------------------------------------------------------------------------------------------
+# Tiny YOLOv2 backbone (model/yolo2.py:140-173) -- SURVEY 8f rank 4
+# ----------------------------------------------------------------------------------------------
+FLOAT32_MIN = -3.4028234663852886e+38          # np.finfo(np.float32).min, the ConstantPad2d value (yolo2.py:150)
+
+
+def tiny_layers(num_anchors=5, num_cls=20, channels=16):
+    """Tiny's conv units in nn.Sequential order (yolo2.py:145-156): (index, cin, cout, k, bn, act, after) with
+    after in {None, 'pool', 'pool_s1'}."""
+    L, cin, idx = [], 3, 0
+    for _ in range(5):
+        L.append(dict(key='layers.%d' % idx, cin=cin, cout=channels, k=3, bn=True, act=True, after='pool'))
+        cin, channels, idx = channels, channels * 2, idx + 2
+    L.append(dict(key='layers.%d' % idx, cin=cin, cout=channels, k=3, bn=True, act=True, after='pool_s1'))
+    cin, channels, idx = channels, channels * 2, idx + 3
+    for _ in range(2):
+        L.append(dict(key='layers.%d' % idx, cin=cin, cout=channels, k=3, bn=True, act=True, after=None))
+        cin, idx = channels, idx + 1
+    cout_head = num_anchors * (5 + num_cls) if num_cls > 1 else num_anchors * 5
+    L.append(dict(key='layers.%d' % idx, cin=cin, cout=cout_head, k=1, bn=False, act=False, after=None))
+    return L
+
+
+def make_tiny_state_dict(seed=0, num_anchors=5, num_cls=20):
+    """Deterministic synthetic Tiny state_dict: xavier-normal convs as `Tiny.init` (yolo2.py:159-165), randomised BN
+    tensors so the folding is exercised, head bias ~ N(0, 0.1)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for l in tiny_layers(num_anchors, num_cls):
+        fan_in, fan_out = l['cin'] * l['k'] ** 2, l['cout'] * l['k'] ** 2
+        std = math.sqrt(2.0 / (fan_in + fan_out))
+        sd[l['key'] + '.conv.weight'] = torch.randn(l['cout'], l['cin'], l['k'], l['k'], generator=g) * std * 2.0
+        if l['bn']:
+            c = l['cout']
+            sd[l['key'] + '.bn.weight'] = torch.rand(c, generator=g) + 0.5
+            sd[l['key'] + '.bn.bias'] = torch.randn(c, generator=g) * 0.1
+            sd[l['key'] + '.bn.running_mean'] = torch.randn(c, generator=g) * 0.1
+            sd[l['key'] + '.bn.running_var'] = torch.rand(c, generator=g) + 0.5
+        else:
+            sd[l['key'] + '.conv.bias'] = torch.randn(l['cout'], generator=g) * 0.1
+    return sd
+
+
+def tiny_forward(sd, x, num_anchors=5, num_cls=20, collect=None):
+    """model/yolo2.py:167-168 (`self.layers(x)`): conv units, MaxPool2d(2) x5, then ConstantPad2d((0,1,0,1), float32
+    min) + MaxPool2d(2, stride=1) after the sixth conv.  `collect` receives every conv unit's (pre-pool) output."""
+    for l in tiny_layers(num_anchors, num_cls):
+        x = conv_unit(x, sd, l['key'], l['k'], l['bn'], l['act'])
+        if collect is not None:
+            collect[l['key']] = x
+        if l['after'] == 'pool':
+            x = F.max_pool2d(x, 2)
+        elif l['after'] == 'pool_s1':
+            x = F.max_pool2d(F.pad(x, (0, 1, 0, 1), value=FLOAT32_MIN), 2, stride=1)
+    return x

@@ -704,6 +704,35 @@ def test_graphed_training_step_matches_eager():
             assert 0.5 <= (dg.norm() / de.norm()).item() <= 2.0, k
 
 
+def test_training_repacks_operands_under_fused_optimizer(ops):
+    """torch.optim.Adam(fused=True) updates parameters without advancing their version counters; the training path must
+    still see the new weights (it re-packs every step), and switching to eval() must re-fold / re-pack too."""
+    import model
+    import model.yolo2
+    import train as yb_train
+    cfg = make_config(1)
+    cfg.read_dict({'model': {'threshold': '0.6'}, 'hparam': {k: str(v) for k, v in O.HPARAM_DEFAULT.items()}, 'train': {'cross_entropy': '1'}})
+    anchors = O.anchors_yolo_voc()
+    dnn = model.yolo2.Darknet(model.ConfigChannels(cfg), anchors, 20)
+    dnn.load_state_dict(O.make_state_dict(0), strict=False)
+    dnn = dnn.to(DEV).train()
+    inference = model.Inference(cfg, dnn, anchors).train()
+    opt = torch.optim.Adam(dnn.parameters(), 1e-3, fused=True)
+    t = O.synth_targets(2, 64, 64, slots=4, seed=3)
+    batch = dict(tensor=O.synth_images(2, 64, 64, seed=4).to(DEV), yx_min=t['yx_min'].to(DEV), yx_max=t['yx_max'].to(DEV), cls=t['cls'].to(DEV))
+    w0 = dnn.layers2[1].conv.weight.detach().clone()
+    yb_train.iterate(inference, opt, anchors, cfg, batch)
+    w1 = dnn.layers2[1].conv.weight.detach().clone()
+    assert not torch.equal(w0, w1)
+    yb_train.iterate(inference, opt, anchors, cfg, batch)          # this forward must have packed w1
+    unit = dnn.engine.units2[0]
+    assert torch.equal(unit.w16, ops.pack_weight_f16(w1.contiguous()))
+    w2 = dnn.layers2[1].conv.weight.detach().clone()
+    dnn.eval(); inference.eval()
+    dnn(batch['tensor'])
+    assert torch.equal(unit.w16, ops.pack_weight_f16(w2.contiguous()))
+
+
 # ------------------------------------------------------------------------------------------------
 # MobileNet plugin (BASELINE configs[4])
 # ------------------------------------------------------------------------------------------------
@@ -741,3 +770,36 @@ def test_mobilenet_depthwise_vs_torch(ops):
         ops.call('yb_dwconv3x3_bn_relu_fwd', x.to(DEV).permute(0, 2, 3, 1).contiguous().half(), w.to(DEV).view(c, 9).contiguous(), scale.to(DEV),
                  shift.to(DEV), y, b, h, h, c, stride)
         assert rel_err(y.permute(0, 3, 1, 2), ref) <= 1e-3
+
+
+# ------------------------------------------------------------------------------------------------
+# Tiny YOLOv2 plugin (reference model/yolo2.py:140-173)
+# ------------------------------------------------------------------------------------------------
+def test_maxpool_stride1_padded_exact(ops):
+    """ConstantPad2d((0,1,0,1), float32 min) + MaxPool2d(2, stride=1): bit-exact against torch on fp16 values."""
+    gen = torch.Generator().manual_seed(4)
+    x = torch.randn(3, 13, 13, 64, generator=gen).half()
+    ref = torch.nn.functional.max_pool2d(torch.nn.functional.pad(x.float().permute(0, 3, 1, 2), (0, 1, 0, 1), value=O.FLOAT32_MIN), 2, stride=1)
+    y = ops.maxpool2x2_s1(x.to(DEV))
+    assert torch.equal(y.float().cpu().permute(0, 3, 1, 2), ref)
+
+
+def test_tiny_plugin_vs_reference_golden(golden_dir):
+    import model
+    import model.yolo2
+    g = np.load(os.path.join(golden_dir, 'tiny.npz'))
+    cfg = make_config(1)
+    anchors = O.anchors_yolo_voc()
+    net = model.yolo2.Tiny(model.ConfigChannels(cfg), anchors, 20)
+    res = net.load_state_dict(O.make_tiny_state_dict(0), strict=False)
+    assert not res.unexpected_keys and all(k.endswith('num_batches_tracked') for k in res.missing_keys)
+    assert net.scope('layers.4.conv.weight') == 'layers.4'
+    net = net.to(DEV).eval()
+    for size, key in ((64, 'feature64'), (416, 'feature416')):
+        x = O.synth_images(1, size, size, seed=10 if size == 64 else 0)
+        f = net(x.to(DEV))
+        e = rel_err(f, torch.from_numpy(g[key]))
+        print('tiny %d feature rel err %.3e' % (size, e))
+        assert f.shape == g[key].shape and e <= 3e-3
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 3, 64, 64))

@@ -156,3 +156,21 @@ def test_mobilenet_oracle_matches_reference(golden_dir):
     assert np.abs(f64.numpy() - g['feature64']).max() <= 2e-5 * np.abs(g['feature64']).max()
     assert np.abs(f416.numpy() - g['feature416']).max() <= 2e-5 * np.abs(g['feature416']).max()
     assert sum(v.numel() for k, v in sd.items() if 'running' not in k) == 3335101
+
+
+def test_tiny_oracle_matches_reference_golden(golden_dir):
+    """oracle.tiny_forward (restating model/yolo2.py:140-173) against outputs of the reference's own Tiny module
+    (tests/golden/make_golden_tiny.py): every conv unit at 64x64 and the 416x416 feature map."""
+    g = np.load(os.path.join(golden_dir, 'tiny.npz'))
+    sd = O.make_tiny_state_dict(seed=0)
+    collect = {}
+    with torch.no_grad():
+        f64 = O.tiny_forward(sd, O.synth_images(1, 64, 64, seed=10), collect=collect)
+        f416 = O.tiny_forward(sd, O.synth_images(1, 416, 416, seed=0))
+    assert f64.shape == (1, 125, 2, 2) and f416.shape == (1, 125, 13, 13)
+    np.testing.assert_allclose(f64.numpy(), g['feature64'], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(f416.numpy(), g['feature416'], rtol=1e-4, atol=1e-5)
+    keys = [k for k in g.files if k.startswith('act_')]
+    assert len(keys) == 9
+    for k in keys:
+        np.testing.assert_allclose(collect[k[4:]].numpy(), g[k], rtol=1e-4, atol=1e-5, err_msg=k)

@@ -37,10 +37,13 @@ class ConvUnit(object):
     def slope(self):
         return 0.1 if self.act else 1.0
 
-    def refresh(self, first_layer=False):
+    def refresh(self, first_layer=False, force=False):
+        """Re-derive the kernel operands when the parameters changed.  `force` skips the version check: training
+        steps always re-pack, because fused multi-tensor optimizers (torch.optim.Adam(fused=True)) update parameters
+        without advancing torch's version counter."""
         w = self.conv.weight
         wver = (w.data_ptr(), w._version)
-        if wver != self._wver:
+        if force or wver != self._wver:
             self.w16 = w.detach().contiguous() if first_layer else ops.pack_weight_f16(w.detach().contiguous(), 0)
             self._wver = wver
         if self.bn is not None:
@@ -123,9 +126,15 @@ class DarknetEngine(object):
             self.plans[key] = p
         return p
 
-    def refresh(self):
+    def refresh(self, force=False):
         for i, u in enumerate(self.all_units()):
-            u.refresh(first_layer=(i == 0))
+            u.refresh(first_layer=(i == 0), force=force)
+
+    def invalidate(self):
+        """Forget every cached operand (called when the module switches between train() and eval())."""
+        for u in self.all_units():
+            u._wver = None
+            u._bver = None
 
     def forward(self, x, conv_flags=0, ref=False, collect=None, plan_id=0):
         """x: fp32 NCHW [B,3,H,W] on the GPU -> feature fp32 NCHW [B,A*(5+C),H/32,W/32]

@@ -162,6 +162,17 @@ def maxpool2x2(x, channels=None, out=None):
     return out
 
 
+def maxpool2x2_s1(x, out=None):
+    """ConstantPad2d((0,1,0,1), -inf) + MaxPool2d(2, stride=1) of model.yolo2.Tiny: fp16 NHWC, same spatial size."""
+    _req(x, torch.float16, 'x')
+    b, h, w, c = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    _req(out, torch.float16, 'out')
+    _ck(_l.load().yb_maxpool2x2_s1_f16(_p(x), _p(out), b, h, w, c, c, _s()), 'yb_maxpool2x2_s1_f16')
+    return out
+
+
 def reorg_f16(x, out, y_ch_off=0):
     _req(x, torch.float16, 'x'); _req(out, torch.float16, 'out')
     b, h, w, c = x.shape

@@ -29,7 +29,7 @@ class DarknetTrainer(object):
         self.engine = engine
         self.grad_scale = float(grad_scale)
         self.sums = {}       # per-unit double[2C] accumulators (self-cleaning)
-        self.wd_cache = {}   # dgrad weights per unit, keyed by parameter version
+        self.wd_cache = {}   # dgrad weight buffers per unit (contents re-packed every step)
         self.on_grad = None  # optional callback(name, grad) fired as soon as a parameter gradient is enqueued (DDP overlap)
 
     # ---- helpers -------------------------------------------------------------------------------------
@@ -85,7 +85,7 @@ class DarknetTrainer(object):
             raise RuntimeError('Darknet (B200) training: input must be a CUDA tensor')
         b, _, h, w = x.shape
         x = x.contiguous().float()
-        eng.refresh()
+        eng.refresh(force=True)      # every step: do not trust parameter version counters (fused optimizers do not advance them)
         for u in eng.all_units()[:-1]:
             if u.bn is None:
                 raise NotImplementedError('training path requires batch_norm/enable = 1')
@@ -151,17 +151,16 @@ class DarknetTrainer(object):
 
     # ---- backward ------------------------------------------------------------------------------------
     def _wd(self, key, u, cout_pad=0):
+        """Data-gradient operand of a unit (rotated, transposed fp16 weights), re-packed every step into a reused buffer."""
         w = u.conv.weight
-        ver = (w.data_ptr(), w._version)
-        hit = self.wd_cache.get(key)
-        if hit is None or hit[0] != ver:
-            cout, cin, k, _ = w.shape
-            cp = max(cout, cout_pad)
+        cout, cin, k, _ = w.shape
+        cp = max(cout, cout_pad)
+        wd = self.wd_cache.get(key)
+        if wd is None or wd.shape != (cin, k, k, cp) or wd.device != w.device:
             wd = torch.empty(cin, k, k, cp, dtype=torch.float16, device=w.device)
-            ops.call('yb_pack_weight_dgrad_f16', w.detach().contiguous(), wd, cout, cin, k, cp)
-            self.wd_cache[key] = (ver, wd)
-            hit = self.wd_cache[key]
-        return hit[1]
+            self.wd_cache[key] = wd
+        ops.call('yb_pack_weight_dgrad_f16', w.detach().contiguous(), wd, cout, cin, k, cp)
+        return wd
 
     def _wgrad(self, u, ain, dz, b, hh, ww, grads, name, cout=None):
         cout = u.cout if cout is None else cout

@@ -70,6 +70,7 @@ void conv_set_trace(void*);
 int bn_fold(const float*, const float*, const float*, const float*, float, float*, float*, int, cudaStream_t);
 int conv0_tc_forward(const void*, int, const float*, const float*, const float*, float, void*, int, int, int, int, int, cudaStream_t);
 int maxpool2x2(const void*, void*, int, int, int, int, int, cudaStream_t);
+int maxpool2x2_s1(const void*, void*, int, int, int, int, int, cudaStream_t);
 int reorg_nhwc(const void*, void*, int, int, int, int, int, int, int, cudaStream_t);
 int reorg_nchw(const float*, float*, int, int, int, int, int, int, cudaStream_t);
 int decode_forward(const float*, const float*, float*, float*, float*, float*, float*, float*, float*, int, int, int, int, int,
@@ -157,6 +158,10 @@ int yb_conv_ref_fwd(const void* x, const void* w, const float* scale, const floa
 
 int yb_maxpool2x2_f16(const void* x, void* y, int batch, int height, int width, int channels, int x_ld, yb_stream_t stream) {
   return yb::maxpool2x2(x, y, batch, height, width, channels, x_ld, S(stream));
+}
+
+int yb_maxpool2x2_s1_f16(const void* x, void* y, int batch, int height, int width, int channels, int x_ld, yb_stream_t stream) {
+  return yb::maxpool2x2_s1(x, y, batch, height, width, channels, x_ld, S(stream));
 }
 
 int yb_reorg_f16(const void* x, void* y, int batch, int height, int width, int channels, int x_ld, int y_ld, int y_ch_off,

@@ -123,6 +123,36 @@ int maxpool2x2(const void* x, void* y, int batch, int height, int width, int cha
 }
 
 // ------------------------------------------------------------------------------------------
+// model.yolo2.Tiny's ConstantPad2d((0, 1, 0, 1), float32 min) + MaxPool2d(2, stride=1)  (model/yolo2.py:150-151): same-size output,
+// out[y, x] = max over the in-range pixels of {y, y+1} x {x, x+1} (the pad value never wins).  thread = 8 channels of one pixel
+__global__ void maxpool2x2_s1_kernel(const __half* __restrict__ x, __half* __restrict__ y, int batch, int height, int width, int channels,
+                                     int x_ld) {
+  const int c8 = channels >> 3;
+  const long long total = static_cast<long long>(batch) * height * width * c8;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cg = static_cast<int>(idx % c8);
+  long long t = idx / c8;
+  const int px = static_cast<int>(t % width); t /= width;
+  const int py = static_cast<int>(t % height);
+  const __half* p00 = x + (t * width + px) * x_ld + cg * 8;       // t = img * height + py
+  uint4 m = __ldg(reinterpret_cast<const uint4*>(p00));
+  const bool right = px + 1 < width, down = py + 1 < height;
+  if (right) m = hmax8(m, __ldg(reinterpret_cast<const uint4*>(p00 + x_ld)));
+  if (down) m = hmax8(m, __ldg(reinterpret_cast<const uint4*>(p00 + static_cast<long long>(width) * x_ld)));
+  if (right && down) m = hmax8(m, __ldg(reinterpret_cast<const uint4*>(p00 + static_cast<long long>(width) * x_ld + x_ld)));
+  reinterpret_cast<uint4*>(y)[idx] = m;
+}
+
+int maxpool2x2_s1(const void* x, void* y, int batch, int height, int width, int channels, int x_ld, cudaStream_t stream) {
+  YB_REQUIRE(x && y && batch > 0 && height > 0 && width > 0 && channels % 8 == 0 && x_ld % 8 == 0 && x_ld >= channels, "maxpool2x2_s1: bad argument");
+  const long long total = static_cast<long long>(batch) * height * width * (channels / 8);
+  maxpool2x2_s1_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(y), batch, height, width, channels, x_ld);
+  return check_launch("maxpool2x2_s1_kernel");
+}
+
+// ------------------------------------------------------------------------------------------
 // reorg on fp16 NHWC: out[b, h', w', y_ch_off + (sh*2+sw)*C + c] = in[b, 2h'+sh, 2w'+sw, c]
 __global__ void reorg_nhwc_kernel(const __half* __restrict__ x, __half* __restrict__ y, int batch, int height, int width, int channels,
                                   int x_ld, int y_ld, int y_ch_off) {

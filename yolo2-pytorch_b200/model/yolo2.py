@@ -177,6 +177,13 @@ class Darknet(nn.Module):
             self._trainer = _train.DarknetTrainer(self.engine)
         return self._trainer
 
+    def train(self, mode=True):
+        """nn.Module.train + drop cached kernel operands: parameters may have been updated by an optimizer that does not
+        advance torch's version counters (fused multi-tensor steps), so the eval engine re-packs after training."""
+        if getattr(self, '_engine', None) is not None and bool(mode) != self.training:
+            self._engine.invalidate()
+        return nn.Module.train(self, mode)
+
     def forward(self, x):
         if self.training:
             # batch-statistics BatchNorm + autograd through the explicit backward chain
@@ -192,3 +199,140 @@ class Darknet(nn.Module):
         if index == 94:
             n = self.stride * self.stride
             return lambda indices, channels: torch.cat([indices + k * channels for k in range(n)])
+
+
+class ConstantPad2d(nn.Module):
+    """Index placeholder for Tiny's nn.ConstantPad2d((0, 1, 0, 1), float32 min) (reference model/yolo2.py:150); the pad
+    is folded into the stride-1 pooling kernel (yb_maxpool2x2_s1_f16)."""
+    is_pool = True
+
+    def __init__(self, padding=(0, 1, 0, 1)):
+        nn.Module.__init__(self)
+        if tuple(padding) != (0, 1, 0, 1):
+            raise ValueError('only ConstantPad2d((0, 1, 0, 1)) is on the Tiny path')
+        self.padding = tuple(padding)
+
+
+class MaxPool2dStride1(nn.Module):
+    """Index placeholder for Tiny's nn.MaxPool2d(kernel_size=2, stride=1) (reference model/yolo2.py:151)."""
+    is_pool = True
+
+    def __init__(self):
+        nn.Module.__init__(self)
+        self.kernel_size, self.stride = 2, 1
+
+
+class Tiny(nn.Module):
+    """Tiny YOLOv2 backbone plugin (reference model/yolo2.py:140-173; the repo's default `model/dnn`, config.ini:25),
+    inference on the B200 kernels.  Same constructor contract `Tiny(config_channels, anchors, num_cls, channels=16)`, same
+    state_dict keys (`layers.{0,2,4,6,8,10,13,14,15}.conv.*`, `.bn.*`), `init()` (xavier-normal, :159-165), `scope()`
+    (:170-171) and forward contract x[B,3,H,W] fp32 -> [B, A*(5+C), H/32, W/32] fp32.
+
+    Kernel chain: the 3->16 first layer runs on the fused first-layer kernel with its 16 filters zero-padded to 32 (the
+    extra channels come out as exact zeros and the next layer's weights are zero-padded on the input side to match), the
+    two Cin = 32 layers on the halo-tile tcgen05 kernel with the 2x2 max-pool fused, the rest on the implicit-GEMM
+    kernel; `ConstantPad2d + MaxPool2d(2, stride=1)` is one HBM kernel."""
+
+    def __init__(self, config_channels, anchors, num_cls, channels=16):
+        nn.Module.__init__(self)
+        cc = config_channels
+        bn = cc.config.getboolean('batch_norm', 'enable')
+        layers = []
+        for _ in range(5):
+            layers.append(Conv2d(cc.channels, cc(channels, 'layers.%d.conv.weight' % len(layers)), 3, bn=bn, padding=True))
+            layers.append(MaxPool2d(2))
+            channels *= 2
+        layers.append(Conv2d(cc.channels, cc(channels, 'layers.%d.conv.weight' % len(layers)), 3, bn=bn, padding=True))
+        layers.append(ConstantPad2d((0, 1, 0, 1)))
+        layers.append(MaxPool2dStride1())
+        channels *= 2
+        for _ in range(2):
+            layers.append(Conv2d(cc.channels, cc(channels, 'layers.%d.conv.weight' % len(layers)), 3, bn=bn, padding=True))
+        layers.append(Conv2d(cc.channels, model.output_channels(len(anchors), num_cls), 1, bn=False, act=False))
+        self.layers = nn.Sequential(*layers)
+        self.init()
+        self._units = None
+        self._pad_cache = {}
+
+    def init(self):
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.xavier_normal_(m.weight)
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.ones_(m.weight)
+                nn.init.zeros_(m.bias)
+
+    def scope(self, name):
+        return '.'.join(name.split('.')[:-2])
+
+    # ---- operands ----------------------------------------------------------------------------------
+    def _plan(self):
+        """[(ConvUnit, followed_by: None | 'pool' | 'pool_s1')] in network order."""
+        if self._units is None:
+            mods = list(self.layers)
+            plan = []
+            for i, m in enumerate(mods):
+                if m.is_pool:
+                    continue
+                after = None
+                if i + 1 < len(mods) and isinstance(mods[i + 1], MaxPool2d):
+                    after = 'pool'
+                elif i + 1 < len(mods) and isinstance(mods[i + 1], ConstantPad2d):
+                    after = 'pool_s1'
+                plan.append((_engine.ConvUnit(m.conv, m.bn if m.has_bn else None, m.has_act), after))
+            self._units = plan
+        return self._units
+
+    def _padded(self, key, u, cout_to, cin_to, first):
+        """Zero-padded copy of a unit's operands (weights, scale, shift), cached per parameter version."""
+        ver = (u._wver, u._bver)
+        hit = self._pad_cache.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        w = u.conv.weight.detach()
+        cout, cin, k, _ = w.shape
+        wp = torch.zeros(cout_to, cin_to, k, k, dtype=torch.float32, device=w.device)
+        wp[:cout, :cin] = w
+        w_op = wp.contiguous() if first else _ops.pack_weight_f16(wp.contiguous(), 0)
+        scale = torch.zeros(cout_to, dtype=torch.float32, device=w.device)
+        shift = torch.zeros(cout_to, dtype=torch.float32, device=w.device)
+        scale[:cout], shift[:cout] = u.scale, u.shift
+        self._pad_cache[key] = (ver, (w_op, scale, shift))
+        return self._pad_cache[key][1]
+
+    def forward(self, x):
+        if self.training:
+            raise NotImplementedError('Tiny (B200): inference only; call .eval()')
+        if not x.is_cuda:
+            raise RuntimeError('Tiny (B200): input must be a CUDA tensor; there is no CPU fallback')
+        b, c, h, w = x.shape
+        if c != 3 or h % 32 or w % 32:
+            raise ValueError('Tiny expects fp32 [B,3,H,W] with H, W multiples of 32, got %s' % (tuple(x.shape),))
+        x = x.contiguous().float()
+        plan = self._plan()
+        for i, (u, _) in enumerate(plan):
+            u.refresh(first_layer=(i == 0))
+        u0, after0 = plan[0]
+        if after0 != 'pool' or u0.cout > 32:
+            raise RuntimeError('Tiny (B200): the first unit must have <= 32 filters and be followed by MaxPool2d(2)')
+        w0, sc0, sh0 = self._padded('u0', u0, 32, 3, True)
+        cur = _ops.conv0_bn_leaky_pool(x, w0, sc0, sh0, u0.slope)          # [B,H/2,W/2,32], channels >= cout are exact zeros
+        chan = 32
+        for i, (u, after) in enumerate(plan[1:], 1):
+            last = i == len(plan) - 1
+            if u.cin != chan:                                              # input side zero-padded to the producer's width
+                w_op, scale, shift = self._padded('u%d' % i, u, u.cout, chan, False)
+            else:
+                w_op, scale, shift = u.w16, u.scale, u.shift
+            if last:
+                return _ops.conv_bn_act(cur, w_op, scale, shift, u.slope, out_mode=_ops.OUT_F32_NCHW)
+            fuse = after == 'pool' and chan == 32 and u.ksize == 3 and u.cout <= 64
+            if fuse:
+                cur = _ops.conv_bn_act(cur, w_op, scale, shift, u.slope, flags=_ops.CONV_POOL2X2)
+            else:
+                cur = _ops.conv_bn_act(cur, w_op, scale, shift, u.slope)
+                if after == 'pool':
+                    cur = _ops.maxpool2x2(cur)
+                elif after == 'pool_s1':
+                    cur = _ops.maxpool2x2_s1(cur)
+            chan = u.cout

@@ -160,8 +160,4 @@ class GraphedStep(object):
 
     def finish(self):
         """Drop operand caches that the graph kept current on its own buffers (see the class docstring)."""
-        dnn = self.inference.dnn
-        for u in dnn.engine.all_units():
-            u._wver = None
-            u._bver = None
-        dnn.trainer.wd_cache.clear()
+        self.inference.dnn.engine.invalidate()
