@@ -188,6 +188,15 @@ int yb_conv_wgrad(const void* x, const void* dz, float* dw_krsc, int batch, int 
                   int dz_ld, yb_stream_t stream);
 int yb_unpack_wgrad(const float* dw_krsc, float* dw_oihw, int cout, int cin, int ksize, float scale, yb_stream_t stream);
 
+/* ---- evaluation matching (eval.py:57-75 `_matching`/`matching`, called per image and class at eval.py:210-216) ----
+ * Segmented batch: image i owns detections [det_off[i], det_off[i+1]) (descending score within the image, as postprocess returns
+ * them) and ground-truth boxes [gt_off[i], gt_off[i+1]); boxes are (y, x) float pairs, classes int32.  tp[d] = 1 iff detection d's
+ * best-IoU ground truth of its own class (ties: lowest index) has IoU > threshold and was not claimed by an earlier detection of
+ * the image.  IoU uses the reference's operation order (utils/iou/torch.py:24-61) with min_union = float32 eps. */
+int yb_eval_match(const float* det_yx_min, const float* det_yx_max, const int* det_cls, const int* det_off, const float* gt_yx_min,
+                  const float* gt_yx_max, const int* gt_cls, const int* gt_off, int batch, int num_cls, int max_gt, float threshold, float min_union,
+                  unsigned char* tp, yb_stream_t stream);
+
 /* ---- MobileNet plugin (model/mobilenet.py:25-85), inference ------------------------------------------------- */
 /* conv_bn(3,32,stride 2) + BN + ReLU: x fp32 NCHW [B,3,H,W] -> y fp16 NHWC [B,H/2,W/2,32] (model/mobilenet.py:25-30). */
 int yb_mb_conv0_bn_relu_fwd(const float* x_nchw, const float* w_oihw, const float* scale, const float* shift, void* y_nhwc_f16, int batch,

@@ -562,3 +562,67 @@ def tiny_forward(sd, x, num_anchors=5, num_cls=20, collect=None):
         elif l['after'] == 'pool_s1':
             x = F.max_pool2d(F.pad(x, (0, 1, 0, 1), value=FLOAT32_MIN), 2, stride=1)
     return x
+
+
+# ----------------------------------------------------------------------------------------------
+# Evaluation matching + VOC AP (eval.py:57-121) -- SURVEY 8f rank 3
+# ----------------------------------------------------------------------------------------------
+def eval_matching(data_yx_min, data_yx_max, yx_min, yx_max, threshold):
+    """eval.py:57-75: detections (descending score) vs the ground truth of the same class -> bool[N]."""
+    n = yx_min.shape[0]
+    tp = np.zeros([n], dtype=bool)
+    if data_yx_min.numel() == 0 or n == 0:
+        return tp
+    m = iou_matrix(yx_min, yx_max, data_yx_min, data_yx_max)
+    iou, index = torch.max(m, -1)
+    detected = set()
+    for i in range(n):
+        if bool(iou[i] > threshold) and int(index[i]) not in detected:
+            tp[i] = True
+            detected.add(int(index[i]))
+    return tp
+
+
+def voc_ap(rec, prec, use_07_metric=False):
+    """eval.py:78-108."""
+    if use_07_metric:
+        ap = 0.
+        for t in np.arange(0., 1.1, 0.1):
+            p = 0 if np.sum(rec >= t) == 0 else np.max(prec[rec >= t])
+            ap = ap + p / 11.
+        return ap
+    mrec = np.concatenate(([0.], rec, [1.]))
+    mpre = np.concatenate(([0.], prec, [0.]))
+    for i in range(mpre.size - 1, 0, -1):
+        mpre[i - 1] = np.maximum(mpre[i - 1], mpre[i])
+    i = np.where(mrec[1:] != mrec[:-1])[0]
+    return np.sum((mrec[i + 1] - mrec[i]) * mpre[i + 1])
+
+
+def average_precision(tp, num, metric07=False):
+    """eval.py:111-120."""
+    tp = np.asarray(tp, dtype=bool)
+    fp = np.cumsum(~tp)
+    tp = np.cumsum(tp)
+    rec = tp / num if num > 0 else np.zeros(len(tp))
+    prec = tp / np.maximum(tp + fp, np.finfo(np.float64).eps)
+    return voc_ap(rec, prec, metric07)
+
+
+def synth_eval_case(seed, n_det=60, n_gt=12, num_cls=4, extent=13.0):
+    """Detections (descending score) and ground truth of one image with many overlaps: jittered copies of the ground truth
+    plus random boxes, so that matched / duplicate / unmatched detections all occur."""
+    g = torch.Generator().manual_seed(seed)
+    gt_min = torch.rand(n_gt, 2, generator=g) * (extent - 4)
+    gt_max = gt_min + 1.0 + torch.rand(n_gt, 2, generator=g) * 3
+    gt_cls = torch.randint(0, num_cls, (n_gt,), generator=g)
+    src = torch.randint(0, n_gt, (n_det,), generator=g)
+    jitter = (torch.rand(n_det, 2, generator=g) - 0.5) * 1.2
+    det_min = gt_min[src] + jitter
+    det_max = gt_max[src] + jitter * 0.5
+    rnd = torch.rand(n_det, generator=g) < 0.3
+    det_min[rnd] = torch.rand(int(rnd.sum()), 2, generator=g) * (extent - 3)
+    det_max[rnd] = det_min[rnd] + 0.5 + torch.rand(int(rnd.sum()), 2, generator=g) * 3
+    det_cls = torch.where(torch.rand(n_det, generator=g) < 0.8, gt_cls[src], torch.randint(0, num_cls, (n_det,), generator=g))
+    score = torch.sort(torch.rand(n_det, generator=g), descending=True)[0]
+    return dict(gt_min=gt_min, gt_max=gt_max, gt_cls=gt_cls, det_min=det_min, det_max=det_max, det_cls=det_cls, score=score)

@@ -803,3 +803,44 @@ def test_tiny_plugin_vs_reference_golden(golden_dir):
         assert f.shape == g[key].shape and e <= 3e-3
     with pytest.raises(RuntimeError):
         net(torch.zeros(1, 3, 64, 64))
+
+
+# ------------------------------------------------------------------------------------------------
+# Evaluation matching on the device (reference eval.py:57-75)
+# ------------------------------------------------------------------------------------------------
+def test_eval_matching_vs_reference_golden(golden_dir):
+    """yb_eval_match (one launch for the whole ragged batch) and the per-class drop-in eval.matching: true-positive
+    flags bit-identical to the reference's, incl. images without ground truth / without detections."""
+    import eval as yb_eval
+    g = np.load(os.path.join(golden_dir, 'eval.npz'))
+    tags = sorted({k.split('_')[0] for k in g.files if k.startswith('case')})
+    cases = [{k[len(t) + 1:]: g[k] for k in g.files if k.startswith(t + '_')} for t in tags]
+    det_off = np.cumsum([0] + [c['det_cls'].shape[0] for c in cases])
+    gt_off = np.cumsum([0] + [c['gt_cls'].shape[0] for c in cases])
+    cat = lambda key, dt: torch.from_numpy(np.concatenate([c[key] for c in cases]).astype(dt)).to(DEV)
+    tp = yb_eval.matching_batch(cat('det_min', np.float32), cat('det_max', np.float32), cat('det_cls', np.int32), torch.from_numpy(det_off),
+                                cat('gt_min', np.float32), cat('gt_max', np.float32), cat('gt_cls', np.int32), torch.from_numpy(gt_off), 20, 0.5)
+    assert np.array_equal(tp.cpu().numpy().astype(bool), np.concatenate([c['tp'] for c in cases]))
+    # per-class drop-in, as Eval.filter_cls calls it
+    case = cases[1]
+    for c in range(int(case['num_cls'])):
+        dm, gm = case['det_cls'] == c, case['gt_cls'] == c
+        got = yb_eval.matching(torch.from_numpy(case['gt_min'][gm]).to(DEV), torch.from_numpy(case['gt_max'][gm]).to(DEV),
+                               torch.from_numpy(case['det_min'][dm]).to(DEV), torch.from_numpy(case['det_max'][dm]).to(DEV), 0.5)
+        assert got.dtype == bool and np.array_equal(got, case['tp'][dm])
+    # a larger random ragged batch against the oracle restatement
+    rows, expect = [], []
+    for i in range(24):
+        case = O.synth_eval_case(100 + i, n_det=40 + 7 * i, n_gt=1 + i, num_cls=20)
+        rows.append(case)
+        tp_i = np.zeros(case['det_cls'].numel(), dtype=bool)
+        for c in range(20):
+            dm, gm = case['det_cls'] == c, case['gt_cls'] == c
+            tp_i[dm.numpy()] = O.eval_matching(case['gt_min'][gm], case['gt_max'][gm], case['det_min'][dm], case['det_max'][dm], 0.45)
+        expect.append(tp_i)
+    det_off = np.cumsum([0] + [r['det_cls'].numel() for r in rows])
+    gt_off = np.cumsum([0] + [r['gt_cls'].numel() for r in rows])
+    tcat = lambda key: torch.cat([r[key] for r in rows]).to(DEV)
+    tp = yb_eval.matching_batch(tcat('det_min'), tcat('det_max'), tcat('det_cls'), torch.from_numpy(det_off), tcat('gt_min'), tcat('gt_max'),
+                                tcat('gt_cls'), torch.from_numpy(gt_off), 20, 0.45)
+    assert np.array_equal(tp.cpu().numpy().astype(bool), np.concatenate(expect))

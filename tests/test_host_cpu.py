@@ -211,3 +211,21 @@ def test_darknet_weights_full_model_round_trip(tmp_path):
     for k, v in sd.items():
         if not k.endswith('num_batches_tracked'):
             assert torch.equal(got[k], v), k
+
+
+def test_eval_ap_host_functions_match_reference_golden():
+    """eval.voc_ap / average_precision / merge_ap (host numpy, reference eval.py:78-121,296-303) against the golden APs."""
+    import eval as yb_eval
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'eval.npz'))
+    for metric07 in (0, 1):
+        config = configparser.ConfigParser()
+        config.read_dict({'eval': {'metric07': str(metric07)}})
+        for c in range(20):
+            ap = yb_eval.average_precision(config, g['sorted_tp_cls%d' % c], int(g['num_cls%d' % c]))
+            assert abs(ap - float(g['ap%d_cls%d' % (metric07, c)])) <= 1e-12
+    config.read_dict({'eval': {'metric07': '0'}})
+    merged = yb_eval.merge_ap(config, [2, 0], [np.array([0.9, 0.1, 0.5]), np.array([0.3])], [np.array([True, False, True]), np.array([False])])
+    assert list(merged) == [0] and abs(merged[0] - 1.0) <= 1e-12          # both ground truths found by the two best-scored detections
+    with pytest.raises(RuntimeError):
+        yb_eval.matching_batch(torch.zeros(1, 2), torch.ones(1, 2), torch.zeros(1), torch.tensor([0, 1]), torch.zeros(1, 2), torch.ones(1, 2),
+                               torch.zeros(1), torch.tensor([0, 1]), 1, 0.5)

@@ -174,3 +174,26 @@ def test_tiny_oracle_matches_reference_golden(golden_dir):
     assert len(keys) == 9
     for k in keys:
         np.testing.assert_allclose(collect[k[4:]].numpy(), g[k], rtol=1e-4, atol=1e-5, err_msg=k)
+
+
+def _eval_cases(g):
+    tags = sorted({k.split('_')[0] for k in g.files if k.startswith('case')})
+    for tag in tags:
+        yield tag, {k[len(tag) + 1:]: g[k] for k in g.files if k.startswith(tag + '_')}
+
+
+def test_eval_matching_and_ap_oracle_matches_reference_golden(golden_dir):
+    """oracle eval_matching / average_precision (restating eval.py:57-121) against outputs of the reference's own
+    functions (tests/golden/make_golden_eval.py), including the no-ground-truth and no-detection cases."""
+    g = load(golden_dir, 'eval.npz')
+    for tag, case in _eval_cases(g):
+        tp = np.zeros(case['det_cls'].shape[0], dtype=bool)
+        for c in range(int(case['num_cls'])):
+            dm, gm = case['det_cls'] == c, case['gt_cls'] == c
+            tp[dm] = O.eval_matching(torch.from_numpy(case['gt_min'][gm]), torch.from_numpy(case['gt_max'][gm]),
+                                     torch.from_numpy(case['det_min'][dm]), torch.from_numpy(case['det_max'][dm]), 0.5)
+        assert np.array_equal(tp, case['tp']), tag
+    for c in range(20):
+        for metric07 in (0, 1):
+            ap = O.average_precision(g['sorted_tp_cls%d' % c], int(g['num_cls%d' % c]), bool(metric07))
+            assert abs(ap - float(g['ap%d_cls%d' % (metric07, c)])) <= 1e-12, (c, metric07)

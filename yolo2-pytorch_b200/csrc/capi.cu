@@ -91,6 +91,8 @@ int bn_param_grad(double*, int, float*, float*, int, float, cudaStream_t);
 int reorg_bwd(const void*, long long, int, void*, int, int, int, int, cudaStream_t);
 int head_grad_prepare(const float*, void*, float*, int, int, int, int, cudaStream_t);
 int conv0_wgrad(const float*, const void*, float*, int, int, int, cudaStream_t);
+int eval_match(const float*, const float*, const int*, const int*, const float*, const float*, const int*, const int*, int, int, int, float, float,
+               unsigned char*, cudaStream_t);
 int unpack_wgrad(const float*, float*, int, int, int, float, cudaStream_t);
 int conv_wgrad_forward(const void*, const void*, float*, int, int, int, int, int, int, int, int, cudaStream_t);
 int mb_conv0(const float*, const float*, const float*, const float*, void*, int, int, int, cudaStream_t);
@@ -265,6 +267,13 @@ int yb_conv_wgrad(const void* x, const void* dz, float* dw_krsc, int batch, int 
 
 int yb_unpack_wgrad(const float* dw_krsc, float* dw_oihw, int cout, int cin, int ksize, float scale, yb_stream_t stream) {
   return yb::unpack_wgrad(dw_krsc, dw_oihw, cout, cin, ksize, scale, S(stream));
+}
+
+int yb_eval_match(const float* det_yx_min, const float* det_yx_max, const int* det_cls, const int* det_off, const float* gt_yx_min,
+                  const float* gt_yx_max, const int* gt_cls, const int* gt_off, int batch, int num_cls, int max_gt, float threshold, float min_union,
+                  unsigned char* tp, yb_stream_t stream) {
+  return yb::eval_match(det_yx_min, det_yx_max, det_cls, det_off, gt_yx_min, gt_yx_max, gt_cls, gt_off, batch, num_cls, max_gt, threshold, min_union, tp,
+                        S(stream));
 }
 
 int yb_mb_conv0_bn_relu_fwd(const float* x_nchw, const float* w_oihw, const float* scale, const float* shift, void* y_nhwc_f16, int batch,

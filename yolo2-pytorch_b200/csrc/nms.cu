@@ -366,4 +366,71 @@ int iou_matrix(const float* yx_min1, const float* yx_max1, const float* yx_min2,
   return check_launch("iou_matrix_kernel");
 }
 
+// ------------------------------------------------------------------------------------------------
+// Evaluation matching (reference eval.py:57-75 `_matching` / `matching`, called per image and per class from
+// eval.py:210-216 `filter_cls`): a detection of class c is a true positive iff its best-IoU ground-truth box of class c
+// (ties -> lowest index, torch.max) has IoU > threshold and was not already claimed by an earlier detection of the
+// image (detections arrive in descending-score order).  One warp per (image, class): the lanes scan the ground truth
+// for each detection in turn, the claimed set is a per-warp bitmap.  Segmented (ragged) inputs: image i owns
+// detections [det_off[i], det_off[i+1]) and ground-truth boxes [gt_off[i], gt_off[i+1]).
+constexpr int kMatchMaxGt = 1024;     // ground-truth boxes per image (bitmap in shared memory)
+
+__global__ void __launch_bounds__(128) eval_match_kernel(const float2* __restrict__ det_min, const float2* __restrict__ det_max,
+                                                         const int* __restrict__ det_cls, const int* __restrict__ det_off,
+                                                         const float2* __restrict__ gt_min, const float2* __restrict__ gt_max,
+                                                         const int* __restrict__ gt_cls, const int* __restrict__ gt_off, int num_cls, float threshold,
+                                                         float eps, unsigned char* __restrict__ tp) {
+  __shared__ unsigned claimed[4][kMatchMaxGt / 32];
+  const int img = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int d0 = det_off[img], d1 = det_off[img + 1];
+  const int g0 = gt_off[img], g1 = gt_off[img + 1];
+  const int ng = g1 - g0;
+  for (int c = blockIdx.y * 4 + warp; c < num_cls; c += gridDim.y * 4) {
+    for (int i = lane; i < (ng + 31) / 32; i += 32) claimed[warp][i] = 0u;
+    __syncwarp();
+    for (int d = d0; d < d1; ++d) {
+      if (det_cls[d] != c) continue;                       // warp-uniform
+      const float2 a0 = det_min[d], a1 = det_max[d];
+      const float area_a = __fmul_rn(__fsub_rn(a1.x, a0.x), __fsub_rn(a1.y, a0.y));
+      float best = -1.f;
+      int best_j = 0x7fffffff;                             // rank among the class-c ground truth is not needed: identity suffices
+      for (int j = lane; j < ng; j += 32) {
+        if (gt_cls[g0 + j] != c) continue;
+        const float2 b0 = gt_min[g0 + j], b1 = gt_max[g0 + j];
+        const float area_b = __fmul_rn(__fsub_rn(b1.x, b0.x), __fsub_rn(b1.y, b0.y));
+        const float v = iou_exact(a0.x, a0.y, a1.x, a1.y, area_a, b0.x, b0.y, b1.x, b1.y, area_b, eps);
+        if (v > best) { best = v; best_j = j; }            // strict: the first (lowest-index) maximum of this lane's stride
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, best_j, o);
+        if (ob > best || (ob == best && oj < best_j)) { best = ob; best_j = oj; }
+      }
+      if (lane == 0) {
+        unsigned char hit = 0;
+        if (best_j != 0x7fffffff && best > threshold) {
+          const unsigned bit = 1u << (best_j & 31);
+          if (!(claimed[warp][best_j >> 5] & bit)) { claimed[warp][best_j >> 5] |= bit; hit = 1; }
+        }
+        tp[d] = hit;
+      }
+      __syncwarp();
+    }
+    __syncwarp();
+  }
+}
+
+int eval_match(const float* det_yx_min, const float* det_yx_max, const int* det_cls, const int* det_off, const float* gt_yx_min,
+               const float* gt_yx_max, const int* gt_cls, const int* gt_off, int batch, int num_cls, int max_gt, float threshold, float min_union,
+               unsigned char* tp, cudaStream_t stream) {
+  YB_REQUIRE(det_off && gt_off && tp && batch > 0 && num_cls > 0, "eval_match: bad argument");
+  YB_REQUIRE(max_gt >= 0 && max_gt <= kMatchMaxGt, "eval_match: at most %d ground-truth boxes per image (got %d)", kMatchMaxGt, max_gt);
+  const int gy = (num_cls + 3) / 4 < 8 ? (num_cls + 3) / 4 : 8;
+  eval_match_kernel<<<dim3(batch, gy), 128, 0, stream>>>(reinterpret_cast<const float2*>(det_yx_min), reinterpret_cast<const float2*>(det_yx_max), det_cls,
+                                                         det_off, reinterpret_cast<const float2*>(gt_yx_min), reinterpret_cast<const float2*>(gt_yx_max),
+                                                         gt_cls, gt_off, num_cls, threshold, min_union, tp);
+  return check_launch("eval_match_kernel");
+}
+
 }  // namespace yb
