@@ -487,8 +487,15 @@ def run_train(args):
                                   frac=value * gflop_train / 1e3 / peaks['tflops'], traffic=None, kernel='whole training step',
                                   peak_source=peaks['source']),
                     allreduce_bytes_per_step=(reducer.bytes_reduced // max(1, args.steps + args.warmup)) if reducer else 0)
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        if use_graph:
+            # a captured graph that contains NCCL kernels keeps the communicator busy at teardown (observed: the workers
+            # never return from destroy_process_group); everything is measured and printed, so leave without the teardown
+            torch.cuda.synchronize()
+            dist.barrier()
+            sys.stdout.flush()
+            os._exit(0)
         dist.destroy_process_group()
 
 

@@ -34,6 +34,18 @@ def _worker(rank, world, port, out):
         ok = ok and torch.allclose(grads['g%d' % i], exp, atol=1e-6)
     spans = [ddp.shard_range(10, r, world) for r in range(world)]
     ok = ok and spans == [(0, 5), (5, 10)] and red.bytes_reduced == sum(4 * int(torch.tensor(s).prod()) for s in shapes)
+    # class-term normalisation: per-rank means re-weighted by global_mean_factor and averaged over ranks == the
+    # reference's loss on the gathered batch, (sum CE / N_total) / cnt_global with cnt_global = world * cnt_local
+    ce_sum = [3.5, 11.25][rank]          # sum of the cross-entropies of this rank's positives
+    npos = [4, 9][rank]
+    cnt_local = 32.0
+    f = ddp.global_mean_factor(torch.tensor(npos))
+    mine = torch.tensor(ce_sum / npos / cnt_local) * f
+    dist.all_reduce(mine)
+    mine = mine / world                  # what gradient averaging does to a per-rank loss term
+    reference = (3.5 + 11.25) / (4 + 9) / (cnt_local * world)
+    ok = ok and abs(float(mine) - reference) <= 1e-7 and abs(float(f) - npos / 13.0) <= 1e-7
+    ok = ok and float(ddp.global_mean_factor(torch.tensor(0), None)) == 0.0
     out[rank] = bool(ok)
     dist.destroy_process_group()
 

@@ -85,6 +85,24 @@ class GradientAllReducer(object):
             off += n
 
 
+def global_mean_factor(local_count, process_group=None):
+    """Weight that turns a per-rank MEAN over `local_count` items into this rank's share of the mean over the items of
+    ALL ranks: local_count / sum_over_ranks(local_count) (one scalar all-reduce).
+
+    Used for the class term of the region loss (`train/cross_entropy = 1`): the reference computes the loss on the
+    batch gathered from all replicas (train.py:344-347), where that term is a mean over the positives of the whole
+    batch and is then divided by cnt = B_global * cells * A (model/__init__.py:162-166).  With images sharded over
+    ranks, (sum_r CE_r / N_r) * f_r / cnt_local averaged over ranks equals (sum CE / N_total) / cnt_global exactly
+    when f_r = N_r / N_total, because cnt_global = world * cnt_local.  The sum-type terms need no correction.
+    `local_count`: 0-dim tensor (any numeric dtype; CUDA with NCCL, CPU with gloo).  Returns a float32 0-dim tensor."""
+    n = local_count.detach().to(torch.float32).reshape(())
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(process_group) == 1:
+        return torch.ones_like(n)
+    total = n.clone()
+    dist.all_reduce(total, op=dist.ReduceOp.SUM, group=process_group)
+    return n / total.clamp(min=1.0)
+
+
 def shard_range(total, rank, world):
     """Contiguous [start, end) of `total` images owned by `rank` (remainder spread over the first ranks)."""
     base, rem = divmod(total, world)

@@ -11,6 +11,9 @@ import logging
 import torch
 import torch.nn as nn
 
+import torch.distributed as _dist
+
+from b200 import ddp as _ddp
 from b200 import ops as _ops
 
 
@@ -135,5 +138,9 @@ def loss(anchors, data, pred, threshold, cross_entropy=True):
     names = ('foreground', 'background', 'center', 'size', 'cls')
     per = feature.size(1) // anchors.size(0)
     losses = {k: v for k, v in zip(names, values) if k != 'cls' or per > 5}
+    if 'cls' in losses and cross_entropy and _dist.is_available() and _dist.is_initialized() and _dist.get_world_size() > 1:
+        # data parallel: the class term is a mean over the positives of the WHOLE batch in the reference (loss on the
+        # gathered batch, train.py:344-347); re-weight this rank's mean so that the rank-averaged gradient matches it
+        losses['cls'] = losses['cls'] * _ddp.global_mean_factor(aux['pos_count'].sum())
     debug = dict(iou=aux['best_iou'], positive=aux['positive'], negative=aux['negative'], pos_count=aux['pos_count'])
     return losses, debug
