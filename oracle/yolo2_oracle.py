@@ -626,3 +626,51 @@ def synth_eval_case(seed, n_det=60, n_gt=12, num_cls=4, extent=13.0):
     det_cls = torch.where(torch.rand(n_det, generator=g) < 0.8, gt_cls[src], torch.randint(0, num_cls, (n_det,), generator=g))
     score = torch.sort(torch.rand(n_det, generator=g), descending=True)[0]
     return dict(gt_min=gt_min, gt_max=gt_max, gt_cls=gt_cls, det_min=det_min, det_max=det_max, det_cls=det_cls, score=score)
+
+
+# ----------------------------------------------------------------------------------------------
+# Input pipeline: cv2.resize (8-bit INTER_LINEAR) + box scaling (transform/resize/label.py:25-31) -- SURVEY 8f rank 2
+# ----------------------------------------------------------------------------------------------
+def _resize_axis(n_dst, n_src):
+    """OpenCV's linear-resize source index / fraction for one axis (imgproc resize.cpp): fx = float((d + 0.5) * scale - 0.5)."""
+    d = np.arange(n_dst)
+    f = ((d + 0.5) * (n_src / n_dst) - 0.5).astype(np.float32)
+    s = np.floor(f).astype(np.int32)
+    return s, (f - s).astype(np.float32)
+
+
+def resize_u8(src, height, width):
+    """cv2.resize(src, (width, height)) for uint8 HWC images, restated from OpenCV's 8-bit fixed-point path: 11-bit
+    coefficients rounded half-to-even; horizontally the fraction is dropped at the borders, vertically the rows are
+    clamped but the fraction kept; column pass (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2."""
+    h0, w0 = src.shape[:2]
+    sx, fx = _resize_axis(width, w0)
+    lo, hi = sx < 0, sx >= w0 - 1
+    fx[lo] = 0; sx[lo] = 0
+    fx[hi] = 0; sx[hi] = w0 - 1
+    ax0 = np.rint((np.float32(1.0) - fx) * np.float32(2048)).astype(np.int32)
+    ax1 = np.rint(fx * np.float32(2048)).astype(np.int32)
+    sx1 = np.minimum(sx + 1, w0 - 1)
+    sy, fy = _resize_axis(height, h0)
+    ay0 = np.rint((np.float32(1.0) - fy) * np.float32(2048)).astype(np.int32)
+    ay1 = np.rint(fy * np.float32(2048)).astype(np.int32)
+    r0, r1 = np.clip(sy, 0, h0 - 1), np.clip(sy + 1, 0, h0 - 1)
+    s = src.astype(np.int32)
+    rows = s[:, sx, :] * ax0[None, :, None] + s[:, sx1, :] * ax1[None, :, None]
+    out = (((ay0[:, None, None] * (rows[r0] >> 4)) >> 16) + ((ay1[:, None, None] * (rows[r1] >> 4)) >> 16) + 2) >> 2
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
+def rescale_label(image, yx_min, yx_max, height, width):
+    """transform/resize/label.py:25-31."""
+    _height, _width = image.shape[:2]
+    scale = np.array([height / _height, width / _width], np.float32)
+    return resize_u8(image, height, width), yx_min * scale, yx_max * scale
+
+
+def synth_frame(seed, h, w):
+    """Deterministic uint8 BGR frame with smooth structure + noise (so interpolation is exercised at all phases)."""
+    rng = np.random.RandomState(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    base = np.stack([127 + 120 * np.sin(yy / (5.0 + c) + xx / (9.0 - c)) for c in range(3)], -1)
+    return np.clip(base + rng.randint(-40, 41, (h, w, 3)), 0, 255).astype(np.uint8)

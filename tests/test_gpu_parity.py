@@ -704,6 +704,30 @@ def test_graphed_training_step_matches_eager():
             assert 0.5 <= (dg.norm() / de.norm()).item() <= 2.0, k
 
 
+@pytest.mark.parametrize('case', [(3, 26, 26, 64, 192, 3), (2, 13, 13, 256, 512, 1), (5, 10, 14, 128, 1024, 3), (64, 13, 13, 512, 1024, 3)])
+def test_conv_fused_batch_statistics(ops, case):
+    """yb_conv_bn_act_stats_fwd: same z as the plain kernel, bit for bit, and per-channel sum / sum of squares of the
+    stored fp16 values equal to a separate yb_bn_stats pass (float partial sums in a different order: 1e-5)."""
+    b, h, w, cin, cout, k = case
+    gen = torch.Generator().manual_seed(cin + cout)
+    x = torch.randn(b, h, w, cin, generator=gen).half().to(DEV)
+    wt = (torch.randn(cout, cin, k, k, generator=gen) * (2.0 / (cin * k * k)) ** 0.5)
+    w16 = ops.pack_weight_f16(wt.to(DEV))
+    one, zero = torch.ones(cout, device=DEV), torch.zeros(cout, device=DEV)
+    z_plain = ops.conv_bn_act(x, w16, one, zero, 1.0)
+    sums = torch.zeros(2 * cout, dtype=torch.float64, device=DEV)
+    z = ops.conv_bn_act_stats(x, w16, one, zero, 1.0, sums)
+    assert torch.equal(z, z_plain)
+    zf = z.double().reshape(-1, cout)
+    exact = torch.cat([zf.sum(0), (zf * zf).sum(0)])
+    scale = exact[cout:].sqrt().repeat(2) * (b * h * w) ** 0.5 + 1e-12      # ~ rows * rms: the natural size of both sums
+    assert ((sums - exact).abs() / scale).max().item() <= 1e-5
+    if 256 % (cout // 8) == 0:                                              # shapes the stand-alone statistics kernel takes
+        ref = torch.zeros(2 * cout, dtype=torch.float64, device=DEV)
+        ops.call('yb_bn_stats', z, cout, b * h * w, cout, ref)
+        assert ((ref - exact).abs() / scale).max().item() <= 1e-5
+
+
 def test_training_repacks_operands_under_fused_optimizer(ops):
     """torch.optim.Adam(fused=True) updates parameters without advancing their version counters; the training path must
     still see the new weights (it re-packs every step), and switching to eval() must re-fold / re-pack too."""
@@ -844,3 +868,48 @@ def test_eval_matching_vs_reference_golden(golden_dir):
     tp = yb_eval.matching_batch(tcat('det_min'), tcat('det_max'), tcat('det_cls'), torch.from_numpy(det_off), tcat('gt_min'), tcat('gt_max'),
                                 tcat('gt_cls'), torch.from_numpy(gt_off), 20, 0.45)
     assert np.array_equal(tp.cpu().numpy().astype(bool), np.concatenate(expect))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU input pipeline (reference transform/resize/label.py:25-31 + transform/image.py:27-29)
+# ------------------------------------------------------------------------------------------------
+def test_resize_batch_bit_exact_vs_cv2_golden(golden_dir):
+    """yb_resize_batch_u8: a ragged batch of frames -> network size in one launch, bit-identical to cv2.resize (goldens made by
+    the reference's rescale with cv2), BGR->RGB swap and box scaling included; then straight into the uint8 model input."""
+    import hashlib
+    import transform
+    import transform.resize.image
+    import transform.resize.label
+    g = np.load(os.path.join(golden_dir, 'resize.npz'))
+    out = transform.resize.image.rescale(g['small_src'], 64, 96)
+    assert out.is_cuda and np.array_equal(out.cpu().numpy(), g['small_out'])
+    for h, w in ((416, 416), (608, 608), (320, 320), (320, 608), (608, 320)):
+        seeds = [s for s in range(8) if tuple(int(v) for v in g['case%d_dims' % s][2:]) == (h, w)]
+        if not seeds:
+            continue
+        frames = [torch.from_numpy(O.synth_frame(s, int(g['case%d_dims' % s][0]), int(g['case%d_dims' % s][1]))) for s in seeds]
+        batch = transform.resize_batch(frames, h, w, bgr2rgb=False).cpu().numpy()
+        for i, s in enumerate(seeds):
+            assert hashlib.sha256(batch[i].tobytes()).digest() == g['case%d_sha' % s].tobytes(), s
+        swapped = transform.resize_batch(frames, h, w, bgr2rgb=True).cpu().numpy()
+        assert np.array_equal(swapped, batch[..., ::-1])
+    # labels: same float32 arithmetic as numpy
+    src = O.synth_frame(3, 100, 80)
+    yx_min = np.array([[3.5, 7.25], [40.0, 11.0], [0.0, 0.0]], np.float32)
+    yx_max = np.array([[30.0, 50.5], [99.0, 79.0], [0.0, 0.0]], np.float32)
+    r_ref, a_ref, b_ref = O.rescale_label(src, yx_min.copy(), yx_max.copy(), 416, 416)
+    r, a, b = transform.resize.label.rescale(src, yx_min, yx_max, 416, 416)
+    assert np.array_equal(r.cpu().numpy(), r_ref) and np.array_equal(a.cpu().numpy(), a_ref) and np.array_equal(b.cpu().numpy(), b_ref)
+    # the resized RGB uint8 batch is a valid model input (ToTensor's 1/255 is applied by the first conv kernel)
+    import model
+    import model.yolo2
+    cfg = make_config(1)
+    anchors = O.anchors_yolo_voc()
+    dnn = model.yolo2.Darknet(model.ConfigChannels(cfg), anchors, 20)
+    dnn.load_state_dict(O.make_state_dict(0), strict=False)
+    dnn = dnn.to(DEV).eval()
+    frames = [torch.from_numpy(O.synth_frame(20 + i, 90 + 13 * i, 120 + 7 * i)) for i in range(3)]
+    u8 = transform.resize_batch(frames, 64, 64, bgr2rgb=True)
+    f_u8 = dnn(u8)
+    f_f32 = dnn((u8.float() / 255.0).permute(0, 3, 1, 2).contiguous())
+    assert rel_err(f_u8, f_f32) <= 2e-3

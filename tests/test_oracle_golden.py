@@ -197,3 +197,26 @@ def test_eval_matching_and_ap_oracle_matches_reference_golden(golden_dir):
         for metric07 in (0, 1):
             ap = O.average_precision(g['sorted_tp_cls%d' % c], int(g['num_cls%d' % c]), bool(metric07))
             assert abs(ap - float(g['ap%d_cls%d' % (metric07, c)])) <= 1e-12, (c, metric07)
+
+
+def test_resize_oracle_matches_cv2_golden(golden_dir):
+    """oracle.resize_u8 / rescale_label (OpenCV's 8-bit INTER_LINEAR restated) against outputs of the reference's
+    transform.resize.label.rescale run with cv2 itself (tests/golden/make_golden_resize.py): bit-exact."""
+    import hashlib
+    g = load(golden_dir, 'resize.npz')
+    assert np.array_equal(O.resize_u8(g['small_src'], 64, 96), g['small_out'])
+    for seed in range(8):
+        h0, w0, h, w = (int(v) for v in g['case%d_dims' % seed])
+        out = O.resize_u8(O.synth_frame(seed, h0, w0), h, w)
+        assert out.shape == (h, w, 3)
+        assert hashlib.sha256(out.tobytes()).digest() == g['case%d_sha' % seed].tobytes(), seed
+    jpg = '/root/reference/image.jpg'
+    if os.path.exists(jpg):                                   # build container only: the reference's own sample image
+        import cv2
+        img = cv2.imread(jpg)
+        if hashlib.sha256(img.tobytes()).digest() == g['jpg_src_sha'].tobytes():
+            r, a, b = O.rescale_label(img, g['jpg_yx_min_in'].copy(), g['jpg_yx_max_in'].copy(), 416, 416)
+            assert hashlib.sha256(r.tobytes()).digest() == g['jpg_sha_bgr'].tobytes()
+            assert hashlib.sha256(r[..., ::-1].tobytes()).digest() == g['jpg_sha_rgb'].tobytes()
+            assert np.array_equal(a, g['jpg_yx_min']) and np.array_equal(b, g['jpg_yx_max'])
+            assert np.array_equal(r[100:132, 200:232], g['jpg_crop'])

@@ -151,6 +151,23 @@ def conv_bn_act(x, w, scale, shift, slope, out=None, out_mode=OUT_F16_NHWC, y_ch
     return out
 
 
+def conv_bn_act_stats(x, w, scale, shift, slope, sums, out=None, flags=0):
+    """conv_bn_act (fp16 NHWC out) that also accumulates per-channel sum / sum of squares of the stored outputs into
+    `sums` (float64 [2*Cout], zero on entry) in its epilogue -- the training forward's batch statistics."""
+    _req(x, torch.float16, 'x'); _req(w, torch.float16, 'w'); _req(scale, torch.float32, 'scale'); _req(shift, torch.float32, 'shift')
+    _req(sums, torch.float64, 'sums')
+    b, h, wd, x_ld = x.shape
+    cout, k, _, cin = w.shape
+    if sums.numel() != 2 * cout:
+        raise ValueError('sums must hold 2 * Cout doubles')
+    if out is None:
+        out = torch.empty(b, h, wd, cout, dtype=torch.float16, device=x.device)
+    _req(out, torch.float16, 'out')
+    _ck(_l.load().yb_conv_bn_act_stats_fwd(_p(x), _p(w), _p(scale), _p(shift), float(slope), _p(out), b, h, wd, cin, cout, k, x_ld, out.shape[-1], 0,
+                                           flags, _p(sums), _s()), 'yb_conv_bn_act_stats_fwd')
+    return out
+
+
 def maxpool2x2(x, channels=None, out=None):
     _req(x, torch.float16, 'x')
     b, h, w, x_ld = x.shape

@@ -31,6 +31,8 @@ class DarknetTrainer(object):
         self.sums = {}       # per-unit double[2C] accumulators (self-cleaning)
         self.wd_cache = {}   # dgrad weight buffers per unit (contents re-packed every step)
         self.on_grad = None  # optional callback(name, grad) fired as soon as a parameter gradient is enqueued (DDP overlap)
+        self.fuse_stats = True   # BN batch statistics in the conv epilogue (yb_conv_bn_act_stats_fwd) instead of yb_bn_stats
+        self._fused_stats = False
 
     # ---- helpers -------------------------------------------------------------------------------------
     def _emit(self, name, grads):
@@ -52,8 +54,14 @@ class DarknetTrainer(object):
             self.sums[key] = t
         return t
 
-    def _raw_conv(self, u, src, out=None, **kw):
+    def _raw_conv(self, u, src, out=None, key=None, **kw):
+        """Raw conv output z.  With `key` (a BN unit of the generic kernel) the batch statistics are accumulated in the
+        conv epilogue into the unit's double accumulators, so `_bn_forward` does not read z again."""
         one, zero = self._ones(u.cout, src.device)
+        self._fused_stats = False
+        if key is not None and self.fuse_stats and not (u.cin == 32 and u.ksize == 3 and u.cout <= 64):
+            self._fused_stats = True
+            return ops.conv_bn_act_stats(src, u.w16, one, zero, 1.0, self._sums(('f', key), u.cout, src.device), out=out)
         return ops.conv_bn_act(src, u.w16, one, zero, 1.0, out=out, **kw)
 
     def _bn_forward(self, key, u, z, rows):
@@ -63,7 +71,9 @@ class DarknetTrainer(object):
         sums = self._sums(('f', key), c, dev)
         mean = torch.empty(c, dtype=torch.float32, device=dev)
         invstd = torch.empty(c, dtype=torch.float32, device=dev)
-        ops.call('yb_bn_stats', z, z.shape[-1], rows, c, sums)
+        if not getattr(self, '_fused_stats', False):
+            ops.call('yb_bn_stats', z, z.shape[-1], rows, c, sums)
+        self._fused_stats = False
         ops.call('yb_bn_finalize', sums, rows, c, float(bn.eps), float(bn.momentum), bn.running_mean, bn.running_var, mean, invstd)
         if bn.num_batches_tracked is not None:
             bn.num_batches_tracked += 1
@@ -108,7 +118,7 @@ class DarknetTrainer(object):
         record('layers1.0', u0, None, z, mean, invstd, h, w, True)
         hh, ww = h // 2, w // 2
         for u, key, pooled in zip(eng.units1[1:], eng._k1[1:], eng.pools1[1:]):
-            z = self._raw_conv(u, cur)
+            z = self._raw_conv(u, cur, key=key)
             mean, invstd = self._bn_forward(key, u, z, b * hh * ww)
             last = key == eng._k1[-1]
             a = self._apply(u, z, mean, invstd, b, hh, ww, pooled and not last)
@@ -121,7 +131,7 @@ class DarknetTrainer(object):
         upt = eng.unit_pt
         cat_ch = upt.cout * 4 + eng.units2[-1].cout
         cat = torch.empty(b, hh // 2, ww // 2, cat_ch, dtype=torch.float16, device=dev)
-        z = self._raw_conv(upt, x1)
+        z = self._raw_conv(upt, x1, key='passthrough')
         mean, invstd = self._bn_forward('passthrough', upt, z, b * hh * ww)
         a_pt = self._apply(upt, z, mean, invstd, b, hh, ww, False)
         record('passthrough', upt, x1, z, mean, invstd, hh, ww, False)
@@ -130,7 +140,7 @@ class DarknetTrainer(object):
         cur = ops.maxpool2x2(x1)
         h32, w32 = hh // 2, ww // 2
         for i, (u, key) in enumerate(zip(eng.units2, eng._k2)):
-            z = self._raw_conv(u, cur)
+            z = self._raw_conv(u, cur, key=key)
             mean, invstd = self._bn_forward(key, u, z, b * h32 * w32)
             if i == len(eng.units2) - 1:
                 self._apply(u, z, mean, invstd, b, h32, w32, False, out=cat, a_off=upt.cout * 4)
@@ -141,7 +151,7 @@ class DarknetTrainer(object):
             cur = a
         saved.keys2 = list(eng._k2[:len(eng.units2)])
         u30, u31 = eng.units3
-        z = self._raw_conv(u30, cat)
+        z = self._raw_conv(u30, cat, key='layers3.0')
         mean, invstd = self._bn_forward('layers3.0', u30, z, b * h32 * w32)
         a30 = self._apply(u30, z, mean, invstd, b, h32, w32, False)
         record('layers3.0', u30, cat, z, mean, invstd, h32, w32, False)

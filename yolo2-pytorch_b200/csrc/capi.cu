@@ -62,7 +62,7 @@ int* debug_word_device() {
 // implemented in the kernel translation units
 long long conv_workspace_bytes();
 int conv_igemm_forward(const void*, const void*, const float*, const float*, float, void*, int, int, int, int, int, int, int, long long,
-                       int, int, int, void*, long long, cudaStream_t);
+                       int, int, int, void*, long long, double*, cudaStream_t);
 int conv_ref_forward(const void*, const void*, const float*, const float*, float, void*, int, int, int, int, int, int, int, long long,
                      int, int, cudaStream_t);
 int pack_weight(const float*, void*, int, int, int, int, int, cudaStream_t);
@@ -91,6 +91,7 @@ int bn_param_grad(double*, int, float*, float*, int, float, cudaStream_t);
 int reorg_bwd(const void*, long long, int, void*, int, int, int, int, cudaStream_t);
 int head_grad_prepare(const float*, void*, float*, int, int, int, int, cudaStream_t);
 int conv0_wgrad(const float*, const void*, float*, int, int, int, cudaStream_t);
+int resize_batch_u8(const void*, const long long*, const int*, void*, int, int, int, int, float*, float*, int, cudaStream_t);
 int eval_match(const float*, const float*, const int*, const int*, const float*, const float*, const int*, const int*, int, int, int, float, float,
                unsigned char*, cudaStream_t);
 int unpack_wgrad(const float*, float*, int, int, int, float, cudaStream_t);
@@ -140,7 +141,14 @@ int yb_conv_bn_act_fwd(const void* x, const void* w, const float* scale, const f
                        int height, int width, int cin, int cout, int ksize, int x_ld, long long y_ld, int y_ch_off, int out_mode,
                        int flags, yb_stream_t stream) {
   return yb::conv_igemm_forward(x, w, scale, shift, slope, y, batch, height, width, cin, cout, ksize, x_ld, y_ld, y_ch_off, out_mode,
-                                flags, nullptr, 0, S(stream));
+                                flags, nullptr, 0, nullptr, S(stream));
+}
+
+int yb_conv_bn_act_stats_fwd(const void* x, const void* w, const float* scale, const float* shift, float slope, void* y, int batch,
+                             int height, int width, int cin, int cout, int ksize, int x_ld, long long y_ld, int y_ch_off, int flags,
+                             double* sums, yb_stream_t stream) {
+  return yb::conv_igemm_forward(x, w, scale, shift, slope, y, batch, height, width, cin, cout, ksize, x_ld, y_ld, y_ch_off, 0, flags, nullptr, 0,
+                                sums, S(stream));
 }
 
 long long yb_conv_workspace_bytes(void) { return yb::conv_workspace_bytes(); }
@@ -149,7 +157,7 @@ int yb_conv_bn_act_fwd_ws(const void* x, const void* w, const float* scale, cons
                           int height, int width, int cin, int cout, int ksize, int x_ld, long long y_ld, int y_ch_off, int out_mode,
                           int flags, void* workspace, long long workspace_bytes, yb_stream_t stream) {
   return yb::conv_igemm_forward(x, w, scale, shift, slope, y, batch, height, width, cin, cout, ksize, x_ld, y_ld, y_ch_off, out_mode,
-                                flags, workspace, workspace_bytes, S(stream));
+                                flags, workspace, workspace_bytes, nullptr, S(stream));
 }
 
 int yb_conv_ref_fwd(const void* x, const void* w, const float* scale, const float* shift, float slope, void* y, int batch, int height,
@@ -267,6 +275,11 @@ int yb_conv_wgrad(const void* x, const void* dz, float* dw_krsc, int batch, int 
 
 int yb_unpack_wgrad(const float* dw_krsc, float* dw_oihw, int cout, int cin, int ksize, float scale, yb_stream_t stream) {
   return yb::unpack_wgrad(dw_krsc, dw_oihw, cout, cin, ksize, scale, S(stream));
+}
+
+int yb_resize_batch_u8(const void* src, const long long* src_off, const int* src_hw, void* dst, int batch, int height, int width, int swap_rb,
+                       float* yx_min, float* yx_max, int slots, yb_stream_t stream) {
+  return yb::resize_batch_u8(src, src_off, src_hw, dst, batch, height, width, swap_rb, yx_min, yx_max, slots, S(stream));
 }
 
 int yb_eval_match(const float* det_yx_min, const float* det_yx_max, const int* det_cls, const int* det_off, const float* gt_yx_min,

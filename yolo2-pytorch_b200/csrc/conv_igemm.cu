@@ -51,6 +51,9 @@ struct ConvParams {
   float* ws;                   // [gridDim.x][MT][BN/32][128][32] fp32
   unsigned* flags;             // [gridDim.x], 0 = empty, 1 = partial ready (reset by the consumer)
   unsigned long long* trace;   // optional (tools/conv_trace.py): block 0 records clock64() per pipeline event, 3 roles x 256 slots
+  // optional (training): per-channel sum and sum of squares of the STORED (fp16-rounded) outputs, added into
+  // stats[0..Cout) / stats[Cout..2Cout) -- the batch statistics of train-mode BatchNorm without a second pass over z
+  double* stats;
 };
 
 // role 0 = TMA producer, 1 = MMA issuer, 2 = epilogue thread 0; slot = running event index of that role
@@ -125,7 +128,7 @@ struct ConvCfg {
   static constexpr int kRowsPerCta = BM * MT;
   static constexpr bool kMergedA = (MT == 2 && !kPair);        // A tile fetched by one 256-pixel TMA box
   static constexpr int kRowsPerTile = kRowsPerCta * (kPair ? 2 : 1);
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 2 * 2 * BN * 4 /*scale/shift x2*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 2 * 2 * BN * 4 /*scale/shift x2*/ + 2 * BN * 4 /*stats*/ + 256 /*barriers*/;
   static_assert(kAccCols <= 512, "accumulator does not fit TMEM");
 };
 
@@ -144,7 +147,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const uint32_t smem_b = smem_base + kStages * Cfg::kABytes;
   float* ep_scale = reinterpret_cast<float*>(smem_gen + kStages * Cfg::kStageBytes);  // [2][BN]
   float* ep_shift = ep_scale + 2 * BN;                                                  // [2][BN]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ep_shift + 2 * BN);
+  float* ep_stats = ep_shift + 2 * BN;                                                  // [2][BN] sum, sum of squares of this tile
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ep_stats + 2 * BN);
   const uint32_t bar_full = smem_u32(bars);                 // [kStages]  (pair: only the leader's are used)
   const uint32_t bar_empty = bar_full + 8 * kStages;        // [kStages]
   const uint32_t bar_tfull = bar_empty + 8 * kStages;       // [2]
@@ -323,6 +327,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const int c = n0 + i;
         sc[i] = (c < p.cout) ? __ldg(p.scale + c) : 0.f;
         sh[i] = (c < p.cout) ? __ldg(p.shift + c) : 0.f;
+        if (p.stats != nullptr) { ep_stats[i] = 0.f; ep_stats[BN + i] = 0.f; }
       }
       if (sk_collect) {
         // the CTA whose range contains this tile's first unit, by inverting sk_start()
@@ -411,6 +416,29 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             f[j] = x > 0.f ? x : x * p.slope;
           }
           if (p.skip & 8) continue;
+          if (p.stats != nullptr) {
+            // column sums over this warp's 32 rows by recursive halving: after step s a lane keeps the half of its values
+            // whose column bit s equals its lane bit s (31 shuffles per quantity); lane l ends up with column cbase + l
+            float a1[32], a2[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float r = row_ok ? __half2float(__float2half_rn(f[j])) : 0.f;      // statistics of the value that is stored
+              a1[j] = r; a2[j] = r * r;
+            }
+#pragma unroll
+            for (int s = 16; s >= 1; s >>= 1) {
+              const bool up = (lane & s) != 0;
+#pragma unroll
+              for (int j = 0; j < s; ++j) {
+                const float k1 = up ? a1[j + s] : a1[j], g1 = up ? a1[j] : a1[j + s];
+                const float k2 = up ? a2[j + s] : a2[j], g2 = up ? a2[j] : a2[j + s];
+                a1[j] = k1 + __shfl_xor_sync(0xffffffffu, g1, s);
+                a2[j] = k2 + __shfl_xor_sync(0xffffffffu, g2, s);
+              }
+            }
+            atomicAdd(&ep_stats[cc * 32 + lane], a1[0]);
+            atomicAdd(&ep_stats[BN + cc * 32 + lane], a2[0]);
+          }
           if (p.out_mode == 0) {
             if (row_ok) {
               __half* dst = reinterpret_cast<__half*>(p.y) + static_cast<long long>(row) * p.y_ld + p.y_ch_off + cbase;
@@ -447,6 +475,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       if (lane == 0) {
         if (!kPair || rank == 0) mbar_arrive(bar_tempty + 8 * acc);
         else mbar_arrive_remote(bar_tempty + 8 * acc, 0);
+      }
+      if (p.stats != nullptr) {
+        // this tile's column sums -> the global double accumulators (the bar.sync at the top of the next tile orders the
+        // re-zeroing of ep_stats after these reads)
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int i = et; i < BN; i += kEpiThreads) {
+          if (n0 + i < p.cout) {
+            atomicAdd(p.stats + n0 + i, static_cast<double>(ep_stats[i]));
+            atomicAdd(p.stats + p.cout + n0 + i, static_cast<double>(ep_stats[BN + i]));
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
       if (sk_collect) {
         // every reader is done with the partials: hand the slots back (the next writer is a later launch)
@@ -1031,8 +1071,9 @@ static int conv_c32_forward(const void* x, const void* w, const float* scale, co
 
 int conv_igemm_forward(const void* x, const void* w, const float* scale, const float* shift, float slope, void* y, int batch,
                        int height, int width, int cin, int cout, int ksize, int x_ld, long long y_ld, int y_ch_off, int out_mode,
-                       int flags, void* workspace, long long workspace_bytes, cudaStream_t stream) {
+                       int flags, void* workspace, long long workspace_bytes, double* stats, cudaStream_t stream) {
   YB_REQUIRE(x && w && scale && shift && y, "conv: null pointer");
+  YB_REQUIRE(stats == nullptr || (out_mode == 0 && !(cin == 32 && ksize == 3 && cout <= 64)), "conv: fused statistics need the generic fp16 NHWC kernel");
   YB_REQUIRE(ksize == 1 || ksize == 3, "conv: ksize %d unsupported (1 or 3)", ksize);
   YB_REQUIRE(batch > 0 && height > 0 && width > 0, "conv: bad shape");
   YB_REQUIRE(cin % 32 == 0, "conv: Cin=%d must be a multiple of 32 (layer 0 uses yb_conv0_*)", cin);
@@ -1059,7 +1100,7 @@ int conv_igemm_forward(const void* x, const void* w, const float* scale, const f
   // accumulator fills all of TMEM (256x256) cannot overlap its epilogue with the next mainloop.
   int bn = 0, mt = 0, pair = 0, streamk = 0;
   // stream-K needs the caller's workspace (one per stream: partial sums + flags); flags bit 3 forbids, bit 30 forces it
-  const bool sk_possible = workspace != nullptr && workspace_bytes >= conv_workspace_bytes() && (flags & 8) == 0 &&
+  const bool sk_possible = stats == nullptr && workspace != nullptr && workspace_bytes >= conv_workspace_bytes() && (flags & 8) == 0 &&
                            (reinterpret_cast<uintptr_t>(workspace) & 255) == 0;
   const bool sk_force = sk_possible && ((flags >> 30) & 1);
   const int force_bn = (flags >> 8) & 0x3FF;
@@ -1144,6 +1185,7 @@ int conv_igemm_forward(const void* x, const void* w, const float* scale, const f
   p.trace = g_conv_trace;
   p.skip = (flags >> 24) & 0xF;
   p.streamk = streamk;
+  p.stats = stats;
   p.sk_base = 0; p.sk_rem = 0; p.ws = nullptr; p.flags = nullptr;
   if (streamk) {
     const long long units = static_cast<long long>(p.m_tiles) * p.n_tiles * p.num_kb;

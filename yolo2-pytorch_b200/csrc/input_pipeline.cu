@@ -1,0 +1,101 @@
+// GPU input pipeline: the step immediately upstream of the first conv kernel.
+// Replaces, for a whole batch of decoded frames in ONE launch, what the reference does per image on the CPU:
+//   transform/resize/image.py:23-24 / label.py:25-31  `rescale`: cv2.resize(image, (width, height)) (INTER_LINEAR, uint8) and the
+//                                                      box scaling yx *= (height / _height, width / _width)
+//   transform/image.py:27-29                          BGR2RGB
+// (ToTensor's 1/255 and the HWC -> network layout change are already fused into yb_conv0_u8_bn_leaky_pool_fwd.)
+//
+// Exactness contract: bit-identical to cv2.resize (OpenCV 4.x, 8-bit, INTER_LINEAR) -- the arithmetic lives in the
+// reference's third-party dependency, so it is restated here from its published algorithm (modules/imgproc resize.cpp,
+// the 8-bit fixed-point path) and pinned by fixtures generated with cv2 itself:
+//   fx = float((dx + 0.5) * (src_w / dst_w) - 0.5) (double arithmetic, one rounding to float); sx = floor(fx); fx -= sx;
+//   horizontally sx < 0 -> (sx, fx) = (0, 0), sx >= src_w - 1 -> (src_w - 1, 0); vertically the two rows are clamped
+//   to the image but the fraction is kept; coefficients are rounded to 11-bit fixed point with round-half-even
+//   (saturate_cast<short>(c * 2048)); the row pass is S[sx] * a0 + S[sx + 1] * a1 in int, the column pass
+//   (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2.
+#include "yb_common.h"
+#include <stdint.h>
+
+namespace yb {
+
+struct ResizeCoef { int s0, s1, a0, a1; };
+
+__device__ __forceinline__ ResizeCoef resize_coef(int d, int n_dst, int n_src, bool clamp_fraction) {
+  const double scale = static_cast<double>(n_src) / static_cast<double>(n_dst);
+  float f = static_cast<float>((static_cast<double>(d) + 0.5) * scale - 0.5);
+  int s = static_cast<int>(floorf(f));
+  f -= static_cast<float>(s);
+  ResizeCoef c;
+  if (clamp_fraction) {
+    if (s < 0) { f = 0.f; s = 0; }
+    if (s >= n_src - 1) { f = 0.f; s = n_src - 1; }
+    c.s0 = s;
+    c.s1 = s + 1 < n_src ? s + 1 : n_src - 1;
+  } else {
+    c.s0 = s < 0 ? 0 : (s < n_src ? s : n_src - 1);
+    c.s1 = s + 1 < 0 ? 0 : (s + 1 < n_src ? s + 1 : n_src - 1);
+  }
+  c.a0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
+  c.a1 = __float2int_rn(__fmul_rn(f, 2048.f));
+  return c;
+}
+
+// one thread per output pixel (3 channels); blockIdx.y = image
+__global__ void __launch_bounds__(256) resize_u8_kernel(const uint8_t* __restrict__ src, const long long* __restrict__ src_off,
+                                                        const int* __restrict__ src_hw, uint8_t* __restrict__ dst, int height, int width,
+                                                        int swap_rb) {
+  const int img = blockIdx.y;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= height * width) return;
+  const int dy = idx / width, dx = idx - dy * width;
+  const int sh = src_hw[2 * img], sw = src_hw[2 * img + 1];
+  const uint8_t* s = src + src_off[img];
+  const ResizeCoef cx = resize_coef(dx, width, sw, true);
+  const ResizeCoef cy = resize_coef(dy, height, sh, false);
+  const uint8_t* r0 = s + static_cast<long long>(cy.s0) * sw * 3;
+  const uint8_t* r1 = s + static_cast<long long>(cy.s1) * sw * 3;
+  uint8_t out[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int h0 = static_cast<int>(r0[cx.s0 * 3 + c]) * cx.a0 + static_cast<int>(r0[cx.s1 * 3 + c]) * cx.a1;
+    const int h1 = static_cast<int>(r1[cx.s0 * 3 + c]) * cx.a0 + static_cast<int>(r1[cx.s1 * 3 + c]) * cx.a1;
+    int v = (((cy.a0 * (h0 >> 4)) >> 16) + ((cy.a1 * (h1 >> 4)) >> 16) + 2) >> 2;
+    v = v < 0 ? 0 : (v > 255 ? 255 : v);
+    out[c] = static_cast<uint8_t>(v);
+  }
+  uint8_t* d = dst + (static_cast<long long>(img) * height * width + idx) * 3;
+  d[0] = swap_rb ? out[2] : out[0];
+  d[1] = out[1];
+  d[2] = swap_rb ? out[0] : out[2];
+}
+
+// boxes [B, G, 2] (y, x): yx *= (height / src_h, width / src_w) in float32 exactly as numpy does it (label.py:27-30)
+__global__ void rescale_boxes_kernel(float* __restrict__ yx_min, float* __restrict__ yx_max, const int* __restrict__ src_hw, int batch, int slots,
+                                     int height, int width) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch * slots) return;
+  const int img = i / slots;
+  // np.array([height / _height, width / _width], np.float32): a double division rounded once more to float32
+  const float sy = static_cast<float>(static_cast<double>(height) / static_cast<double>(src_hw[2 * img]));
+  const float sx = static_cast<float>(static_cast<double>(width) / static_cast<double>(src_hw[2 * img + 1]));
+  yx_min[2 * i] = __fmul_rn(yx_min[2 * i], sy); yx_min[2 * i + 1] = __fmul_rn(yx_min[2 * i + 1], sx);
+  yx_max[2 * i] = __fmul_rn(yx_max[2 * i], sy); yx_max[2 * i + 1] = __fmul_rn(yx_max[2 * i + 1], sx);
+}
+
+int resize_batch_u8(const void* src, const long long* src_off, const int* src_hw, void* dst, int batch, int height, int width, int swap_rb,
+                    float* yx_min, float* yx_max, int slots, cudaStream_t stream) {
+  YB_REQUIRE(src && src_off && src_hw && dst && batch > 0 && height > 0 && width > 0, "resize_batch_u8: bad argument");
+  YB_REQUIRE((yx_min == nullptr) == (yx_max == nullptr) && slots >= 0, "resize_batch_u8: boxes come as a (yx_min, yx_max) pair");
+  const int pixels = height * width;
+  resize_u8_kernel<<<dim3((pixels + 255) / 256, batch), 256, 0, stream>>>(static_cast<const uint8_t*>(src), src_off, src_hw, static_cast<uint8_t*>(dst),
+                                                                          height, width, swap_rb);
+  int rc = check_launch("resize_u8_kernel");
+  if (rc) return rc;
+  if (yx_min != nullptr && slots > 0) {
+    rescale_boxes_kernel<<<(batch * slots + 127) / 128, 128, 0, stream>>>(yx_min, yx_max, src_hw, batch, slots, height, width);
+    rc = check_launch("rescale_boxes_kernel");
+  }
+  return rc;
+}
+
+}  // namespace yb

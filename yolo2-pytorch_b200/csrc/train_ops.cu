@@ -475,14 +475,29 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src, bool valid) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  const int n = valid ? 4 : 0;                                   // src-size 0: the 4 destination bytes are zero-filled
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gmem_src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+
+struct W0Smem {
+  float patch[2][3][kW0Rows + 2][kW0Cols + 2];
+  __align__(16) __half dzs[2][kW0Rows * kW0Cols][kW0DzStride];
+  float s_dw[32 * 32];            // [tap (padded)][co]
+};
+
 __global__ void __launch_bounds__(256) conv0_wgrad_kernel(const float* __restrict__ x, const __half* __restrict__ dz, float* __restrict__ dw, int batch,
                                                           int height, int width, int tiles_x, int tiles_y, int num_tiles) {
-  __shared__ float patch[3][kW0Rows + 2][kW0Cols + 2];
-  __shared__ __align__(16) __half dzs[kW0Rows * kW0Cols][kW0DzStride];
-  __shared__ float s_dw[32 * 32];            // [tap (padded)][co]
+  extern __shared__ __align__(16) uint8_t w0_raw[];
+  W0Smem& sm = *reinterpret_cast<W0Smem*>(w0_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  for (int i = tid; i < 32 * 32; i += 256) s_dw[i] = 0.f;
+  for (int i = tid; i < 32 * 32; i += 256) sm.s_dw[i] = 0.f;
   float acc[2][4][4];
 #pragma unroll
   for (int a = 0; a < 2; ++a)
@@ -500,38 +515,54 @@ __global__ void __launch_bounds__(256) conv0_wgrad_kernel(const float* __restric
     const int tc = a_ok[j] ? tap / 9 : 0, tr = a_ok[j] ? (tap % 9) / 3 : 0, ts = a_ok[j] ? tap % 3 : 0;
     a_off[j] = (tc * (kW0Rows + 2) + warp + tr) * (kW0Cols + 2) + ts;
   }
-  const float* pflat = &patch[0][0][0];
   // ldmatrix.x4.trans row addresses: matrix j = lane >> 3: K-half (j & 1), co block (j >> 1) (+2 for the second load)
   const int lm_row = (lane & 7) + ((lane >> 3) & 1) * 8;
   const int lm_col = (lane >> 4) * 8;
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+
+  // stage one tile (haloed fp32 patch + fp16 dz tile) into buffer `buf` with cp.async: the copy of tile i+1 overlaps the
+  // tensor-core work on tile i
+  auto stage = [&](int tile, int buf) {
     const int tx = tile % tiles_x;
     const int t2 = tile / tiles_x;
     const int ty = t2 % tiles_y;
     const int img = t2 / tiles_y;
     const int y0 = ty * kW0Rows, x0 = tx * kW0Cols;
-    __syncthreads();
     for (int i = tid; i < 3 * (kW0Rows + 2) * (kW0Cols + 2); i += 256) {
       const int c = i / ((kW0Rows + 2) * (kW0Cols + 2));
       const int rem = i - c * ((kW0Rows + 2) * (kW0Cols + 2));
       const int r = rem / (kW0Cols + 2), col = rem - r * (kW0Cols + 2);
       const int iy = y0 - 1 + r, ix = x0 - 1 + col;
-      patch[c][r][col] = (iy >= 0 && iy < height && ix >= 0 && ix < width) ? __ldg(x + ((static_cast<long long>(img) * 3 + c) * height + iy) * width + ix) : 0.f;
+      const bool ok = iy >= 0 && iy < height && ix >= 0 && ix < width;
+      const float* src = x + ((static_cast<long long>(img) * 3 + c) * height + (ok ? iy : 0)) * width + (ok ? ix : 0);
+      cp_async_4(&sm.patch[buf][c][r][col], src, ok);
     }
     for (int i = tid; i < kW0Rows * kW0Cols * 4; i += 256) {        // 4 x 16 B per pixel
       const int pix = i >> 2, part = i & 3;
       const int py = pix / kW0Cols, pxx = pix % kW0Cols;
-      *reinterpret_cast<uint4*>(&dzs[pix][part * 8]) =
-          __ldg(reinterpret_cast<const uint4*>(dz + ((static_cast<long long>(img) * height + y0 + py) * width + x0 + pxx) * 32) + part);
+      cp_async_16(&sm.dzs[buf][pix][part * 8], dz + ((static_cast<long long>(img) * height + y0 + py) * width + x0 + pxx) * 32 + part * 8);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  int buf = 0;
+  if (static_cast<int>(blockIdx.x) < num_tiles) stage(blockIdx.x, 0);
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int next = tile + gridDim.x;
+    if (next < num_tiles) {
+      stage(next, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
+    const float* pflat = &sm.patch[buf][0][0][0];
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
       // B fragments (dz): b[n-tile][0..1]
       uint32_t bfr[4][2];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const uint32_t addr = static_cast<uint32_t>(__cvta_generic_to_shared(&dzs[warp * kW0Cols + ks * 16 + lm_row][h * 16 + lm_col]));
+        const uint32_t addr = static_cast<uint32_t>(__cvta_generic_to_shared(&sm.dzs[buf][warp * kW0Cols + ks * 16 + lm_row][h * 16 + lm_col]));
         asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
                      : "=r"(bfr[2 * h][0]), "=r"(bfr[2 * h][1]), "=r"(bfr[2 * h + 1][0]), "=r"(bfr[2 * h + 1][1]) : "r"(addr));
       }
@@ -556,6 +587,8 @@ __global__ void __launch_bounds__(256) conv0_wgrad_kernel(const float* __restric
                        : "+f"(acc[mt][nt][0]), "+f"(acc[mt][nt][1]), "+f"(acc[mt][nt][2]), "+f"(acc[mt][nt][3])
                        : "r"(afr[mt][0]), "r"(afr[mt][1]), "r"(afr[mt][2]), "r"(afr[mt][3]), "r"(bfr[nt][0]), "r"(bfr[nt][1]));
     }
+    __syncthreads();                 // everyone is done with `buf` before the next iteration's prefetch overwrites it
+    buf ^= 1;
   }
   __syncthreads();
   // D fragment: (row g, cols 2t, 2t+1), (row g + 8, same cols) of each 16 x 8 tile
@@ -564,15 +597,15 @@ __global__ void __launch_bounds__(256) conv0_wgrad_kernel(const float* __restric
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
       const int r0 = mt * 16 + g, c0 = nt * 8 + t * 2;
-      atomicAdd(&s_dw[r0 * 32 + c0], acc[mt][nt][0]);
-      atomicAdd(&s_dw[r0 * 32 + c0 + 1], acc[mt][nt][1]);
-      atomicAdd(&s_dw[(r0 + 8) * 32 + c0], acc[mt][nt][2]);
-      atomicAdd(&s_dw[(r0 + 8) * 32 + c0 + 1], acc[mt][nt][3]);
+      atomicAdd(&sm.s_dw[r0 * 32 + c0], acc[mt][nt][0]);
+      atomicAdd(&sm.s_dw[r0 * 32 + c0 + 1], acc[mt][nt][1]);
+      atomicAdd(&sm.s_dw[(r0 + 8) * 32 + c0], acc[mt][nt][2]);
+      atomicAdd(&sm.s_dw[(r0 + 8) * 32 + c0 + 1], acc[mt][nt][3]);
     }
   __syncthreads();
   for (int i = tid; i < 27 * 32; i += 256) {
     const int k = i / 32, co = i % 32;                 // k = ci*9 + r*3 + s  -> OIHW flat index co*27 + k
-    atomicAdd(&dw[co * 27 + k], s_dw[i]);
+    atomicAdd(&dw[co * 27 + k], sm.s_dw[i]);
   }
 }
 
@@ -582,13 +615,15 @@ int conv0_wgrad(const float* x, const void* dz, float* dw, int batch, int height
   const int tiles_x = width / kW0Cols, tiles_y = height / kW0Rows;
   const long long tiles = static_cast<long long>(tiles_x) * tiles_y * batch;
   static int resident = 0;                       // persistent blocks: exactly what fits (a partial second wave would double the time)
+  const int smem = static_cast<int>(sizeof(W0Smem));
   if (resident == 0) {
-    YB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, conv0_wgrad_kernel, 256, 0));
+    YB_CUDA(cudaFuncSetAttribute(conv0_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    YB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, conv0_wgrad_kernel, 256, smem));
     if (resident < 1) resident = 1;
   }
   const int cap = sm_count() * resident;
   const int grid = tiles < cap ? static_cast<int>(tiles) : cap;
-  conv0_wgrad_kernel<<<grid, 256, 0, stream>>>(x, reinterpret_cast<const __half*>(dz), dw, batch, height, width, tiles_x, tiles_y,
+  conv0_wgrad_kernel<<<grid, 256, smem, stream>>>(x, reinterpret_cast<const __half*>(dz), dw, batch, height, width, tiles_x, tiles_y,
                                                static_cast<int>(tiles));
   return check_launch("conv0_wgrad_kernel");
 }

@@ -1,0 +1,35 @@
+"""transform -- the part of the reference's `transform/` package that sits immediately upstream of the network input
+(SURVEY 8f rank 2), on the GPU: `transform.resize.image.rescale`, `transform.resize.label.rescale`,
+`transform.image.BGR2RGB`, and the batched `transform.resize_batch` that does all three for a whole batch of decoded
+frames in one launch.  Augmentations (random crop / flip / rotate, `transform/augmentation.py`) are not part of this build."""
+import torch
+
+from b200 import ops as _ops
+
+
+def resize_batch(frames, height, width, bgr2rgb=True, yx_min=None, yx_max=None):
+    """frames: list of uint8 [h_i, w_i, 3] tensors (CPU or CUDA; BGR as cv2.imread gives them) -> uint8 CUDA tensor
+    [B, height, width, 3], cv2.resize-exact, RGB when `bgr2rgb`.  Optional padded boxes yx_min / yx_max [B, G, 2] (source
+    pixels) are returned scaled by (height / h_i, width / w_i) like transform.resize.label.rescale.  One kernel launch;
+    the result can be fed straight to the model (`Darknet.forward` accepts uint8 NHWC frames)."""
+    dev = torch.device('cuda', torch.cuda.current_device())
+    sizes, offs, total = [], [], 0
+    for f in frames:
+        if f.dtype != torch.uint8 or f.dim() != 3 or f.shape[2] != 3:
+            raise ValueError('frames must be uint8 [h, w, 3]')
+        sizes += [int(f.shape[0]), int(f.shape[1])]
+        offs.append(total)
+        total += f.numel()
+    packed = torch.empty(total, dtype=torch.uint8, device=dev)
+    for f, o in zip(frames, offs):
+        packed[o:o + f.numel()].copy_(f.reshape(-1), non_blocking=True)
+    src_off = torch.tensor(offs, dtype=torch.int64).to(dev, non_blocking=True)
+    src_hw = torch.tensor(sizes, dtype=torch.int32).to(dev, non_blocking=True)
+    out = torch.empty(len(frames), height, width, 3, dtype=torch.uint8, device=dev)
+    slots = 0
+    if yx_min is not None:
+        yx_min = yx_min.to(device=dev, dtype=torch.float32).contiguous().clone()
+        yx_max = yx_max.to(device=dev, dtype=torch.float32).contiguous().clone()
+        slots = yx_min.shape[1]
+    _ops.call('yb_resize_batch_u8', packed, src_off, src_hw, out, len(frames), int(height), int(width), int(bool(bgr2rgb)), yx_min, yx_max, slots)
+    return (out, yx_min, yx_max) if yx_min is not None else out
