@@ -1,0 +1,53 @@
+#!/usr/bin/env python
+"""Summarise `ncu --page raw --csv` tables (tools/ncu_capture.sh) into a compact markdown table:
+    python tools/ncu_summarise.py gpurun_out/ncu_infer_raw.csv > profiles/rNN_ncu_infer_full.md"""
+import csv
+import re
+import sys
+
+COLS = [('gpu__time_duration.sum', 'us', 1e-3), ('sm__inst_executed_pipe_tensor.sum', None, None),
+        ('sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active', 'tensor pipe %', 1.0),
+        ('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'tensor pipe %', 1.0),
+        ('dram__bytes_read.sum', 'DRAM rd MB', None), ('dram__bytes_write.sum', 'DRAM wr MB', None),
+        ('dram__throughput.avg.pct_of_peak_sustained_elapsed', 'dram %', 1.0), ('lts__throughput.avg.pct_of_peak_sustained_elapsed', 'L2 %', 1.0),
+        ('sm__throughput.avg.pct_of_peak_sustained_elapsed', 'SM %', 1.0), ('launch__registers_per_thread', 'regs', 1.0)]
+
+
+def to_bytes(value, unit):
+    mult = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(unit, 1)
+    return float(value.replace(',', '')) * mult
+
+
+def main(path):
+    rows = list(csv.reader(open(path)))
+    start = next(i for i, r in enumerate(rows) if r and r[0] == 'ID')
+    header, units = rows[start], rows[start + 1]
+    idx = {name: i for i, name in enumerate(header)}
+    tensor_key = next((k for k in idx if 'pipe_tensor' in k and 'pct_of_peak_sustained_active' in k), None)
+    print('| kernel | grid | us | tensor pipe % (active) | DRAM rd MB | DRAM wr MB | dram % | L2 % | SM % | regs |')
+    print('|---|---|---|---|---|---|---|---|---|---|')
+    tot_us = tot_rd = tot_wr = 0.0
+    n = 0
+    for r in rows[start + 2:]:
+        if len(r) < len(header):
+            continue
+        name = re.sub(r'\(.*', '', r[idx['Kernel Name']]).replace('void yb::', '').replace('yb::', '')
+
+        def num(key):
+            return float(r[idx[key]].replace(',', '')) if key in idx and r[idx[key]] not in ('', 'n/a') else float('nan')
+        dur = num('gpu__time_duration.sum')
+        dur_us = dur / 1e3 if units[idx['gpu__time_duration.sum']] in ('ns', 'nsecond') else (dur if units[idx['gpu__time_duration.sum']] in ('us', 'usecond') else dur * 1e3)
+        rd = to_bytes(r[idx['dram__bytes_read.sum']], units[idx['dram__bytes_read.sum']]) / 1e6
+        wr = to_bytes(r[idx['dram__bytes_write.sum']], units[idx['dram__bytes_write.sum']]) / 1e6
+        tens = num(tensor_key) if tensor_key else float('nan')
+        print('| %s | %s | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f | %d |' % (
+            name[:60], r[idx['Grid Size']], dur_us, tens, rd, wr, num('dram__throughput.avg.pct_of_peak_sustained_elapsed'),
+            num('lts__throughput.avg.pct_of_peak_sustained_elapsed'), num('sm__throughput.avg.pct_of_peak_sustained_elapsed'),
+            int(num('launch__registers_per_thread'))))
+        tot_us += dur_us; tot_rd += rd; tot_wr += wr; n += 1
+    print()
+    print('Totals over %d launches: %.1f us, DRAM read %.1f MB + write %.1f MB = %.1f MB (%.1f MB per launch).' % (n, tot_us, tot_rd, tot_wr, tot_rd + tot_wr, (tot_rd + tot_wr) / max(n, 1)))
+
+
+if __name__ == '__main__':
+    main(sys.argv[1])
