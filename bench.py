@@ -363,8 +363,8 @@ def run_b200(args):
     achieved = prof['conv_flops'] / (prof['conv_ms'] / 1e3) / 1e12
     graph_step_ms = ms / args.steps
     roofline = dict(bound='tensor', achieved=achieved, peak=peaks['tflops'], unit='TFLOP/s', frac=achieved / peaks['tflops'],
-                    traffic=38.7e6, traffic_source='profiles/r01_ncu_conv_full.md: (dram read 641.9 MB + write 208.8 MB) / 22 launches, B=32',
-                    kernel='conv_igemm_kernel (22 launches/step)', peak_source=peaks['source'],
+                    traffic=33.6e6, traffic_source='profiles/r01_ncu_infer_full_v2.md: (dram read 642.5 MB + write 96.8 MB) / 22 tcgen05 conv launches, B=32 (ncu --set full)',
+                    kernel='conv_igemm_kernel x21 + conv_c32_kernel x1 (the tcgen05 implicit-GEMM conv family, 22 launches/step)', peak_source=peaks['source'],
                     flops_per_launch=prof['conv_flops'] / prof['launches'], us_per_launch=prof['conv_ms'] * 1e3 / prof['launches'],
                     share_of_step=prof['conv_ms'] / prof['kernels_ms'],
                     whole_step_frac=(B * GFLOP_PER_IMAGE_416 / 1e3) / (graph_step_ms / 1e3) / peaks['tflops'])

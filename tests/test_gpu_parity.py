@@ -602,7 +602,7 @@ def test_training_step_vs_oracle():
     """C3-style step at a small size through the plugin surface: train-mode forward (batch-stat BN), region
     loss, full backward, gradients on every parameter.  End to end, batch-stat BN over 22 random layers amplifies
     ANY fp16 rounding chaotically (an fp32 oracle whose activations/weights are merely rounded to fp16 deviates by
-    2.4e-2 from itself, tools/train_diag.py + DESIGN.md), so this is a wiring / sanity check with loose bounds; the
+    2.4e-2 from itself, tests/diag_train.py + DESIGN.md), so this is a wiring / sanity check with loose bounds; the
     numerical parity of every kernel is asserted per unit in test_training_unit_forward_backward."""
     import model
     import model.yolo2

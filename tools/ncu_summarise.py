@@ -23,9 +23,11 @@ def main(path):
     start = next(i for i, r in enumerate(rows) if r and r[0] == 'ID')
     header, units = rows[start], rows[start + 1]
     idx = {name: i for i, name in enumerate(header)}
-    tensor_key = next((k for k in idx if 'pipe_tensor' in k and 'pct_of_peak_sustained_active' in k), None)
-    print('| kernel | grid | us | tensor pipe % (active) | DRAM rd MB | DRAM wr MB | dram % | L2 % | SM % | regs |')
-    print('|---|---|---|---|---|---|---|---|---|---|')
+    tensor_key = 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active'
+    tensor_el = 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed'
+    dram_key = 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'
+    print('| kernel | grid | us | tensor pipe % of peak while SM active | tensor pipe % of peak, whole launch | DRAM rd MB | DRAM wr MB | dram % | L2 % | SM % | regs |')
+    print('|---|---|---|---|---|---|---|---|---|---|---|')
     tot_us = tot_rd = tot_wr = 0.0
     n = 0
     for r in rows[start + 2:]:
@@ -39,9 +41,9 @@ def main(path):
         dur_us = dur / 1e3 if units[idx['gpu__time_duration.sum']] in ('ns', 'nsecond') else (dur if units[idx['gpu__time_duration.sum']] in ('us', 'usecond') else dur * 1e3)
         rd = to_bytes(r[idx['dram__bytes_read.sum']], units[idx['dram__bytes_read.sum']]) / 1e6
         wr = to_bytes(r[idx['dram__bytes_write.sum']], units[idx['dram__bytes_write.sum']]) / 1e6
-        tens = num(tensor_key) if tensor_key else float('nan')
-        print('| %s | %s | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f | %d |' % (
-            name[:60], r[idx['Grid Size']], dur_us, tens, rd, wr, num('dram__throughput.avg.pct_of_peak_sustained_elapsed'),
+        tens = num(tensor_key)
+        print('| %s | %s | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f | %d |' % (
+            name[:60], r[idx['Grid Size']], dur_us, tens, num(tensor_el), rd, wr, num(dram_key),
             num('lts__throughput.avg.pct_of_peak_sustained_elapsed'), num('sm__throughput.avg.pct_of_peak_sustained_elapsed'),
             int(num('launch__registers_per_thread'))))
         tot_us += dur_us; tot_rd += rd; tot_wr += wr; n += 1

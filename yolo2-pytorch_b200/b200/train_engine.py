@@ -13,6 +13,8 @@ Gradients travel in fp16 multiplied by `grad_scale` (static loss scaling; parame
 BatchNorm statistics are per process (per GPU), exactly like the per-replica statistics of the reference's
 nn.DataParallel.
 """
+import os
+
 import torch
 
 from . import ops
@@ -31,7 +33,8 @@ class DarknetTrainer(object):
         self.sums = {}       # per-unit double[2C] accumulators (self-cleaning)
         self.wd_cache = {}   # dgrad weight buffers per unit (contents re-packed every step)
         self.on_grad = None  # optional callback(name, grad) fired as soon as a parameter gradient is enqueued (DDP overlap)
-        self.fuse_stats = True   # BN batch statistics in the conv epilogue (yb_conv_bn_act_stats_fwd) instead of yb_bn_stats
+        # BN batch statistics in the conv epilogue (yb_conv_bn_act_stats_fwd) instead of yb_bn_stats; YB_FUSE_STATS=0 for A/B runs
+        self.fuse_stats = os.environ.get('YB_FUSE_STATS', '1') != '0'
         self._fused_stats = False
 
     # ---- helpers -------------------------------------------------------------------------------------
