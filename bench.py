@@ -486,7 +486,7 @@ def run_train(args):
                     roofline=dict(bound='tensor', achieved=value * gflop_train / 1e3, peak=peaks['tflops'], unit='TFLOP/s',
                                   frac=value * gflop_train / 1e3 / peaks['tflops'], traffic=None, kernel='whole training step',
                                   peak_source=peaks['source']),
-                    allreduce_bytes_per_step=(reducer.bytes_reduced // max(1, args.steps + args.warmup)) if reducer else 0)
+                    allreduce_bytes_per_step=(reducer.bytes_reduced // max(1, reducer.steps)) if reducer else 0)
         print(json.dumps(line), flush=True)
     if world > 1:
         if use_graph:

@@ -728,6 +728,38 @@ def test_conv_fused_batch_statistics(ops, case):
         assert ((ref - exact).abs() / scale).max().item() <= 1e-5
 
 
+@pytest.mark.parametrize('size', [320, 608])
+def test_training_step_multiscale_shapes(size):
+    """BASELINE configs[3] trains at {320, 416, 608}: one graphed step per size through the same GraphedStep object (one
+    CUDA graph per input shape, shared optimizer state); grids of 10x10 / 19x19 cells exercise the ragged-tile paths of
+    every training kernel.  Checks: finite loss of the usual size, every parameter moved, running statistics updated."""
+    import model
+    import model.yolo2
+    import train as yb_train
+    cfg = make_config(1)
+    cfg.read_dict({'model': {'threshold': '0.6'}, 'hparam': {k: str(v) for k, v in O.HPARAM_DEFAULT.items()}, 'train': {'cross_entropy': '1'}})
+    anchors = O.anchors_yolo_voc()
+    sd0 = O.make_state_dict(0)
+    dnn = model.yolo2.Darknet(model.ConfigChannels(cfg), anchors, 20)
+    dnn.load_state_dict(sd0, strict=False)
+    dnn = dnn.to(DEV).train()
+    inference = model.Inference(cfg, dnn, anchors).train()
+    opt = torch.optim.SGD(dnn.parameters(), 1e-3, momentum=0.9)
+    step = yb_train.GraphedStep(inference, opt, anchors, cfg)
+    losses = []
+    for i, s in enumerate((size, 416, size)):
+        t = O.synth_targets(2, s, s, slots=5, seed=40 + i)
+        out = step(dict(tensor=O.synth_images(2, s, s, seed=50 + i).to(DEV), yx_min=t['yx_min'].to(DEV), yx_max=t['yx_max'].to(DEV), cls=t['cls'].to(DEV)))
+        assert (out['rows'], out['cols']) == (s // 32, s // 32)
+        losses.append(float(out['loss_total'].item()))
+    assert len(step.graphs) == 2 and all(l == l and 0.0 < l < 10.0 for l in losses), losses
+    sd = dnn.state_dict()
+    for k, v in sd0.items():
+        if k.endswith('conv.weight') or k.endswith('running_mean'):
+            assert torch.isfinite(sd[k]).all() and not torch.equal(sd[k].float().cpu(), v.float()), k
+    assert int(sd['layers1.0.bn.num_batches_tracked']) == 3
+
+
 def test_training_repacks_operands_under_fused_optimizer(ops):
     """torch.optim.Adam(fused=True) updates parameters without advancing their version counters; the training path must
     still see the new weights (it re-packs every step), and switching to eval() must re-fold / re-pack too."""

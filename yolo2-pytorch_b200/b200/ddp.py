@@ -24,6 +24,7 @@ class GradientAllReducer(object):
         self._bucket = []
         self._bucket_size = 0
         self.bytes_reduced = 0
+        self.steps = 0          # finish() calls executed by Python (CUDA-graph replays do not come through here)
 
     # ---- called by the backward chain -----------------------------------------------------------------
     def on_grad(self, name, grad):
@@ -61,6 +62,7 @@ class GradientAllReducer(object):
         """Flush the last bucket, wait for every all-reduce and write the averaged gradients back in place."""
         if self.world == 1:
             return
+        self.steps += 1
         self._flush()
         scale = 1.0 / self.world
         for flat, items, work, cuda in self._pending:

@@ -9,6 +9,7 @@
 #include "yb_common.h"
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace yb {
 
@@ -328,7 +329,8 @@ static int grid_for(long long work_items, int items_per_thread = 1) {
 
 // keep cg = threadIdx % c8 constant along the grid stride: total stride must be a multiple of c8
 static int grid_for_groups(long long work_items, int c8) {
-  int g = grid_for(work_items, 16);    // every block pays ~50 parameter loads per thread and 2C global double atomics
+  static const int items = getenv("YB_BN_ITEMS") ? atoi(getenv("YB_BN_ITEMS")) : 16;   // tuning knob (tools): work items per thread
+  int g = grid_for(work_items, items > 0 ? items : 16);    // every block pays ~50 parameter loads per thread and 2C global double atomics
   (void)c8;  // blockDim (256) is a multiple of every supported c8 (4..128), so any grid size works
   return g;
 }
