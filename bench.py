@@ -476,11 +476,11 @@ def run_train(args):
     if rank == 0:
         value = world * B * args.steps / (ms / 1e3)
         peaks = measured_peaks()
-        gflop_train = 3 * GFLOP_PER_IMAGE_416 - GFLOP_LAYER0_416          # 87.78 GFLOP / image
-        line = dict(metric='416x416 training images/sec', value=value, unit='images/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
+        gflop_train = (3 * GFLOP_PER_IMAGE_416 - GFLOP_LAYER0_416) * (H * W) / (416.0 * 416.0)   # 87.78 GFLOP / image at 416x416
+        line = dict(metric='%dx%d training images/sec' % (H, W), value=value, unit='images/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f16', data='synthetic',
-                    config=dict(workload='Darknet-19 416x416 batch-%d training step: train-mode fwd + region loss + bwd%s + Adam (BASELINE configs[2])'
-                                % (B, ' + NCCL gradient all-reduce' if world > 1 else ''), global_batch=B * world, per_gpu_batch=B,
+                    config=dict(workload='Darknet-19 %dx%d batch-%d training step: train-mode fwd + region loss + bwd%s + Adam (BASELINE configs[2])'
+                                % (H, W, B, ' + NCCL gradient all-reduce' if world > 1 else ''), global_batch=B * world, per_gpu_batch=B,
                                 parallelism='dp%d' % world, l2='0.6+ GB of activations per step (> L2)', cuda_graph=bool(use_graph)),
                     clocks=clocks, gpu_launches=launches, loss_total=float(out['loss_total'].item()),
                     roofline=dict(bound='tensor', achieved=value * gflop_train / 1e3, peak=peaks['tflops'], unit='TFLOP/s',

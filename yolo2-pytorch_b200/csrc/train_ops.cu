@@ -206,7 +206,40 @@ __global__ void __launch_bounds__(kTrainThreads) bn_act_bwd_kernel(const __half*
   float acc1[8], acc2[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { acc1[i] = 0.f; acc2[i] = 0.f; }
-#pragma unroll(kWin ? 1 : 2)
+  if constexpr (!kWin) {
+    // ---- plain units (no pooling window; the gradient is `da`): four pixels per trip, all eight 16-byte loads issued
+    // before any arithmetic -- the kernel is latency-bound, not issue-bound, so memory-level parallelism is what counts
+    constexpr int U = 4;
+    for (unsigned p0 = blockIdx.x * (blockDim.x / c8) + threadIdx.x / c8; p0 < npix; p0 += U * pstride) {
+      uint4 zr[U], dr[U];
+      bool ok[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const unsigned q = p0 + u * pstride;
+        ok[u] = q < npix;
+        const long long pix = ok[u] ? q : p0;
+        zr[u] = __ldg(reinterpret_cast<const uint4*>(z + pix * ld_z + cg * 8));
+        dr[u] = __ldg(reinterpret_cast<const uint4*>(g.da + pix * g.ld_da + g.da_off + cg * 8));
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (!ok[u]) continue;
+        float zf[8], gd[8], out[8];
+        h8_to_f(zr[u], zf);
+        h8_to_f(dr[u], gd);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float y = fmaf(zf[i], k.sc[i], k.sh[i]);
+          const float dy = y > 0.f ? gd[i] : gd[i] * bn.slope;
+          const float xhat = fmaf(zf[i], xa[i], xb[i]);
+          if (kMode == 0) { acc1[i] += dy; acc2[i] = fmaf(dy, xhat, acc2[i]); }
+          else out[i] = fmaf(k.sc[i], dy, -fmaf(k2[i], xhat, k1[i]));
+        }
+        if (kMode == 1) *reinterpret_cast<uint4*>(dz + static_cast<long long>(p0 + u * pstride) * ld_dz + cg * 8) = f_to_h8(out);
+      }
+    }
+  } else
+#pragma unroll 1
   for (unsigned p = blockIdx.x * (blockDim.x / c8) + threadIdx.x / c8; p < npix; p += pstride) {
     long long in0;
     if (kWin) {
