@@ -46,11 +46,21 @@ __global__ void __launch_bounds__(kTrainThreads) bn_stats_kernel(const __half* _
 #pragma unroll
   for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
   if (rib < rpi) {
-    for (long long r = static_cast<long long>(blockIdx.x) * rpi + rib; r < rows; r += static_cast<long long>(gridDim.x) * rpi) {
-      float f[8];
-      h8_to_f(__ldg(reinterpret_cast<const uint4*>(z + r * ld + cg * 8)), f);
+    const long long rstride = static_cast<long long>(gridDim.x) * rpi;
+    for (long long r0 = static_cast<long long>(blockIdx.x) * rpi + rib; r0 < rows; r0 += 4 * rstride) {
+      uint4 raw[4];                                    // four rows per trip, loads first (latency-bound otherwise)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] += f[i] * f[i]; }
+      for (int u = 0; u < 4; ++u) {
+        const long long r = r0 + u * rstride;
+        raw[u] = r < rows ? __ldg(reinterpret_cast<const uint4*>(z + r * ld + cg * 8)) : make_uint4(0u, 0u, 0u, 0u);   // fp16 zeros add nothing
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float f[8];
+        h8_to_f(raw[u], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] += f[i] * f[i]; }
+      }
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -125,6 +135,32 @@ __global__ void __launch_bounds__(kTrainThreads) bn_act_apply_kernel(const __hal
   const unsigned npix = static_cast<unsigned>(batch) * oh * ow;                 // output pixels (< 2^31, checked on the host)
   const unsigned pstride = gridDim.x * (blockDim.x / c8);
   constexpr int nwin = kPool ? 4 : 1;
+  if constexpr (!kPool) {
+    // four pixels per trip, loads first: these kernels are latency-bound (see bn_act_bwd_kernel)
+    constexpr int U = 4;
+    for (unsigned p0 = blockIdx.x * (blockDim.x / c8) + threadIdx.x / c8; p0 < npix; p0 += U * pstride) {
+      uint4 raw[U];
+      bool ok[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const unsigned q = p0 + u * pstride;
+        ok[u] = q < npix;
+        raw[u] = __ldg(reinterpret_cast<const uint4*>(z + static_cast<long long>(ok[u] ? q : p0) * ld_z + cg * 8));
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (!ok[u]) continue;
+        float f[8], y[8];
+        h8_to_f(raw[u], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float v = fmaf(f[i], k.sc[i], k.sh[i]);
+          y[i] = v > 0.f ? v : v * bn.slope;
+        }
+        *reinterpret_cast<uint4*>(a + static_cast<long long>(p0 + u * pstride) * ld_a + a_ch_off + cg * 8) = f_to_h8(y);
+      }
+    }
+  } else
 #pragma unroll 2
   for (unsigned p = blockIdx.x * (blockDim.x / c8) + threadIdx.x / c8; p < npix; p += pstride) {
     long long in0;
