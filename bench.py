@@ -368,6 +368,22 @@ def run_b200(args):
                     flops_per_launch=prof['conv_flops'] / prof['launches'], us_per_launch=prof['conv_ms'] * 1e3 / prof['launches'],
                     share_of_step=prof['conv_ms'] / prof['kernels_ms'],
                     whole_step_frac=(B * GFLOP_PER_IMAGE_416 / 1e3) / (graph_step_ms / 1e3) / peaks['tflops'])
+    # HBM-bound kernels of the step: algorithmic bytes (SURVEY 8d, fp16 activations inside the backbone) / CUDA-event time
+    S = H // 32
+    boxes = B * S * S * len(ANCHORS_HW)
+    alg_bytes = {
+        'conv0_bn_leaky_pool': B * 3 * H * W * 4 + B * (H // 2) * (W // 2) * 32 * 2,
+        'maxpool2x2': int(1.25 * 2 * B * ((H // 4) ** 2 * 128 + (H // 8) ** 2 * 256 + (H // 16) ** 2 * 512)),
+        'reorg_f16': 2 * B * (H // 16) ** 2 * 64 * 2,
+        'decode': B * 125 * S * S * 4 + boxes * (1 + 8 + 20 + 20) * 4,
+        'filter_nms': boxes * (1 + 4 + 20) * 4,
+    }
+    hbm_kernels = {}
+    for name, nbytes in alg_bytes.items():
+        rec = prof['others'].get(name)
+        if rec and rec['us_per_step'] > 0:
+            gbs = nbytes / (rec['us_per_step'] * 1e-6) / 1e9
+            hbm_kernels[name] = dict(us=rec['us_per_step'], alg_bytes=nbytes, achieved_gbs=gbs, frac_of_hbm_peak=gbs / peaks['hbm'])
     os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
     with open(os.path.join(ROOT, 'gpurun_out', 'bench_layers.json'), 'w') as f:
         json.dump(dict(prof, graph_step_ms=graph_step_ms, value=value), f, indent=1)
@@ -386,7 +402,7 @@ def run_b200(args):
                 clocks=clocks, e2e=dict(value=e2e_value, unit='images/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=ms_e2e / args.steps,
                          input='fp32 NCHW tensors (the reference forward() signature)'),
                 e2e_u8=e2e_u8,
-                gpu_launches=graph_launches, roofline=roofline, cpu_baseline=cpu, wall_ms=wall_ms)
+                gpu_launches=graph_launches, roofline=roofline, hbm_kernels=hbm_kernels, cpu_baseline=cpu, wall_ms=wall_ms)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

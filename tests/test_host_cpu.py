@@ -229,3 +229,26 @@ def test_eval_ap_host_functions_match_reference_golden():
     with pytest.raises(RuntimeError):
         yb_eval.matching_batch(torch.zeros(1, 2), torch.ones(1, 2), torch.zeros(1), torch.tensor([0, 1]), torch.zeros(1, 2), torch.ones(1, 2),
                                torch.zeros(1), torch.tensor([0, 1]), 1, 0.5)
+
+
+def test_convert_darknet_torch_cli_round_trip(tmp_path):
+    """The converter CLI (reference convert_darknet_torch.py:83-125): .weights -> .pth -> .weights is the identity for
+    the network the config describes (model.yolo2.Darknet, yolo-voc anchors, 20 classes)."""
+    import subprocess
+    import sys
+    from oracle import yolo2_oracle as O
+    from utils import darknet_weights as dw
+    sd = O.make_state_dict(3)
+    w0 = str(tmp_path / 'a.weights')
+    dw.save_darknet_weights(w0, sd, 5, header=dict(major=0, minor=2, revision=0, seen=777))
+    cli = os.path.join(PKG, 'convert_darknet_torch.py')
+    env = dict(os.environ, PYTHONPATH=PKG)
+    cfg = ['-c', 'config.ini', 'config/darknet/yolo-voc.ini']
+    pth = str(tmp_path / 'a.pth')
+    subprocess.run([sys.executable, cli, w0, pth] + cfg, check=True, env=env)
+    got = torch.load(pth, map_location='cpu')
+    for k, v in sd.items():
+        assert torch.equal(got[k], v), k
+    w1 = str(tmp_path / 'b.weights')
+    subprocess.run([sys.executable, cli, pth, w1, '--reverse'] + cfg, check=True, env=env)
+    assert open(w1, 'rb').read()[16:] == open(w0, 'rb').read()[16:]
