@@ -206,6 +206,10 @@ int yb_unpack_wgrad(const float* dw_krsc, float* dw_oihw, int cout, int cin, int
 int yb_resize_batch_u8(const void* src, const long long* src_off, const int* src_hw, void* dst, int batch, int height, int width, int swap_rb,
                        float* yx_min, float* yx_max, int slots, yb_stream_t stream);
 
+/* torchvision ToTensor for a batch (the `transform_tensor` step, utils/data.py:120-121): uint8 NHWC [B,H,W,3] -> fp32 NCHW [B,3,H,W],
+ * value / 255.  Only the training path needs the fp32 image (inference reads the uint8 frames in the first conv kernel). */
+int yb_totensor_u8(const void* src_nhwc_u8, float* dst_nchw_f32, int batch, int height, int width, yb_stream_t stream);
+
 /* ---- evaluation matching (eval.py:57-75 `_matching`/`matching`, called per image and class at eval.py:210-216) ----
  * Segmented batch: image i owns detections [det_off[i], det_off[i+1]) (descending score within the image, as postprocess returns
  * them) and ground-truth boxes [gt_off[i], gt_off[i+1]); boxes are (y, x) float pairs, classes int32.  tp[d] = 1 iff detection d's

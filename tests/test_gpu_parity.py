@@ -945,3 +945,43 @@ def test_resize_batch_bit_exact_vs_cv2_golden(golden_dir):
     f_u8 = dnn(u8)
     f_f32 = dnn((u8.float() / 255.0).permute(0, 3, 1, 2).contiguous())
     assert rel_err(f_u8, f_f32) <= 2e-3
+
+
+def test_collate_gpu_batch_and_training_step_from_uint8_frames():
+    """utils.data.Collate: a list of decoded BGR frames of different sizes + ragged labels -> one GPU batch at the scheduled
+    size (frames bit-identical to cv2.resize + BGR2RGB, boxes scaled like transform.resize.label.rescale, labels zero-padded
+    like padding_labels), ToTensor on the device bit-identical to torchvision's `.float().div(255)`, and the batch drives a
+    training step as is."""
+    import model
+    import model.yolo2
+    import train as yb_train
+    import transform
+    import utils.data as ud
+    samples = []
+    for i, (h, w, n) in enumerate(((90, 120, 2), (75, 100, 0), (64, 64, 3))):
+        g = np.random.RandomState(60 + i)
+        lo = (g.rand(n, 2) * [h * 0.5, w * 0.5]).astype(np.float32)
+        samples.append(dict(image=O.synth_frame(30 + i, h, w), yx_min=lo, yx_max=lo + (g.rand(n, 2) * [h * 0.4, w * 0.4] + 4).astype(np.float32),
+                            cls=g.randint(0, 20, n)))
+    collate = ud.Collate([(64, 64)], maintain=3, seed=1)
+    batch = collate(samples)
+    assert batch['tensor'].shape == (3, 64, 64, 3) and batch['tensor'].dtype == torch.uint8 and batch['yx_min'].shape == (3, 3, 2)
+    for i, smp in enumerate(samples):
+        ref_img, a, b = O.rescale_label(smp['image'], smp['yx_min'].copy(), smp['yx_max'].copy(), 64, 64)
+        assert np.array_equal(batch['tensor'][i].cpu().numpy(), ref_img[..., ::-1])
+        n = len(smp['cls'])
+        assert np.array_equal(batch['yx_min'][i, :n].cpu().numpy(), a) and np.array_equal(batch['yx_max'][i, :n].cpu().numpy(), b)
+        assert float(batch['yx_max'][i, n:].abs().sum()) == 0.0 and batch['cls'][i, :n].tolist() == smp['cls'].tolist()
+    x = transform.to_tensor(batch['tensor'])
+    assert torch.equal(x, batch['tensor'].permute(0, 3, 1, 2).float().div(255))
+    cfg = make_config(1)
+    cfg.read_dict({'model': {'threshold': '0.6'}, 'hparam': {k: str(v) for k, v in O.HPARAM_DEFAULT.items()}, 'train': {'cross_entropy': '1'}})
+    anchors = O.anchors_yolo_voc()
+    dnn = model.yolo2.Darknet(model.ConfigChannels(cfg), anchors, 20)
+    dnn.load_state_dict(O.make_state_dict(0), strict=False)
+    dnn = dnn.to(DEV).train()
+    inference = model.Inference(cfg, dnn, anchors).train()
+    opt = torch.optim.SGD(dnn.parameters(), 1e-4)
+    out = yb_train.iterate(inference, opt, anchors, cfg, batch)
+    lt = float(out['loss_total'].item())
+    assert lt == lt and 0.0 < lt < 10.0 and (out['height'], out['width']) == (64, 64)

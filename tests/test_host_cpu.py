@@ -252,3 +252,32 @@ def test_convert_darknet_torch_cli_round_trip(tmp_path):
     w1 = str(tmp_path / 'b.weights')
     subprocess.run([sys.executable, cli, pth, w1, '--reverse'] + cfg, check=True, env=env)
     assert open(w1, 'rb').read()[16:] == open(w0, 'rb').read()[16:]
+
+
+def test_padding_labels_and_size_schedule():
+    """utils.data: padding_labels (reference utils/data.py:28-41), load_sizes (utils/train.py:129-131) and the multi-scale
+    schedule (Collate.next_size, utils/data.py:135-141): a size is kept for `maintain` further batches; the same seed
+    gives every rank the same sequence."""
+    import utils.data as ud
+    d = ud.padding_labels(dict(yx_min=np.ones((2, 2), np.float32), yx_max=np.ones((2, 2), np.float32), cls=np.array([3, 4]), difficult=np.array([0, 1])), 5)
+    assert d['yx_min'].shape == (5, 2) and d['cls'].tolist() == [3, 4, 0, 0, 0] and d['difficult'].tolist() == [0, 1, 0, 0, 0]
+    assert float(d['yx_max'][2:].sum()) == 0.0
+    config = load_config()
+    sizes = ud.load_sizes(config)
+    assert (320, 320) in sizes and (416, 416) in sizes and (608, 608) in sizes and all(h % 32 == 0 and w % 32 == 0 for h, w in sizes)
+    a, b = ud.SizeSchedule(sizes, maintain=10, seed=5), ud.SizeSchedule(sizes, maintain=10, seed=5)
+    seq = [a.next_size() for _ in range(45)]
+    assert seq == [b.next_size() for _ in range(45)]                      # ranks stay in step
+    runs = [seq[i:i + 11] for i in range(0, 44, 11)]
+    assert all(len(set(r)) == 1 for r in runs) and len(set(seq)) > 1     # held for maintain + 1 batches, then redrawn
+    # reference semantics, restated: _maintain counts from 0 after a draw
+    import random
+    rng, ref, m, cur = random.Random(5), [], 10, None
+    cnt = m
+    for _ in range(45):
+        if cnt < m:
+            cnt += 1
+        else:
+            cur, cnt = rng.choice(sizes), 0
+        ref.append(cur)
+    assert seq == ref

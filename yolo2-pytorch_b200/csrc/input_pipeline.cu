@@ -82,6 +82,27 @@ __global__ void rescale_boxes_kernel(float* __restrict__ yx_min, float* __restri
   yx_max[2 * i] = __fmul_rn(yx_max[2 * i], sy); yx_max[2 * i + 1] = __fmul_rn(yx_max[2 * i + 1], sx);
 }
 
+// torchvision.transforms.ToTensor on a batch (transform/image.py + the `transform_tensor` step of utils/data.py:120-121):
+// uint8 NHWC [B,H,W,3] -> fp32 NCHW [B,3,H,W], value / 255 (IEEE division, as `.div(255)` does).  The inference path never
+// needs this (the first conv kernel reads the uint8 frames directly); the training forward and its first-layer weight
+// gradient read the fp32 NCHW image the reference hands them.
+__global__ void totensor_u8_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, int batch, int hw) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;     // one thread per pixel
+  if (idx >= static_cast<long long>(batch) * hw) return;
+  const long long img = idx / hw, pix = idx - img * hw;
+  const uint8_t* s = src + idx * 3;
+  float* d = dst + img * 3 * hw + pix;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) d[static_cast<long long>(c) * hw] = __fdiv_rn(static_cast<float>(s[c]), 255.f);
+}
+
+int totensor_u8(const void* src, float* dst, int batch, int height, int width, cudaStream_t stream) {
+  YB_REQUIRE(src && dst && batch > 0 && height > 0 && width > 0, "totensor_u8: bad argument");
+  const long long total = static_cast<long long>(batch) * height * width;
+  totensor_u8_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(static_cast<const uint8_t*>(src), dst, batch, height * width);
+  return check_launch("totensor_u8_kernel");
+}
+
 int resize_batch_u8(const void* src, const long long* src_off, const int* src_hw, void* dst, int batch, int height, int width, int swap_rb,
                     float* yx_min, float* yx_max, int slots, cudaStream_t stream) {
   YB_REQUIRE(src && src_off && src_hw && dst && batch > 0 && height > 0 && width > 0, "resize_batch_u8: bad argument");

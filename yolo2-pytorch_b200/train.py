@@ -48,6 +48,9 @@ def iterate(inference, optimizer, anchors, config, data, reducer=None):
     dev = torch.device('cuda', torch.cuda.current_device())
     data = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in data.items()}
     tensor = data['tensor']
+    if tensor.dtype == torch.uint8:                 # uint8 NHWC frames from utils.data.Collate: ToTensor on the device
+        import transform
+        tensor = transform.to_tensor(tensor)
     height, width = tensor.shape[-2:]
     dnn = inference.dnn
     if reducer is None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
