@@ -973,7 +973,8 @@ def test_collate_gpu_batch_and_training_step_from_uint8_frames():
         assert np.array_equal(batch['yx_min'][i, :n].cpu().numpy(), a) and np.array_equal(batch['yx_max'][i, :n].cpu().numpy(), b)
         assert float(batch['yx_max'][i, n:].abs().sum()) == 0.0 and batch['cls'][i, :n].tolist() == smp['cls'].tolist()
     x = transform.to_tensor(batch['tensor'])
-    assert torch.equal(x, batch['tensor'].permute(0, 3, 1, 2).float().div(255))
+    # the reference's ToTensor runs on the CPU (a true IEEE division; torch's CUDA `div` by a scalar multiplies by the reciprocal)
+    assert torch.equal(x.cpu(), batch['tensor'].cpu().permute(0, 3, 1, 2).float().div(255))
     cfg = make_config(1)
     cfg.read_dict({'model': {'threshold': '0.6'}, 'hparam': {k: str(v) for k, v in O.HPARAM_DEFAULT.items()}, 'train': {'cross_entropy': '1'}})
     anchors = O.anchors_yolo_voc()
