@@ -87,6 +87,13 @@ def test_iou_known_answers(golden_dir):
     assert np.array_equal(m1, g['m1'])
     mb = iou.batch_iou_matrix(t('r_min'), t('r_max'), t('s_min'), t('s_max')).cpu().numpy()
     assert np.array_equal(mb, g['mb'])                                                                    # bit-exact vs the reference
+    # batch_iou_pair known answers (utils/iou/torch.py:236-289): box1 tiled over cells, box2 tiled over the batch
+    for bbox1, bbox2, ans in (([(1, 1, 2, 2)], [(0, 0, 1, 1), (0, 1, 1, 2), (0, 2, 1, 3), (1, 0, 2, 1), (2, 0, 3, 1), (1, 2, 2, 3), (2, 1, 3, 2), (2, 2, 3, 3)], [[0] * 8]),
+                              ([(1, 1, 3, 3), (0, 0, 4, 4)], [(0, 0, 2, 2), (2, 0, 4, 2), (0, 2, 2, 4), (2, 2, 4, 4)], [[1 / 7] * 4, [4 / 16] * 4])):
+        b1 = np.tile(np.reshape(np.array(bbox1, np.float32), [-1, 1, 4]), [1, len(bbox2), 1])
+        b2 = np.tile(np.reshape(np.array(bbox2, np.float32), [1, -1, 4]), [len(bbox1), 1, 1])
+        pair = iou.batch_iou_pair(*(torch.from_numpy(np.ascontiguousarray(a)).to(DEV) for a in (b1[..., :2], b1[..., 2:], b2[..., :2], b2[..., 2:])))
+        np.testing.assert_almost_equal(pair.cpu().numpy(), np.array(ans, np.float32))
 
 
 @pytest.mark.parametrize('tag', list('abcdef'))
