@@ -281,3 +281,20 @@ def test_padding_labels_and_size_schedule():
             cur, cnt = rng.choice(sizes), 0
         ref.append(cur)
     assert seq == ref
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/yolo2_b200.h is a C header (no torch / C++ types in any signature): it compiles with a C99 compiler in
+    pedantic mode and as C++."""
+    import shutil
+    import subprocess
+    gcc = shutil.which('gcc')
+    if gcc is None:
+        pytest.skip('no gcc')
+    src = tmp_path / 'hdr.c'
+    src.write_text('#include "yolo2_b200.h"\nint main(void) { return yb_version() < 0; }\n')
+    inc = os.path.join(ROOT, 'include')
+    subprocess.run([gcc, '-std=c99', '-Wall', '-Wextra', '-pedantic', '-Werror', '-fsyntax-only', '-I', inc, str(src)], check=True)
+    gxx = shutil.which('g++')
+    if gxx is not None:
+        subprocess.run([gxx, '-std=c++11', '-fsyntax-only', '-x', 'c++', '-I', inc, str(src)], check=True)
