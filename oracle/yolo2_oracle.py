@@ -12,11 +12,18 @@ Parity status
   produced by executing the *reference's own code* (`/root/reference`, imported with the one-line
   `async` rename that Python >= 3.7 needs) by `tests/golden/make_golden.py`, plus the reference's
   embedded IoU known-answer tests (`utils/iou/torch.py:79-113,179-213`).
-* region loss (`loss`, `iou_match`, `fit_positive`, `fill_norm`): PARITY UNPINNED BY EXECUTION.
-  The reference's `model.loss` does not run on torch >= 0.4 (IndexError at
+* region loss (`loss`, `iou_match`, `fit_positive`, `fill_norm`): PINNED BY EXECUTION UNDER TWO SHIMS.
+  The reference's `model.loss` does not run on torch >= 0.4 as is (IndexError at
   `model/__init__.py:154`, and `fit_positive` silently mis-masks because `torch.prod` of a
-  comparison is no longer a mask), so it is restated here with torch-0.3.1 semantics written out
-  explicitly; each deviation is commented.  Its building blocks (`batch_iou_matrix`) are pinned.
+  comparison is no longer a mask).  `tests/golden/make_golden_loss.py` executes the reference's
+  unmodified loss source with the two torch-0.3.1 behaviours supplied from outside (masks stay masks
+  under `prod`; `x[mask]` broadcasts the mask) and stores losses, masks, matched IoU and the gradient
+  w.r.t. the head feature map for four cases (13x13, 19x19, one ground-truth slot, the one-hot branch);
+  `tests/test_oracle_golden.py::test_region_loss_oracle_matches_executed_reference` checks the
+  restatement below against them (terms 1e-5, masks exact, gradient 1e-4).  The restatement writes the
+  same 0.3.1 semantics out explicitly; each deviation is commented.
+* Tiny backbone, evaluation matching / VOC AP, Darknet head permutation, cv2-exact resize: PINNED by
+  fixtures made with the reference's functions (and cv2) -- see the generators under `tests/golden/`.
 
 The conv / BN / pooling / softmax / sort arithmetic of the reference lives in its third-party
 dependency torch (`requirements.txt:5`, `torch<=0.3.1`, not vendored); the restatement calls the

@@ -448,7 +448,7 @@ def test_inference_and_postprocess_batch(darknet):
 
 @pytest.mark.parametrize('case', [(4, 13, 16, 0), (7, 19, 6, 1), (2, 10, 1, 2)])
 def test_region_loss_values_masks_and_gradient(case):
-    """K8/K9 vs the oracle's restated model.loss (PARITY UNPINNED BY EXECUTION, see oracle header):
+    """K8/K9 vs the oracle's restated model.loss (itself pinned against the executed reference, see oracle header):
     the five scalars, positive/negative masks, matched IoU and d(total)/dfeature via autograd."""
     import model
     b, s, g, seed = case

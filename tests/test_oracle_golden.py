@@ -114,7 +114,7 @@ def test_iou_known_answers(golden_dir):
 
 
 def test_loss_restatement_self_consistency():
-    """The loss is parity-unpinned by execution (see oracle header); check its closed-form gradient
+    """Self-consistency of the restated loss (it is also pinned against the executed reference below); check its closed-form gradient
     (SURVEY 8a derived spec) against autograd and basic invariants."""
     torch.manual_seed(0)
     anchors = O.anchors_yolo_voc()
@@ -220,3 +220,27 @@ def test_resize_oracle_matches_cv2_golden(golden_dir):
             assert hashlib.sha256(r[..., ::-1].tobytes()).digest() == g['jpg_sha_rgb'].tobytes()
             assert np.array_equal(a, g['jpg_yx_min']) and np.array_equal(b, g['jpg_yx_max'])
             assert np.array_equal(r[100:132, 200:232], g['jpg_crop'])
+
+
+@pytest.mark.parametrize('tag', list('abcd'))
+def test_region_loss_oracle_matches_executed_reference(golden_dir, tag):
+    """oracle.loss (the restatement the CUDA kernels are checked against) vs the reference's OWN model.loss executed on CPU
+    under the two documented torch-0.3.1 shims (tests/golden/make_golden_loss.py): the five terms, the positive / negative
+    masks, the matched IoU and the gradient w.r.t. the head feature map; case d is the one-hot (train/cross_entropy = 0)
+    branch, b a 19x19 grid, c a single ground-truth slot."""
+    g = load(golden_dir, 'loss.npz')
+    b, s, slots, seed, one_hot = (int(v) for v in g[tag + '_dims'])
+    anchors = O.anchors_yolo_voc()
+    feature = torch.from_numpy(g[tag + '_feature']).clone().requires_grad_(True)
+    pred = O.decode(feature, anchors)
+    pred['feature'] = feature
+    data = O.norm_data(O.synth_targets(b, s * 32, s * 32, slots=slots, seed=20 + seed), s * 32, s * 32, s, s)
+    losses, debug = O.loss(anchors, data, pred, 0.6, cross_entropy=not one_hot)
+    for k, v in losses.items():
+        ref = float(g[tag + '_loss_' + k])
+        assert abs(v.item() - ref) <= 1e-5 * abs(ref) + 1e-9, (k, v.item(), ref)
+    assert np.array_equal(debug['positive'].numpy().astype(np.uint8), g[tag + '_positive'])
+    assert np.array_equal(debug['negative'].numpy().astype(np.uint8), g[tag + '_negative'])
+    np.testing.assert_allclose(debug['iou'].numpy(), g[tag + '_iou'], rtol=1e-6, atol=1e-7)
+    grad, = torch.autograd.grad(O.loss_total(losses), feature)
+    np.testing.assert_allclose(grad.numpy(), g[tag + '_grad'], rtol=1e-4, atol=1e-8)
