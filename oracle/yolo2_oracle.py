@@ -22,6 +22,8 @@ Parity status
   `tests/test_oracle_golden.py::test_region_loss_oracle_matches_executed_reference` checks the
   restatement below against them (terms 1e-5, masks exact, gradient 1e-4).  The restatement writes the
   same 0.3.1 semantics out explicitly; each deviation is commented.
+* one whole training step (train-mode backbone + loss + autograd + running statistics): PINNED against the step executed
+  with the reference's own modules (`tests/golden/make_golden_train.py`).
 * Tiny backbone, evaluation matching / VOC AP, Darknet head permutation, cv2-exact resize: PINNED by
   fixtures made with the reference's functions (and cv2) -- see the generators under `tests/golden/`.
 

@@ -244,3 +244,45 @@ def test_region_loss_oracle_matches_executed_reference(golden_dir, tag):
     np.testing.assert_allclose(debug['iou'].numpy(), g[tag + '_iou'], rtol=1e-6, atol=1e-7)
     grad, = torch.autograd.grad(O.loss_total(losses), feature)
     np.testing.assert_allclose(grad.numpy(), g[tag + '_grad'], rtol=1e-4, atol=1e-8)
+
+
+def test_training_step_oracle_matches_executed_reference(golden_dir):
+    """One whole training step of the oracle (train-mode Darknet with batch-statistics BatchNorm, decode, region loss,
+    hparam-weighted sum, autograd) against the same step executed with the reference's own modules
+    (tests/golden/make_golden_train.py): head feature, loss terms, every parameter gradient (norm + first elements,
+    small tensors in full) and the BatchNorm running statistics after the step (momentum 0.01, unbiased variance)."""
+    g = load(golden_dir, 'train_step.npz')
+    sd0 = O.make_state_dict(seed=0)
+    anchors = O.anchors_yolo_voc()
+    b, size = 4, 128
+    s = size // 32
+    x = O.synth_images(b, size, size, seed=12)
+    data = O.norm_data(O.synth_targets(b, size, size, slots=6, seed=13), size, size, s, s)
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'running' not in k else v.clone()) for k, v in sd0.items()}
+    stats, collect = {}, {}
+    feature = O.darknet_forward(sd, x, train=True, stats=stats, collect=collect)
+    pred = O.decode(feature, anchors)
+    pred['feature'] = feature
+    losses, _ = O.loss(anchors, data, pred, 0.6)
+    O.loss_total(losses).backward()
+    np.testing.assert_allclose(feature.detach().numpy(), g['feature'], rtol=2e-3, atol=2e-4)
+    for k, v in losses.items():
+        assert abs(v.item() - float(g['loss_' + k])) <= 1e-3 * abs(float(g['loss_' + k])), k
+    for name, p in sd.items():
+        if not p.requires_grad:
+            continue
+        gr = p.grad
+        ref_norm = float(g['gnorm_' + name])
+        assert abs(gr.double().norm().item() - ref_norm) <= 5e-3 * ref_norm + 1e-12, name
+        head = g['ghead_' + name]
+        np.testing.assert_allclose(gr.flatten()[:16].numpy(), head, rtol=2e-2, atol=2e-3 * float(np.abs(head).max()) + 1e-9, err_msg=name)
+        if 'gfull_' + name in g.files:
+            full = g['gfull_' + name]
+            assert np.linalg.norm(gr.numpy() - full) <= 1e-2 * np.linalg.norm(full) + 1e-9, name
+    # running statistics after one step: 0.99 * old + 0.01 * batch statistic (unbiased variance), model/yolo2.py:58
+    for key, (mean, var) in stats.items():
+        n = collect[key].numel() // collect[key].shape[1]
+        exp_mean = 0.99 * sd0[key + '.bn.running_mean'] + 0.01 * mean.detach()
+        exp_var = 0.99 * sd0[key + '.bn.running_var'] + 0.01 * var.detach() * n / (n - 1)
+        np.testing.assert_allclose(exp_mean.numpy(), g['buf_' + key + '.bn.running_mean'], rtol=1e-3, atol=1e-5, err_msg=key)
+        np.testing.assert_allclose(exp_var.numpy(), g['buf_' + key + '.bn.running_var'], rtol=1e-3, atol=1e-6, err_msg=key)
