@@ -286,3 +286,31 @@ def test_training_step_oracle_matches_executed_reference(golden_dir):
         exp_var = 0.99 * sd0[key + '.bn.running_var'] + 0.01 * var.detach() * n / (n - 1)
         np.testing.assert_allclose(exp_mean.numpy(), g['buf_' + key + '.bn.running_mean'], rtol=1e-3, atol=1e-5, err_msg=key)
         np.testing.assert_allclose(exp_var.numpy(), g['buf_' + key + '.bn.running_var'], rtol=1e-3, atol=1e-6, err_msg=key)
+
+
+def test_c1_single_image_chain_oracle_matches_executed_reference(golden_dir):
+    """BASELINE configs[0]: the reference's detect.py chain on its own image.jpg (resize, BGR2RGB, ToTensor, Darknet-19,
+    decode, softmax, postprocess with detect/fix = 1), executed by tests/golden/make_golden_c1.py, against the oracle on the
+    stored 416x416 RGB network input: feature map, and the detection tuple with exact class / box-index agreement."""
+    g = load(golden_dir, 'c1_image.npz')
+    sd = O.make_state_dict(seed=0)
+    anchors = O.anchors_yolo_voc()
+    x = torch.from_numpy(g['rgb'].transpose(2, 0, 1).copy()).float().div(255).unsqueeze(0)
+    with torch.no_grad():
+        feature = O.darknet_forward(sd, x)
+        pred = O.decode(feature, anchors)
+        prob = O.class_prob(pred)
+        res = O.postprocess(pred['iou'][0].reshape(-1), pred['yx_min'][0].reshape(-1, 2), pred['yx_max'][0].reshape(-1, 2),
+                            prob[0].reshape(-1, prob.size(-1)), True, 0.3, 0.005, 0.45)
+    np.testing.assert_allclose(feature.numpy(), g['feature'], rtol=1e-4, atol=1e-5)
+    assert (res is None) == bool(g['none'])
+    if res is not None:
+        assert res[3].tolist() == g['det_cls'].tolist()
+        np.testing.assert_allclose(res[0].numpy(), g['det_iou'], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(res[1].numpy(), g['det_yx_min'], rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(res[4].numpy(), g['det_score'], rtol=1e-5, atol=1e-8)
+    # the stored network input is what the oracle's cv2-exact resize produces from the reference's sample image, if present
+    jpg = '/root/reference/image.jpg'
+    if os.path.exists(jpg):
+        import cv2
+        assert np.array_equal(O.resize_u8(cv2.imread(jpg), 416, 416)[..., ::-1], g['rgb'])
