@@ -993,3 +993,21 @@ def test_collate_gpu_batch_and_training_step_from_uint8_frames():
     out = yb_train.iterate(inference, opt, anchors, cfg, batch)
     lt = float(out['loss_total'].item())
     assert lt == lt and 0.0 < lt < 10.0 and (out['height'], out['width']) == (64, 64)
+
+
+def test_c1_single_image_feature_vs_executed_reference(golden_dir):
+    """BASELINE configs[0] on the GPU: the 416x416 RGB uint8 network input the reference's transform produced from its own
+    image.jpg goes into the model as is (ToTensor fused into the first conv kernel); head feature vs the reference's
+    detect.py chain executed on CPU (tests/golden/make_golden_c1.py), same bound as the synthetic 416x416 golden."""
+    import model
+    import model.yolo2
+    g = np.load(os.path.join(golden_dir, 'c1_image.npz'))
+    cfg = make_config(1)
+    anchors = O.anchors_yolo_voc()
+    dnn = model.yolo2.Darknet(model.ConfigChannels(cfg), anchors, 20)
+    dnn.load_state_dict(O.make_state_dict(0), strict=False)
+    dnn = dnn.to(DEV).eval()
+    f = dnn(torch.from_numpy(g['rgb'])[None].contiguous().to(DEV))
+    e = rel_err(f, torch.from_numpy(g['feature']))
+    print('C1 image.jpg feature rel err %.3e' % e)
+    assert f.shape == g['feature'].shape and e <= 3e-3
