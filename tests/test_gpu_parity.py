@@ -29,6 +29,26 @@ def rel_l2(got, ref):
     return ((got - ref).norm() / ref.norm().clamp_min(1e-30)).item()
 
 
+MEASURED = {}
+
+
+def record(name, value):
+    """Measured parity figures of this run -> gpurun_out/parity_measured.json (copied to profiles/ when committed)."""
+    import json
+    MEASURED[name] = value
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    os.makedirs(os.path.join(root, 'gpurun_out'), exist_ok=True)
+    with open(os.path.join(root, 'gpurun_out', 'parity_measured.json'), 'w') as f:
+        json.dump(MEASURED, f, indent=1, sort_keys=True)
+
+
+# Contract (BASELINE.json north_star): conv/BN activations within 1e-3 relative of the reference's fp32 -- asserted for
+# precision='strict'.  The default precision='fast' (fp16 operands, one tensor-core pass) has a documented end-to-end drift of up to
+# 2.5e-3 (23 layers x 2 operand roundings of 2e-4 each, tools/error_budget.py); its per-layer error stays inside 1e-3.
+TOL_CONTRACT = 1e-3
+TOL_FAST_E2E = 2.5e-3
+
+
 def make_config(fix):
     config = configparser.ConfigParser()
     config.read_dict({'batch_norm': {'enable': '1'},
@@ -339,9 +359,88 @@ def test_conv_tile_shapes_agree(ops, cfg):
     assert rel_err(y.permute(0, 3, 1, 2), ref) <= 1e-3
 
 
+SPLIT_CASES = [
+    # b, h, w, cin, cout, k, split_a, split_w, src_lo
+    (2, 16, 16, 64, 128, 3, True, True, True),
+    (3, 13, 13, 128, 256, 3, True, False, True),
+    (3, 13, 13, 128, 256, 3, False, True, False),
+    (2, 26, 26, 256, 128, 1, True, True, True),
+    (2, 26, 26, 256, 128, 1, False, True, True),     # input buffer holds [hi | lo] but the unit reads hi only
+    (32, 13, 13, 512, 1024, 3, True, True, True),
+    (3, 21, 19, 32, 64, 3, False, True, False),      # Cin = 32 leaves the halo-tile kernel when an operand is split
+    (5, 19, 17, 96, 136, 3, True, True, True),       # BK = 32 path, ragged column tile
+]
+
+
+@pytest.mark.parametrize('case', SPLIT_CASES)
+def test_conv_split_precision_vs_oracle(ops, case):
+    """yb_conv_bn_act_split_fwd: with an operand split into fp16 hi + lo the unit reproduces the fp32 oracle on that operand to
+    ~1e-6; an operand that stays fp16 is compared with the oracle run on the fp16-rounded operand.  Also checks the [hi | lo]
+    output: hi is the fp16 rounding of the result, hi + lo carries it to ~2^-21."""
+    b, h, w, cin, cout, k, split_a, split_w, src_lo = case
+    gen = torch.Generator().manual_seed(cin * 5 + cout + k)
+    x = torch.randn(b, cin, h, w, generator=gen)
+    wt = torch.randn(cout, cin, k, k, generator=gen) * (2.0 / (cin * k * k)) ** 0.5
+    sd = {'u.bn.weight': torch.rand(cout, generator=gen) + 0.5, 'u.bn.bias': torch.randn(cout, generator=gen) * 0.1,
+          'u.bn.running_mean': torch.randn(cout, generator=gen) * 0.1, 'u.bn.running_var': torch.rand(cout, generator=gen) + 0.5}
+    sd['u.conv.weight'] = wt if split_w else wt.half().float()
+    ref = O.conv_unit(x if split_a else x.half().float(), sd, 'u', k, True, True)
+    scale, shift = ops.bn_fold(*(sd['u.bn.' + n].to(DEV) for n in ('weight', 'bias', 'running_mean', 'running_var')))
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    hi = xn.half()
+    src = torch.cat([hi, (xn - hi.float()).half()], -1).contiguous().to(DEV) if src_lo else hi.to(DEV)
+    w16 = ops.pack_weight_split_f16(wt.to(DEV), split_a, split_w)
+    assert w16.shape == (cout, k, k, cin * (1 + int(split_a) + int(split_w)))
+    out = torch.full((b, h, w, 2 * cout + 8), 7.0, dtype=torch.float16, device=DEV)
+    ops.conv_bn_act_split(src, w16, scale, shift, 0.1, out, a_channels=cin * (2 if split_a else 1), y_ch_off=0, lo_ch_off=cout)
+    got_hi, got_lo = out[..., :cout].float().cpu(), out[..., cout:2 * cout].float().cpu()
+    assert bool((out[..., 2 * cout:] == 7).all()), 'wrote outside its channel slices'
+    full = (got_hi + got_lo).permute(0, 3, 1, 2)
+    err = rel_err(full, ref)
+    assert err <= 2e-5, 'hi + lo rel err %.3e' % err
+    assert torch.equal(got_hi.permute(0, 3, 1, 2).half(), full.half()), 'hi is not the fp16 rounding of hi + lo'
+    # fp32 NCHW output of the same operands (the head's mode)
+    y32 = torch.empty(b, cout, h, w, dtype=torch.float32, device=DEV)
+    ops.conv_bn_act_split(src, w16, scale, shift, 0.1, y32, a_channels=cin * (2 if split_a else 1), out_mode=ops.OUT_F32_NCHW)
+    assert rel_err(y32, ref) <= 2e-5
+
+
+def test_maxpool_split_exact(ops):
+    gen = torch.Generator().manual_seed(77)
+    v = torch.randn(3, 12, 10, 64, generator=gen)
+    v[0, :2, :2, :8] = 1.0                               # ties: the first element of the window wins
+    hi = v.half()
+    lo = (v - hi.float()).half()
+    x = torch.cat([hi, lo], -1).contiguous().to(DEV)
+    out = torch.empty(3, 6, 5, 128, dtype=torch.float16, device=DEV)
+    ops.maxpool2x2_split(x, 64, out)
+    val = (hi.float() + lo.float()).permute(0, 3, 1, 2)
+    ref = torch.nn.functional.max_pool2d(val, 2)
+    got = (out[..., :64].float() + out[..., 64:].float()).permute(0, 3, 1, 2).cpu()
+    assert torch.equal(got, ref)
+
+
 # ------------------------------------------------------------------------------------------------
 # whole backbone through the plugin surface
 # ------------------------------------------------------------------------------------------------
+def _build_darknet(precision):
+    import model
+    import model.yolo2
+    cfg = make_config(1)
+    cfg.read_dict({'b200': {'precision': precision}})
+    dnn = model.yolo2.Darknet(model.ConfigChannels(cfg), O.anchors_yolo_voc(), 20)
+    dnn.load_state_dict(O.make_state_dict(0), strict=False)
+    dnn = dnn.to(DEV).eval()
+    assert dnn.engine.precision == precision
+    return dnn
+
+
+@pytest.fixture(scope='module')
+def darknet_strict():
+    """precision='strict' ([b200] precision in the INI): split-precision operands, the mode the 1e-3 contract is asserted in."""
+    return _build_darknet('strict')
+
+
 @pytest.fixture(scope='module')
 def darknet():
     import model
@@ -352,33 +451,45 @@ def darknet():
     return dnn.to(DEV).eval()
 
 
-def test_darknet_64_every_layer_golden(darknet, golden_dir):
+@pytest.mark.parametrize('precision', ['strict', 'fast'])
+def test_darknet_64_every_layer_golden(darknet, darknet_strict, golden_dir, precision):
     """Each unit on the GPU vs the REFERENCE's own activation for the same image (golden), fed by
     the GPU's own previous layer (so this is the end-to-end drift, layer by layer)."""
+    dnn, tol = (darknet_strict, TOL_CONTRACT) if precision == 'strict' else (darknet, TOL_FAST_E2E)
     g = np.load(os.path.join(golden_dir, 'darknet_64.npz'))
     x = O.synth_images(1, 64, 64, seed=10).to(DEV)
     collect = {}
-    feature = darknet.engine.forward(x, collect=collect).clone()
+    feature = dnn.engine.forward(x, collect=collect).clone()
     worst = 0.0
     for key, act in collect.items():
         if 'act_' + key not in g:
             continue
         e = rel_err(act.permute(0, 3, 1, 2), torch.from_numpy(g['act_' + key]))
         worst = max(worst, e)
-        assert e <= 3e-3, '%s rel err %.3e' % (key, e)
+        assert e <= tol, '%s rel err %.3e' % (key, e)
     e = rel_err(feature, torch.from_numpy(g['feature']))
-    print('darknet64 worst layer rel %.3e, feature rel %.3e' % (worst, e))
-    assert e <= 3e-3
+    record('darknet64_%s' % precision, dict(worst_layer=worst, feature=e))
+    assert e <= tol
 
 
-def test_darknet_416_feature_golden(darknet, golden_dir):
+@pytest.mark.parametrize('precision', ['strict', 'fast'])
+def test_darknet_416_feature_golden(darknet, darknet_strict, golden_dir, precision):
+    dnn, tol = (darknet_strict, TOL_CONTRACT) if precision == 'strict' else (darknet, TOL_FAST_E2E)
     g = np.load(os.path.join(golden_dir, 'darknet_416.npz'))
     x = O.synth_images(1, 416, 416, seed=0).to(DEV)
-    f = darknet(x)
+    f = dnn(x)
     e = rel_err(f, torch.from_numpy(g['feature']))
-    print('darknet416 feature rel %.3e' % e)
+    record('darknet416_%s' % precision, e)
     assert f.shape == (1, 125, 13, 13)
-    assert e <= 3e-3
+    assert e <= tol
+
+
+def test_strict_pipeline_with_and_without_collect_agree(darknet_strict):
+    """The strict forward takes a different route when a test inspects every layer (no fused pool on layers1.2): same feature."""
+    x = O.synth_images(2, 96, 96, seed=21).to(DEV)
+    f0 = darknet_strict.engine.forward(x).clone()
+    f1 = darknet_strict.engine.forward(x, collect={}).clone()
+    assert torch.equal(f0, f1)
 
 
 def test_darknet_per_layer_on_oracle_inputs(darknet, ops):
@@ -470,6 +581,48 @@ def test_region_loss_values_masks_and_gradient(case):
     np.testing.assert_allclose(dbg['iou'].cpu().numpy(), dbg_ref['iou'].numpy(), rtol=1e-5, atol=1e-6)
     for k in ('foreground', 'background', 'center', 'size', 'cls'):
         assert abs(l_gpu[k].item() - l_ref[k].item()) <= 1e-4 * abs(l_ref[k].item()) + 1e-9, (k, l_gpu[k].item(), l_ref[k].item())
+    assert rel_err(f_gpu.grad, f_ref.grad) <= 1e-4
+
+
+@pytest.mark.parametrize('tag', list('abcd'))
+def test_region_loss_vs_executed_reference_golden(golden_dir, tag):
+    """The loss kernels directly against what the reference's own model.loss returned (tests/golden/make_golden_loss.py): 13x13
+    G=16 (a), 19x19 (b), one ground-truth slot (c) and the one-hot class branch train/cross_entropy = 0 (d, model/__init__.py:156-160)."""
+    import model
+    g = np.load(os.path.join(golden_dir, 'loss.npz'))
+    b, s, slots, seed, one_hot = (int(v) for v in g[tag + '_dims'])
+    anchors = O.anchors_yolo_voc()
+    data = O.norm_data(O.synth_targets(b, s * 32, s * 32, slots=slots, seed=20 + seed), s * 32, s * 32, s, s)
+    f = torch.from_numpy(g[tag + '_feature']).to(DEV).requires_grad_(True)
+    losses, dbg = model.loss(anchors, {k: v.to(DEV) for k, v in data.items()}, dict(feature=f), 0.6, cross_entropy=not one_hot)
+    sum(losses[k] * O.HPARAM_DEFAULT[k] for k in losses).backward()
+    for k, v in losses.items():
+        ref = float(g[tag + '_loss_' + k])
+        assert abs(v.item() - ref) <= 1e-4 * abs(ref) + 1e-9, (k, v.item(), ref)
+    assert np.array_equal(dbg['positive'].cpu().numpy().astype(np.uint8), g[tag + '_positive'])
+    assert np.array_equal(dbg['negative'].cpu().numpy().astype(np.uint8), g[tag + '_negative'])
+    np.testing.assert_allclose(dbg['iou'].cpu().numpy(), g[tag + '_iou'], rtol=1e-5, atol=1e-6)
+    assert rel_err(f.grad, torch.from_numpy(g[tag + '_grad'])) <= 1e-4
+
+
+def test_region_loss_single_class_head():
+    """A*5-channel head (model.output_channels with one category, model/__init__.py:46-50): no class targets, no class term."""
+    import model
+    anchors = O.anchors_yolo_voc()
+    b, s = 3, 13
+    feat = torch.randn(b, 25, s, s, generator=torch.Generator().manual_seed(4)) * 0.7
+    data = O.norm_data(O.synth_targets(b, s * 32, s * 32, slots=8, seed=31), s * 32, s * 32, s, s)
+    f_ref = feat.clone().requires_grad_(True)
+    l_ref, dbg_ref = O.loss(anchors, data, O.decode(f_ref, anchors), 0.6)
+    assert 'cls' not in l_ref
+    O.loss_total(l_ref).backward()
+    f_gpu = feat.to(DEV).requires_grad_(True)
+    l_gpu, dbg = model.loss(anchors, {k: v.to(DEV) for k, v in data.items()}, dict(feature=f_gpu), 0.6)
+    assert set(l_gpu) == set(l_ref)
+    sum(l_gpu[k] * O.HPARAM_DEFAULT[k] for k in l_gpu).backward()
+    assert torch.equal(dbg['positive'].cpu().bool(), dbg_ref['positive']) and torch.equal(dbg['negative'].cpu().bool(), dbg_ref['negative'])
+    for k in l_ref:
+        assert abs(l_gpu[k].item() - l_ref[k].item()) <= 1e-4 * abs(l_ref[k].item()) + 1e-9, k
     assert rel_err(f_gpu.grad, f_ref.grad) <= 1e-4
 
 
@@ -651,6 +804,61 @@ def test_training_step_vs_oracle():
         rm = dict(dnn.named_buffers())[key + '.bn.running_mean'].cpu()
         exp = 0.99 * sd0[key + '.bn.running_mean'] + 0.01 * mean.detach()
         assert rel_err(rm, exp) <= 2e-2, key
+
+
+def test_c3_batch64_training_step_vs_executed_reference(golden_dir):
+    """BASELINE configs[2] at its real size: one 64 x 3 x 416 x 416 training step (train-mode forward with batch-statistics BatchNorm,
+    region loss, full backward) against the SAME step executed with the reference's own modules on CPU
+    (tests/golden/make_golden_c3.py).  With 10,816+ samples behind every batch statistic the step is well conditioned (unlike the
+    4 x 128 x 128 wiring test above), so the bounds are parity bounds: head feature and the five loss terms to 5e-3 / 1e-2, every
+    parameter-gradient norm to 3e-2, running statistics to 2e-3; the measured values go to parity_measured.json."""
+    import model
+    import model.yolo2
+    g = np.load(os.path.join(golden_dir, 'c3_train64.npz'))
+    cfg = make_config(1)
+    anchors = O.anchors_yolo_voc()
+    sd0 = O.make_state_dict(0)
+    b, size = 64, 416
+    s = size // 32
+    x = O.synth_images(b, size, size, seed=64)
+    data = O.norm_data(O.synth_targets(b, size, size, slots=16, seed=65), size, size, s, s)
+    dnn = model.yolo2.Darknet(model.ConfigChannels(cfg), anchors, 20)
+    dnn.load_state_dict(sd0, strict=False)
+    dnn = dnn.to(DEV).train()
+    inference = model.Inference(cfg, dnn, anchors).train()
+    pred = model._inference(inference, x.to(DEV))
+    losses, dbg = model.loss(anchors, {k: v.to(DEV) for k, v in data.items()}, pred, 0.6)
+    sum(losses[k] * O.HPARAM_DEFAULT[k] for k in losses).backward()
+    f = pred['feature'].detach().cpu()
+    e_f = max(((f[bi] - torch.from_numpy(g['feature'][slot])).abs().max() / float(g['feature_absmax'][bi])).item() for slot, bi in enumerate((0, b - 1)))
+    e_loss = {k: abs(losses[k].item() - float(g['loss_' + k])) / abs(float(g['loss_' + k])) for k in losses}
+    npos, nneg = int(dbg['positive'].sum().item()), int(dbg['negative'].sum().item())
+    worst_norm, worst_head = (0.0, None), (1.0, None)
+    small = 0.0
+    for name, p in dnn.named_parameters():
+        assert p.grad is not None, name
+        gr = p.grad.detach().float().cpu()
+        rn = abs(gr.double().norm().item() / float(g['gnorm_' + name]) - 1.0)
+        if rn > worst_norm[0]:
+            worst_norm = (rn, name)
+        h, hr = gr.flatten()[:16], torch.from_numpy(g['ghead_' + name])
+        cos = (torch.dot(h, hr) / (h.norm() * hr.norm() + 1e-30)).item()
+        if cos < worst_head[0]:
+            worst_head = (cos, name)
+        if 'gfull_' + name in g:
+            small = max(small, rel_l2(gr, torch.from_numpy(g['gfull_' + name])))
+    e_run = max(rel_err(buf, torch.from_numpy(g['buf_' + name])) for name, buf in dnn.named_buffers() if 'running' in name)
+    record('c3_batch64_train', dict(feature=e_f, losses=e_loss, positives=(npos, int(g['positives'])), negatives=(nneg, int(g['negatives'])),
+                                    worst_grad_norm=worst_norm, worst_grad_head_cosine=worst_head, small_grads_rel_l2=small, running_stats=e_run))
+    assert npos == int(g['positives'])
+    assert abs(nneg - int(g['negatives'])) <= 1e-3 * int(g['negatives'])
+    assert e_f <= 5e-3, e_f
+    for k, v in e_loss.items():
+        assert v <= 1e-2, (k, v)
+    assert worst_norm[0] <= 3e-2, worst_norm
+    assert worst_head[0] >= 0.99, worst_head
+    assert small <= 3e-2, small
+    assert e_run <= 2e-3, e_run
 
 
 def test_graphed_training_step_matches_eager():
@@ -995,19 +1203,94 @@ def test_collate_gpu_batch_and_training_step_from_uint8_frames():
     assert lt == lt and 0.0 < lt < 10.0 and (out['height'], out['width']) == (64, 64)
 
 
-def test_c1_single_image_feature_vs_executed_reference(golden_dir):
+def _match_detections(got, ref, iou_min=0.98):
+    """Greedy one-to-one matching of two detection lists (yx_min, yx_max, cls): same class and box IoU >= iou_min.
+    Returns the number of matched pairs."""
+    gmin, gmax, gcls = got
+    rmin, rmax, rcls = ref
+    if len(gcls) == 0 or len(rcls) == 0:
+        return 0
+    iou = O.iou_matrix(gmin, gmax, rmin, rmax)
+    iou = torch.where(gcls[:, None] == rcls[None, :], iou, torch.zeros_like(iou))
+    used, n = set(), 0
+    for i in range(iou.shape[0]):
+        row = iou[i].clone()
+        for j in used:
+            row[j] = 0
+        j = int(row.argmax())
+        if row[j] >= iou_min:
+            used.add(j); n += 1
+    return n
+
+
+@pytest.mark.parametrize('precision', ['strict', 'fast'])
+def test_c1_single_image_feature_and_detections_vs_executed_reference(golden_dir, precision):
     """BASELINE configs[0] on the GPU: the 416x416 RGB uint8 network input the reference's transform produced from its own
-    image.jpg goes into the model as is (ToTensor fused into the first conv kernel); head feature vs the reference's
-    detect.py chain executed on CPU (tests/golden/make_golden_c1.py), same bound as the synthetic 416x416 golden."""
+    image.jpg goes into the model as is (ToTensor fused into the first conv kernel); head feature AND the detections (the
+    reference returns 586 for these weights) vs the reference's detect.py chain executed on CPU (tests/golden/make_golden_c1.py)."""
+    import detect
     import model
-    import model.yolo2
     g = np.load(os.path.join(golden_dir, 'c1_image.npz'))
+    dnn = _build_darknet(precision)
+    tol = TOL_CONTRACT if precision == 'strict' else TOL_FAST_E2E
     cfg = make_config(1)
     anchors = O.anchors_yolo_voc()
-    dnn = model.yolo2.Darknet(model.ConfigChannels(cfg), anchors, 20)
-    dnn.load_state_dict(O.make_state_dict(0), strict=False)
-    dnn = dnn.to(DEV).eval()
-    f = dnn(torch.from_numpy(g['rgb'])[None].contiguous().to(DEV))
+    inference = model.Inference(cfg, dnn, anchors).eval()
+    pred = model._inference(inference, torch.from_numpy(g['rgb'])[None].contiguous().to(DEV))
+    f = pred['feature']
     e = rel_err(f, torch.from_numpy(g['feature']))
-    print('C1 image.jpg feature rel err %.3e' % e)
-    assert f.shape == g['feature'].shape and e <= 3e-3
+    assert f.shape == g['feature'].shape and e <= tol, 'feature rel err %.3e' % e
+    res = detect.postprocess_batch(cfg, pred)[0]
+    assert res is not None and not bool(g['none'])
+    iou, yx_min, yx_max, cls, score = (t.cpu() for t in res)
+    ref = (torch.from_numpy(g['det_yx_min']), torch.from_numpy(g['det_yx_max']), torch.from_numpy(g['det_cls']))
+    matched = _match_detections((yx_min, yx_max, cls), ref)
+    n_ref, n_got = len(g['det_cls']), len(cls)
+    record('c1_%s' % precision, dict(feature=e, detections_ref=n_ref, detections_gpu=n_got, matched=matched, kept_ref=len(g['det_iou']), kept_gpu=len(iou)))
+    # every decision (0.005 score threshold, IoU 0.45 suppression) is taken on values that differ by the feature error above, so a
+    # handful of borderline boxes may flip; the sets must otherwise coincide
+    assert matched >= 0.97 * max(n_ref, n_got), (matched, n_ref, n_got)
+    if matched == n_ref == n_got:
+        order = np.lexsort((cls.numpy(), yx_min[:, 1].numpy(), yx_min[:, 0].numpy()))
+        order_r = np.lexsort((g['det_cls'], g['det_yx_min'][:, 1], g['det_yx_min'][:, 0]))
+        np.testing.assert_allclose(score.numpy()[order], g['det_score'][order_r], rtol=2e-2, atol=1e-4)
+
+
+def test_c2_batch32_feature_and_detections_vs_executed_reference(golden_dir):
+    """BASELINE configs[1] at its real size: 32 x 3 x 416 x 416 through backbone (strict precision) + decode + filter + NMS + per-class
+    expansion in one pipeline call; head features of three images vs the reference's (1e-3), and the detection SETS of all 32
+    images vs the ones the reference returns (tests/golden/make_golden_c2.py)."""
+    import detect
+    import model
+    g = np.load(os.path.join(golden_dir, 'c2_batch32.npz'))
+    b = int(g['batch'])
+    dnn = _build_darknet('strict')
+    cfg = make_config(1)
+    anchors = O.anchors_yolo_voc()
+    inference = model.Inference(cfg, dnn, anchors).eval()
+    x = O.synth_images(b, 416, 416, seed=int(g['seed'])).to(DEV)
+    pred = model._inference(inference, x)
+    f = pred['feature'].cpu()
+    errs = []
+    for slot, bi in enumerate(g['images']):       # per image: max|d| over the image / max|ref| of that image (stricter than the whole-batch norm)
+        errs.append(((f[bi] - torch.from_numpy(g['feature'][slot])).abs().max() / float(g['feature_absmax'][bi])).item())
+    assert max(errs) <= TOL_CONTRACT, errs
+    np.testing.assert_allclose(f.abs().reshape(b, -1).max(1).values.numpy(), g['feature_absmax'], rtol=2e-3)
+    results = detect.postprocess_batch(cfg, pred)
+    off_k = np.concatenate([[0], np.cumsum(g['n_keep'])])
+    off_d = np.concatenate([[0], np.cumsum(g['n_det'])])
+    tot_ref = tot_got = tot_match = kept_same = 0
+    for bi, res in enumerate(results):
+        n_ref = int(g['n_det'][bi])
+        if res is None:
+            assert n_ref == 0
+            continue
+        iou, yx_min, yx_max, cls, score = (t.cpu() for t in res)
+        sl = slice(off_d[bi], off_d[bi + 1])
+        ref = (torch.from_numpy(g['det_yx_min'][sl]), torch.from_numpy(g['det_yx_max'][sl]), torch.from_numpy(g['det_cls'][sl]))
+        tot_match += _match_detections((yx_min, yx_max, cls), ref)
+        tot_ref += n_ref
+        tot_got += len(cls)
+        kept_same += int(len(iou) == int(g['n_keep'][bi]))
+    record('c2_batch32_strict', dict(feature=max(errs), detections_ref=tot_ref, detections_gpu=tot_got, matched=tot_match, images_same_keep_count=kept_same))
+    assert tot_match >= 0.97 * max(tot_ref, tot_got), (tot_match, tot_ref, tot_got)

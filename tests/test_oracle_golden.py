@@ -314,3 +314,33 @@ def test_c1_single_image_chain_oracle_matches_executed_reference(golden_dir):
     if os.path.exists(jpg):
         import cv2
         assert np.array_equal(O.resize_u8(cv2.imread(jpg), 416, 416)[..., ::-1], g['rgb'])
+
+
+def test_c2_batch32_oracle_matches_executed_reference(golden_dir):
+    """BASELINE configs[1] at its real size (32 x 3 x 416 x 416): the oracle chain against the reference's own modules executed on
+    the same batch (tests/golden/make_golden_c2.py): three head features, every image's max|feature|, kept-box and detection counts,
+    and the detections themselves (classes exact, boxes / scores to float tolerance)."""
+    g = load(golden_dir, 'c2_batch32.npz')
+    b = int(g['batch'])
+    sd = O.make_state_dict(seed=0)
+    anchors = O.anchors_yolo_voc()
+    x = O.synth_images(b, 416, 416, seed=int(g['seed']))
+    with torch.no_grad():
+        feature = O.darknet_forward(sd, x)
+        pred = O.decode(feature, anchors)
+        prob = O.class_prob(pred)
+    for slot, bi in enumerate(g['images']):
+        np.testing.assert_allclose(feature[bi].numpy(), g['feature'][slot], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(feature.abs().reshape(b, -1).max(1).values.numpy(), g['feature_absmax'], rtol=1e-5)
+    off = np.concatenate([[0], np.cumsum(g['n_det'])])
+    for bi in range(b):
+        res = O.postprocess(pred['iou'][bi].reshape(-1), pred['yx_min'][bi].reshape(-1, 2), pred['yx_max'][bi].reshape(-1, 2),
+                            prob[bi].reshape(-1, prob.size(-1)), True, 0.3, 0.005, 0.45)
+        assert (res is None) == (int(g['n_det'][bi]) == 0)
+        if res is None:
+            continue
+        assert len(res[0]) == int(g['n_keep'][bi]) and len(res[3]) == int(g['n_det'][bi]), bi
+        sl = slice(off[bi], off[bi + 1])
+        assert np.array_equal(res[3].numpy(), g['det_cls'][sl])
+        np.testing.assert_allclose(res[1].numpy(), g['det_yx_min'][sl], rtol=1e-4, atol=1e-4)
+        np.testing.assert_allclose(res[4].numpy(), g['det_score'][sl], rtol=1e-3, atol=1e-6)

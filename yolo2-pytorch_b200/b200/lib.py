@@ -24,6 +24,10 @@ SIGNATURES = {
     'yb_conv_workspace_bytes': [],
     'yb_conv_bn_act_fwd_ws': [P, P, P, P, c_float, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_longlong, c_int, c_int, c_int, P,
                               c_longlong, P],
+    'yb_conv_bn_act_split_fwd': [P, P, P, P, c_float, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_longlong, c_int, c_int, c_int,
+                                 c_int, P, c_longlong, P],
+    'yb_pack_weight_split_f16': [P, P, c_int, c_int, c_int, c_int, c_int, P],
+    'yb_maxpool2x2_split_f16': [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P],
     'yb_conv_ref_fwd': [P, P, P, P, c_float, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_longlong, c_int, c_int, P],
     'yb_maxpool2x2_f16': [P, P, c_int, c_int, c_int, c_int, c_int, P],
     'yb_maxpool2x2_s1_f16': [P, P, c_int, c_int, c_int, c_int, c_int, P],

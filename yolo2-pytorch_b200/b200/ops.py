@@ -67,6 +67,20 @@ def pack_weight_f16(w, mode=0):
     return out
 
 
+SPLIT_SEGMENTS = {(True, False): (2, 0b00), (False, True): (2, 0b10), (True, True): (3, 0b100)}
+
+
+def pack_weight_split_f16(w, split_a, split_w):
+    """[Cout,Cin,k,k] fp32 -> fp16 [Cout,k,k,S*Cin], the concatenated B operand of the split-precision conv: segments
+    [w_hi | w_hi] (activation split), [w_hi | w_lo] (weight split) or [w_hi | w_hi | w_lo] (both)."""
+    _req(w, torch.float32, 'weight')
+    cout, cin, k, _ = w.shape
+    segments, lo_mask = SPLIT_SEGMENTS[(bool(split_a), bool(split_w))]
+    out = torch.empty(cout, k, k, segments * cin, dtype=torch.float16, device=w.device)
+    _ck(_l.load().yb_pack_weight_split_f16(_p(w), _p(out), cout, cin, k, segments, lo_mask, _s()), 'yb_pack_weight_split_f16')
+    return out
+
+
 def bn_fold(gamma, beta, mean, var, eps=1e-5):
     for n, t in (('gamma', gamma), ('beta', beta), ('mean', mean), ('var', var)):
         _req(t, torch.float32, n)
@@ -151,6 +165,33 @@ def conv_bn_act(x, w, scale, shift, slope, out=None, out_mode=OUT_F16_NHWC, y_ch
     return out
 
 
+def conv_bn_act_split(x, w, scale, shift, slope, out, a_channels, y_ch_off=0, lo_ch_off=-1, out_mode=OUT_F16_NHWC, flags=0, workspace=None):
+    """Split-precision conv unit (yb_conv_bn_act_split_fwd).  x: fp16 [B,H,W,x_ld] holding `a_channels` usable channels
+    (C, or 2C = [hi | lo]); w: fp16 [Cout,k,k,K'] from pack_weight_split_f16; out fp16 [B,H,W,y_ld]: hi at y_ch_off, and the fp16
+    rounding residual at lo_ch_off when lo_ch_off >= 0; or out fp32 [B,Cout,H,W]."""
+    _req(x, torch.float16, 'x'); _req(w, torch.float16, 'w'); _req(scale, torch.float32, 'scale'); _req(shift, torch.float32, 'shift')
+    b, h, wd, x_ld = x.shape
+    cout, k, _, kch = w.shape
+    if out_mode == OUT_F16_NHWC:
+        _req(out, torch.float16, 'out')
+        y_ld = out.shape[-1]
+    else:
+        _req(out, torch.float32, 'out')
+        y_ld = 0
+    ws_ptr, ws_bytes = (None, 0) if workspace is None else (_p(_req(workspace, torch.uint8, 'workspace')), workspace.numel())
+    _ck(_l.load().yb_conv_bn_act_split_fwd(_p(x), _p(w), _p(scale), _p(shift), float(slope), _p(out), b, h, wd, kch, int(a_channels), cout, k, x_ld,
+                                           y_ld, y_ch_off, lo_ch_off, out_mode, flags, ws_ptr, ws_bytes, _s()), 'yb_conv_bn_act_split_fwd')
+    return out
+
+
+def maxpool2x2_split(x, channels, out):
+    """nn.MaxPool2d(2) on [hi | lo] activations: x [B,H,W,2C] -> out [B,H/2,W/2,2C]."""
+    _req(x, torch.float16, 'x'); _req(out, torch.float16, 'out')
+    b, h, w, x_ld = x.shape
+    _ck(_l.load().yb_maxpool2x2_split_f16(_p(x), _p(out), b, h, w, channels, x_ld, channels, out.shape[-1], channels, _s()), 'yb_maxpool2x2_split_f16')
+    return out
+
+
 def conv_bn_act_stats(x, w, scale, shift, slope, sums, out=None, flags=0):
     """conv_bn_act (fp16 NHWC out) that also accumulates per-channel sum / sum of squares of the stored outputs into
     `sums` (float64 [2*Cout], zero on entry) in its epilogue -- the training forward's batch statistics."""
@@ -190,10 +231,15 @@ def maxpool2x2_s1(x, out=None):
     return out
 
 
-def reorg_f16(x, out, y_ch_off=0):
+def reorg_f16(x, out, y_ch_off=0, channels=None, x_ch_off=0):
+    """space-to-depth(2) of channels [x_ch_off, x_ch_off + channels) of x into channels [y_ch_off, y_ch_off + 4*channels) of out."""
     _req(x, torch.float16, 'x'); _req(out, torch.float16, 'out')
-    b, h, w, c = x.shape
-    _ck(_l.load().yb_reorg_f16(_p(x), _p(out), b, h, w, c, c, out.shape[-1], y_ch_off, _s()), 'yb_reorg_f16')
+    b, h, w, x_ld = x.shape
+    c = x_ld if channels is None else channels
+    if x_ch_off % 8 or x_ch_off + c > x_ld:
+        raise ValueError('reorg: bad channel slice')
+    xp = ctypes.c_void_p(x.data_ptr() + 2 * x_ch_off)
+    _ck(_l.load().yb_reorg_f16(xp, _p(out), b, h, w, c, x_ld, out.shape[-1], y_ch_off, _s()), 'yb_reorg_f16')
     return out
 
 

@@ -110,6 +110,9 @@ class DarknetTrainer(object):
             raise RuntimeError('Darknet (B200) training: input must be a CUDA tensor')
         b, _, h, w = x.shape
         x = x.contiguous().float()
+        if eng.precision != 'fast':
+            raise RuntimeError("Darknet (B200) training uses fp16 operands with fp32 accumulation; precision='strict' is an inference mode "
+                               "(call dnn.engine.set_precision('fast') before train())")
         eng.refresh(force=True)      # every step: do not trust parameter version counters (fused optimizers do not advance them)
         for u in eng.all_units()[:-1]:
             if u.bn is None:

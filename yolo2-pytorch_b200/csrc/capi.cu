@@ -62,7 +62,9 @@ int* debug_word_device() {
 // implemented in the kernel translation units
 long long conv_workspace_bytes();
 int conv_igemm_forward(const void*, const void*, const float*, const float*, float, void*, int, int, int, int, int, int, int, long long,
-                       int, int, int, void*, long long, double*, cudaStream_t);
+                       int, int, int, void*, long long, double*, int, int, cudaStream_t);
+int pack_weight_split(const float*, void*, int, int, int, int, int, cudaStream_t);
+int maxpool2x2_split(const void*, void*, int, int, int, int, int, int, int, int, cudaStream_t);
 int conv_ref_forward(const void*, const void*, const float*, const float*, float, void*, int, int, int, int, int, int, int, long long,
                      int, int, cudaStream_t);
 int pack_weight(const float*, void*, int, int, int, int, int, cudaStream_t);
@@ -142,14 +144,14 @@ int yb_conv_bn_act_fwd(const void* x, const void* w, const float* scale, const f
                        int height, int width, int cin, int cout, int ksize, int x_ld, long long y_ld, int y_ch_off, int out_mode,
                        int flags, yb_stream_t stream) {
   return yb::conv_igemm_forward(x, w, scale, shift, slope, y, batch, height, width, cin, cout, ksize, x_ld, y_ld, y_ch_off, out_mode,
-                                flags, nullptr, 0, nullptr, S(stream));
+                                flags, nullptr, 0, nullptr, 0, -1, S(stream));
 }
 
 int yb_conv_bn_act_stats_fwd(const void* x, const void* w, const float* scale, const float* shift, float slope, void* y, int batch,
                              int height, int width, int cin, int cout, int ksize, int x_ld, long long y_ld, int y_ch_off, int flags,
                              double* sums, yb_stream_t stream) {
   return yb::conv_igemm_forward(x, w, scale, shift, slope, y, batch, height, width, cin, cout, ksize, x_ld, y_ld, y_ch_off, 0, flags, nullptr, 0,
-                                sums, S(stream));
+                                sums, 0, -1, S(stream));
 }
 
 long long yb_conv_workspace_bytes(void) { return yb::conv_workspace_bytes(); }
@@ -158,7 +160,24 @@ int yb_conv_bn_act_fwd_ws(const void* x, const void* w, const float* scale, cons
                           int height, int width, int cin, int cout, int ksize, int x_ld, long long y_ld, int y_ch_off, int out_mode,
                           int flags, void* workspace, long long workspace_bytes, yb_stream_t stream) {
   return yb::conv_igemm_forward(x, w, scale, shift, slope, y, batch, height, width, cin, cout, ksize, x_ld, y_ld, y_ch_off, out_mode,
-                                flags, workspace, workspace_bytes, nullptr, S(stream));
+                                flags, workspace, workspace_bytes, nullptr, 0, -1, S(stream));
+}
+
+int yb_conv_bn_act_split_fwd(const void* x, const void* w_split, const float* scale, const float* shift, float slope, void* y, int batch,
+                             int height, int width, int k_channels, int a_channels, int cout, int ksize, int x_ld, long long y_ld,
+                             int y_ch_off, int lo_ch_off, int out_mode, int flags, void* workspace, long long workspace_bytes,
+                             yb_stream_t stream) {
+  return yb::conv_igemm_forward(x, w_split, scale, shift, slope, y, batch, height, width, k_channels, cout, ksize, x_ld, y_ld, y_ch_off,
+                                out_mode, flags, workspace, workspace_bytes, nullptr, a_channels, lo_ch_off, S(stream));
+}
+
+int yb_pack_weight_split_f16(const float* w_oihw, void* w_f16, int cout, int cin, int ksize, int segments, int lo_mask, yb_stream_t stream) {
+  return yb::pack_weight_split(w_oihw, w_f16, cout, cin, ksize, segments, lo_mask, S(stream));
+}
+
+int yb_maxpool2x2_split_f16(const void* x, void* y, int batch, int height, int width, int channels, int x_ld, int x_lo_off, int y_ld,
+                            int y_lo_off, yb_stream_t stream) {
+  return yb::maxpool2x2_split(x, y, batch, height, width, channels, x_ld, x_lo_off, y_ld, y_lo_off, S(stream));
 }
 
 int yb_conv_ref_fwd(const void* x, const void* w, const float* scale, const float* shift, float slope, void* y, int batch, int height,

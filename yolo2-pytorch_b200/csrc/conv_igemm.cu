@@ -54,6 +54,14 @@ struct ConvParams {
   // optional (training): per-channel sum and sum of squares of the STORED (fp16-rounded) outputs, added into
   // stats[0..Cout) / stats[Cout..2Cout) -- the batch statistics of train-mode BatchNorm without a second pass over z
   double* stats;
+  // split-precision ("strict") mode.  The reduction dimension of the GEMM is a concatenation of fp16 terms,
+  //   A = [a_hi | a_lo | a_hi] (channels of one pixel),  W = [w_hi | w_hi | w_lo] (per tap),
+  // so a_hi*w_hi + a_lo*w_hi + a_hi*w_lo accumulate into ONE fp32 TMEM accumulator: the fp16 rounding of either operand
+  // (2^-11 relative, the source of the 1.6e-3 end-to-end drift) drops to ~2^-22.  `cin` is then the concatenated width,
+  // `a_wrap` the number of channels the activation tensor really holds (C or 2C): channel offsets past it wrap around.
+  // `lo_off` != 0: the epilogue also stores lo = fp16(v - fp32(fp16(v))) at y + lo_off (fp16 NHWC only).
+  int a_wrap;
+  long long lo_off;
 };
 
 // role 0 = TMA producer, 1 = MMA issuer, 2 = epilogue thread 0; slot = running event index of that role
@@ -222,7 +230,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         }
         for (int kb = it.kb0; kb < it.kb1; ++kb) {
           const int tap = kb / p.kb_per_tap;
-          const int c0 = (kb - tap * p.kb_per_tap) * BK;
+          const int c0 = (kb - tap * p.kb_per_tap) * BK;    // offset inside the (possibly concatenated) weight row of this tap
+          const int ca = c0 >= p.a_wrap ? c0 - p.a_wrap : c0;   // activation channel (split mode: the hi part is read twice)
           const int r = tap / p.ksize;
           const int s = tap - r * p.ksize;
           mbar_wait(bar_empty + 8 * stage, phase ^ 1, p.dbg, 0x100 | stage);
@@ -235,8 +244,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             // a large per-instruction cost (profiles/r01_wgrad_variants.txt), rows past the tensor end are zero-filled
             if (!(p.skip & 1)) {
               const uint32_t dst = smem_a + stage * Cfg::kABytes;
-              if (p.a_im2col) tma_load_im2col_4d(dst, &tmap_a, full, c0, w0[0] - p.pad, h0[0] - p.pad, img[0], static_cast<uint16_t>(s), static_cast<uint16_t>(r));
-              else tma_load_2d(dst, &tmap_a, full, c0, m_cta);
+              if (p.a_im2col) tma_load_im2col_4d(dst, &tmap_a, full, ca, w0[0] - p.pad, h0[0] - p.pad, img[0], static_cast<uint16_t>(s), static_cast<uint16_t>(r));
+              else tma_load_2d(dst, &tmap_a, full, ca, m_cta);
             }
           } else {
 #pragma unroll
@@ -244,11 +253,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             if (t < nsub) {
               const uint32_t dst = smem_a + stage * Cfg::kABytes + t * Cfg::kASubBytes;
               if (p.a_im2col) {
-                if (kPair) tma_load_im2col_4d_pair(dst, &tmap_a, full, c0, w0[t] - p.pad, h0[t] - p.pad, img[t], static_cast<uint16_t>(s), static_cast<uint16_t>(r));
-                else tma_load_im2col_4d(dst, &tmap_a, full, c0, w0[t] - p.pad, h0[t] - p.pad, img[t], static_cast<uint16_t>(s), static_cast<uint16_t>(r));
+                if (kPair) tma_load_im2col_4d_pair(dst, &tmap_a, full, ca, w0[t] - p.pad, h0[t] - p.pad, img[t], static_cast<uint16_t>(s), static_cast<uint16_t>(r));
+                else tma_load_im2col_4d(dst, &tmap_a, full, ca, w0[t] - p.pad, h0[t] - p.pad, img[t], static_cast<uint16_t>(s), static_cast<uint16_t>(r));
               } else {
-                if (kPair) tma_load_2d_pair(dst, &tmap_a, full, c0, m_cta + t * BM);
-                else tma_load_2d(dst, &tmap_a, full, c0, m_cta + t * BM);
+                if (kPair) tma_load_2d_pair(dst, &tmap_a, full, ca, m_cta + t * BM);
+                else tma_load_2d(dst, &tmap_a, full, ca, m_cta + t * BM);
               }
             }
           }
@@ -455,6 +464,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                   pk.z = *reinterpret_cast<uint32_t*>(&h2);
                   pk.w = *reinterpret_cast<uint32_t*>(&h3);
                   *reinterpret_cast<uint4*>(dst + g * 8) = pk;
+                  if (p.lo_off != 0) {
+                    // residual of the fp16 rounding, itself rounded to fp16: hi + lo carries ~22 mantissa bits
+                    const float2 r0 = __half22float2(h0), r1 = __half22float2(h1), r2 = __half22float2(h2), r3 = __half22float2(h3);
+                    __half2 l0 = __floats2half2_rn(f[g * 8 + 0] - r0.x, f[g * 8 + 1] - r0.y);
+                    __half2 l1 = __floats2half2_rn(f[g * 8 + 2] - r1.x, f[g * 8 + 3] - r1.y);
+                    __half2 l2 = __floats2half2_rn(f[g * 8 + 4] - r2.x, f[g * 8 + 5] - r2.y);
+                    __half2 l3 = __floats2half2_rn(f[g * 8 + 6] - r3.x, f[g * 8 + 7] - r3.y);
+                    uint4 pl;
+                    pl.x = *reinterpret_cast<uint32_t*>(&l0);
+                    pl.y = *reinterpret_cast<uint32_t*>(&l1);
+                    pl.z = *reinterpret_cast<uint32_t*>(&l2);
+                    pl.w = *reinterpret_cast<uint32_t*>(&l3);
+                    *reinterpret_cast<uint4*>(dst + p.lo_off + g * 8) = pl;
+                  }
                 }
               }
             }
@@ -1071,13 +1094,19 @@ static int conv_c32_forward(const void* x, const void* w, const float* scale, co
 
 int conv_igemm_forward(const void* x, const void* w, const float* scale, const float* shift, float slope, void* y, int batch,
                        int height, int width, int cin, int cout, int ksize, int x_ld, long long y_ld, int y_ch_off, int out_mode,
-                       int flags, void* workspace, long long workspace_bytes, double* stats, cudaStream_t stream) {
+                       int flags, void* workspace, long long workspace_bytes, double* stats, int a_channels, int lo_ch_off, cudaStream_t stream) {
   YB_REQUIRE(x && w && scale && shift && y, "conv: null pointer");
+  // split-precision operands (see ConvParams::a_wrap): cin is the concatenated reduction width, a_channels what x really holds
+  if (a_channels <= 0) a_channels = cin;
+  const bool split = a_channels != cin || lo_ch_off >= 0;
+  YB_REQUIRE(a_channels <= cin && a_channels % 32 == 0 && cin - a_channels <= a_channels, "conv: a_channels=%d does not fit cin=%d", a_channels, cin);
+  YB_REQUIRE(lo_ch_off < 0 || (out_mode == 0 && stats == nullptr && lo_ch_off % 8 == 0 && lo_ch_off >= y_ch_off + cout && lo_ch_off + cout <= y_ld),
+             "conv: lo_ch_off=%d (needs fp16 NHWC output with room for a second Cout-wide slice)", lo_ch_off);
   YB_REQUIRE(stats == nullptr || (out_mode == 0 && !(cin == 32 && ksize == 3 && cout <= 64)), "conv: fused statistics need the generic fp16 NHWC kernel");
   YB_REQUIRE(ksize == 1 || ksize == 3, "conv: ksize %d unsupported (1 or 3)", ksize);
   YB_REQUIRE(batch > 0 && height > 0 && width > 0, "conv: bad shape");
   YB_REQUIRE(cin % 32 == 0, "conv: Cin=%d must be a multiple of 32 (layer 0 uses yb_conv0_*)", cin);
-  YB_REQUIRE(x_ld >= cin && x_ld % 8 == 0, "conv: x_ld=%d", x_ld);
+  YB_REQUIRE(x_ld >= a_channels && x_ld % 8 == 0, "conv: x_ld=%d", x_ld);
   YB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0, "conv: x/w must be 16B aligned");
   YB_REQUIRE(out_mode == 0 || out_mode == 1, "conv: out_mode");
   if (out_mode == 0) {
@@ -1088,10 +1117,10 @@ int conv_igemm_forward(const void* x, const void* w, const float* scale, const f
   YB_REQUIRE(m_total_ll < (1ll << 31) - BM, "conv: too many pixels");
   const int pool = (flags >> 4) & 1;        // YB_CONV_POOL2X2
   // 3x3, Cin = 32, Cout <= 64 (layers1.2): halo-tile kernel unless a test asks for one of the im2col kernels
-  if (cin == 32 && ksize == 3 && cout <= 64 && out_mode == 0 && ((flags >> 28) & 1) == 0 && ((flags >> 5) & 1) == 0 && ((flags >> 8) & 0xFFFF) == 0)
+  if (!split && cin == 32 && ksize == 3 && cout <= 64 && out_mode == 0 && ((flags >> 28) & 1) == 0 && ((flags >> 5) & 1) == 0 && ((flags >> 8) & 0xFFFF) == 0)
     return conv_c32_forward(x, w, scale, shift, slope, y, batch, height, width, cout, x_ld, y_ld, y_ch_off, pool, flags, stream);
   if (pool) return fail(YB_ERR_UNSUPPORTED, "conv: YB_CONV_POOL2X2 is only implemented for the Cin = 32 3x3 layer");
-  const int bk = (cin % 64 == 0) ? 64 : 32;
+  const int bk = (cin % 64 == 0 && a_channels % 64 == 0) ? 64 : 32;     // K-blocks never straddle the wrap point
   // tile shape: flags may force BLOCK_N (bits 8..17) and the number of M-subtiles (bits 20..21);
   // otherwise pick the (BLOCK_N, M-subtiles) pair with the lowest modelled time.  The model was
   // fitted to tools/conv_sweep.py on B200 (profiles/r01_conv_sweep.md): the kernel is bound by the
@@ -1155,7 +1184,7 @@ int conv_igemm_forward(const void* x, const void* w, const float* scale, const f
     if (bn == 0) { bn = force_bn ? force_bn : 128; mt = force_mt ? force_mt : 1; pair = force_pair == 2; streamk = 0; }
   }
   // small-K specialisation (Cin = 32, 3x3, Cout <= 64, fp16 NHWC out): all 9 taps per stage, resident weights
-  const bool smallk = (cin == 32 && ksize == 3 && cout <= 64 && out_mode == 0 && !force_bn && !force_mt && !force_pair && ((flags >> 28) & 1) == 0);
+  const bool smallk = (!split && cin == 32 && ksize == 3 && cout <= 64 && out_mode == 0 && !force_bn && !force_mt && !force_pair && ((flags >> 28) & 1) == 0);
   if (smallk) { bn = 64; mt = 1; pair = 0; streamk = 0; }
   YB_REQUIRE(bn == 64 || bn == 128 || bn == 256, "conv: BN=%d", bn);
   YB_REQUIRE(mt == 1 || mt == 2, "conv: MT=%d", mt);
@@ -1186,6 +1215,8 @@ int conv_igemm_forward(const void* x, const void* w, const float* scale, const f
   p.skip = (flags >> 24) & 0xF;
   p.streamk = streamk;
   p.stats = stats;
+  p.a_wrap = a_channels;
+  p.lo_off = lo_ch_off >= 0 ? static_cast<long long>(lo_ch_off - y_ch_off) : 0;
   p.sk_base = 0; p.sk_rem = 0; p.ws = nullptr; p.flags = nullptr;
   if (streamk) {
     const long long units = static_cast<long long>(p.m_tiles) * p.n_tiles * p.num_kb;
@@ -1201,7 +1232,7 @@ int conv_igemm_forward(const void* x, const void* w, const float* scale, const f
   CUresult cr;
   const int a_rows = (mt == 2 && !pair && !smallk) ? 2 * BM : BM;   // pixels per A box (ConvCfg::kMergedA)
   if (a_im2col) {
-    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(cin), static_cast<cuuint64_t>(width), static_cast<cuuint64_t>(height),
+    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(a_channels), static_cast<cuuint64_t>(width), static_cast<cuuint64_t>(height),
                                 static_cast<cuuint64_t>(batch)};
     const cuuint64_t strides[3] = {static_cast<cuuint64_t>(x_ld) * 2, static_cast<cuuint64_t>(x_ld) * 2 * width,
                                    static_cast<cuuint64_t>(x_ld) * 2 * width * height};
@@ -1219,7 +1250,7 @@ int conv_igemm_forward(const void* x, const void* w, const float* scale, const f
     const unsigned long long span_bytes = static_cast<unsigned long long>(x_ld) * 2ull * width * height * batch;
     if (drv <= 13010 && span_bytes < 131072ull) reinterpret_cast<uint64_t*>(&ta)[1] &= ~(1ull << 21);
   } else {
-    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cin), static_cast<cuuint64_t>(p.m_total)};
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(a_channels), static_cast<cuuint64_t>(p.m_total)};
     const cuuint64_t strides[1] = {static_cast<cuuint64_t>(x_ld) * 2};
     const cuuint32_t box[2] = {static_cast<cuuint32_t>(bk), static_cast<cuuint32_t>(a_rows)};
     const cuuint32_t estr[2] = {1, 1};

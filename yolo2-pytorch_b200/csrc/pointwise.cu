@@ -64,6 +64,35 @@ int pack_weight(const float* w, void* out, int cout, int cin, int k, int mode, i
   return check_launch("pack_weight_kernel");
 }
 
+// Split-precision B operand (strict mode, see ConvParams::a_wrap in conv_igemm.cu): out[co][tap][s*Cin + ci] for s in [0, segments),
+// segment s holding w_hi = fp16(w) or, where bit s of lo_mask is set, w_lo = fp16(w - fp32(w_hi)).  Same tiling as mode 0.
+__global__ void __launch_bounds__(128) pack_weight_split_kernel(const float* __restrict__ w, __half* __restrict__ out, int cin, int k, int segments,
+                                                                int lo_mask) {
+  __shared__ float tile[128 * 9 + 8];
+  const int k2 = k * k;
+  const int co = blockIdx.y, ci0 = blockIdx.x * 128, t = threadIdx.x;
+  const int nci = cin - ci0 < 128 ? cin - ci0 : 128;
+  const float* src = w + (static_cast<long long>(co) * cin + ci0) * k2;
+  for (int j = t; j < nci * k2; j += 128) tile[j] = src[j];
+  __syncthreads();
+  if (t < nci) {
+    const long long kw = static_cast<long long>(segments) * cin;
+    for (int tap = 0; tap < k2; ++tap) {
+      const float v = tile[t * k2 + tap];
+      const __half hi = __float2half_rn(v);
+      const __half lo = __float2half_rn(v - __half2float(hi));
+      for (int s = 0; s < segments; ++s)
+        out[(static_cast<long long>(co) * k2 + tap) * kw + static_cast<long long>(s) * cin + ci0 + t] = ((lo_mask >> s) & 1) ? lo : hi;
+    }
+  }
+}
+
+int pack_weight_split(const float* w, void* out, int cout, int cin, int k, int segments, int lo_mask, cudaStream_t stream) {
+  YB_REQUIRE(w && out && cout > 0 && cin > 0 && (k == 1 || k == 3) && segments >= 1 && segments <= 3, "pack_weight_split: bad argument");
+  pack_weight_split_kernel<<<dim3((cin + 127) / 128, cout), 128, 0, stream>>>(w, reinterpret_cast<__half*>(out), cin, k, segments, lo_mask);
+  return check_launch("pack_weight_split_kernel");
+}
+
 // ------------------------------------------------------------------------------------------
 __global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
                                const float* __restrict__ var, float eps, float* __restrict__ scale, float* __restrict__ shift, int c) {
@@ -120,6 +149,59 @@ int maxpool2x2(const void* x, void* y, int batch, int height, int width, int cha
   maxpool2x2_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
       reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(y), batch, height, width, channels, x_ld);
   return check_launch("maxpool2x2_kernel");
+}
+
+// nn.MaxPool2d(2) on split-precision activations (hi at channel c, lo at c + lo_off of the same pixel): the window element with the
+// largest hi + lo (fp32) wins and its (hi, lo) pair is copied, so the pooled value is exactly the maximum of the represented values.
+__global__ void maxpool2x2_split_kernel(const __half* __restrict__ x, __half* __restrict__ y, int batch, int height, int width, int channels,
+                                        int x_ld, int x_lo_off, int y_ld, int y_lo_off) {
+  const int c8 = channels >> 3;
+  const int oh = height >> 1, ow = width >> 1;
+  const long long total = static_cast<long long>(batch) * oh * ow * c8;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cg = static_cast<int>(idx % c8);
+  long long t = idx / c8;
+  const int px = static_cast<int>(t % ow); t /= ow;
+  const int py = static_cast<int>(t % oh);
+  const int img = static_cast<int>(t / oh);
+  const __half* p00 = x + ((static_cast<long long>(img) * height + 2 * py) * width + 2 * px) * x_ld + cg * 8;
+  const long long offs[4] = {0, x_ld, static_cast<long long>(width) * x_ld, static_cast<long long>(width) * x_ld + x_ld};
+  uint4 hi[4], lo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    hi[j] = __ldg(reinterpret_cast<const uint4*>(p00 + offs[j]));
+    lo[j] = __ldg(reinterpret_cast<const uint4*>(p00 + offs[j] + x_lo_off));
+  }
+  uint4 oh4, ol4;
+  __half* ph = reinterpret_cast<__half*>(&oh4);
+  __half* pl = reinterpret_cast<__half*>(&ol4);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    float best = -INFINITY;
+    __half bh = __float2half_rn(0.f), bl = bh;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __half h = reinterpret_cast<const __half*>(&hi[j])[e], l = reinterpret_cast<const __half*>(&lo[j])[e];
+      const float v = __half2float(h) + __half2float(l);
+      if (v > best) { best = v; bh = h; bl = l; }
+    }
+    ph[e] = bh; pl[e] = bl;
+  }
+  __half* dst = y + ((static_cast<long long>(img) * oh + py) * ow + px) * y_ld + cg * 8;
+  *reinterpret_cast<uint4*>(dst) = oh4;
+  *reinterpret_cast<uint4*>(dst + y_lo_off) = ol4;
+}
+
+int maxpool2x2_split(const void* x, void* y, int batch, int height, int width, int channels, int x_ld, int x_lo_off, int y_ld, int y_lo_off,
+                     cudaStream_t stream) {
+  YB_REQUIRE(x && y && batch > 0 && height % 2 == 0 && width % 2 == 0 && channels % 8 == 0 && x_ld % 8 == 0 && y_ld % 8 == 0 && x_lo_off % 8 == 0 &&
+                 y_lo_off % 8 == 0 && x_lo_off >= channels && y_lo_off >= channels && x_ld >= x_lo_off + channels && y_ld >= y_lo_off + channels,
+             "maxpool2x2_split: bad argument");
+  const long long total = static_cast<long long>(batch) * (height / 2) * (width / 2) * (channels / 8);
+  maxpool2x2_split_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(y), batch, height, width, channels, x_ld, x_lo_off, y_ld, y_lo_off);
+  return check_launch("maxpool2x2_split_kernel");
 }
 
 // ------------------------------------------------------------------------------------------

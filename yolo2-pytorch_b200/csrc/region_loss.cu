@@ -113,7 +113,14 @@ __global__ void __launch_bounds__(kLossThreads) region_main_kernel(const LossPar
     const float2 a = reinterpret_cast<const float2*>(p.gt_min)[static_cast<long long>(img) * p.num_gt + g];
     const float2 b = reinterpret_cast<const float2*>(p.gt_max)[static_cast<long long>(img) * p.num_gt + g];
     gt[g] = make_float4(a.x, a.y, b.x, b.y);
-    gcls[g] = static_cast<int>(p.gt_cls[static_cast<long long>(img) * p.num_gt + g]);
+    // single-class heads (A*5 channels, model.output_channels) carry no class targets: gt_cls may be NULL.  Ids outside
+    // [0, C) (corrupt labels) are clamped so the logit indexing below stays inside the feature map.
+    int cls_id = 0;
+    if (p.num_cls > 0 && p.gt_cls != nullptr) {
+      const long long raw = p.gt_cls[static_cast<long long>(img) * p.num_gt + g];
+      cls_id = raw < 0 ? 0 : (raw >= p.num_cls ? p.num_cls - 1 : static_cast<int>(raw));
+    }
+    gcls[g] = cls_id;
   }
   int npos = 0;
   for (int b = 0; b < p.batch; ++b) npos += p.pos_count[b];

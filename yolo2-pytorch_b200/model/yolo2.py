@@ -69,7 +69,7 @@ class Conv2d(nn.Module):
         """Stand-alone use of one unit on an fp32 NCHW tensor (tests, pruning tools).  Layout/dtype
         conversion at this boundary is plain data movement; the conv runs on the tcgen05 kernel."""
         if self.training and self.has_bn:
-            raise NotImplementedError('training-mode BatchNorm is not part of this build (SURVEY 8f/next)')
+            raise NotImplementedError('a stand-alone Conv2d unit runs in eval mode only; training goes through Darknet.forward (b200.train_engine)')
         if self._unit is None:
             self._unit = _engine.ConvUnit(self.conv, self.bn if self.has_bn else None, self.has_act)
         u = self._unit
@@ -155,6 +155,9 @@ class Darknet(nn.Module):
         self.init()
         self._engine = None
         self._trainer = None
+        # optional `[b200] precision = fast | strict` in the INI (not a reference key): see b200.engine.DarknetEngine.set_precision
+        cfg = config_channels.config
+        self._precision = cfg.get('b200', 'precision') if cfg.has_option('b200', 'precision') else None
 
     def init(self):
         """kaiming-normal conv weights, BN gamma = 1, beta = 0 (reference model/yolo2.py:117-123)."""
@@ -169,6 +172,8 @@ class Darknet(nn.Module):
     def engine(self):
         if self._engine is None:
             self._engine = _engine.DarknetEngine(self)
+            if self._precision is not None:
+                self._engine.set_precision(self._precision)
         return self._engine
 
     @property
@@ -188,7 +193,7 @@ class Darknet(nn.Module):
         if self.training:
             # batch-statistics BatchNorm + autograd through the explicit backward chain
             return _DarknetTrainFunction.apply(self, x, *[p for _, p in self.named_parameters()])
-        return self.engine.forward(x).clone()
+        return self.engine.forward(x).clone()     # the plan-owned buffer is overwritten by the next call; callers own what we return
 
     def scope(self, name):
         """'layers1.4.conv.weight' -> 'layers1.4' (reference model/yolo2.py:132-133)."""
