@@ -248,6 +248,24 @@ int yb_mb_conv0_bn_relu_fwd(const float* x_nchw, const float* w_oihw, const floa
 int yb_dwconv3x3_bn_relu_fwd(const void* x, const float* w_c9, const float* scale, const float* shift, void* y, int batch, int height,
                              int width, int channels, int stride, yb_stream_t stream);
 
+/* ---- data-parallel gradient exchange (replaces nn.DataParallel's replicate / gather / reduce_add_coalesced, train.py:65-71) ----
+ * One process per GPU.  The communicator is an NCCL communicator owned by this library (NCCL is bound with dlopen at the first
+ * call: the libnccl.so.2 already in the process -- PyTorch ships one -- else the system's, else $YB_NCCL_PATH).
+ *   yb_comm_unique_id   rank 0 creates the 128-byte rendezvous id; the caller ships it to the other ranks (any side channel);
+ *   yb_comm_init        collective over all ranks, with the current CUDA device bound to the calling process' GPU;
+ *   yb_allreduce_bucket in-place SUM over ranks of `count` elements of one gradient bucket, asynchronous on `stream` (the caller
+ *                       orders it after the kernels that fill the bucket with CUDA events; capturable into a CUDA graph).  The
+ *                       1/world of the average is folded into the gradient kernels' un-scaling (yb_unpack_wgrad `scale`, ...);
+ *   yb_broadcast_buffer root's buffer to every rank (initial parameters / buffers, as DataParallel replicates GPU 0's);
+ *   yb_comm_destroy     after every CUDA graph that captured a collective has been destroyed.
+ * dtype: 0 = float32, 1 = float16, 2 = bfloat16, 3 = int32. */
+int yb_comm_version(int* nccl_version);
+int yb_comm_unique_id(void* id128);
+int yb_comm_init(void** comm, int nranks, const void* id128, int rank);
+int yb_comm_destroy(void* comm);
+int yb_allreduce_bucket(void* comm, void* buf, long long count, int dtype, yb_stream_t stream);
+int yb_broadcast_buffer(void* comm, void* buf, long long count, int dtype, int root, yb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,6 +54,12 @@ SIGNATURES = {
     'yb_resize_batch_u8': [P, P, P, P, c_int, c_int, c_int, c_int, P, P, c_int, P],
     'yb_totensor_u8': [P, P, c_int, c_int, c_int, P],
     'yb_eval_match': [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_float, c_float, P, P],
+    'yb_comm_version': [ctypes.POINTER(c_int)],
+    'yb_comm_unique_id': [P],
+    'yb_comm_init': [ctypes.POINTER(P), c_int, P, c_int],
+    'yb_comm_destroy': [P],
+    'yb_allreduce_bucket': [P, P, c_longlong, c_int, P],
+    'yb_broadcast_buffer': [P, P, c_longlong, c_int, c_int, P],
     'yb_mb_conv0_bn_relu_fwd': [P, P, P, P, P, c_int, c_int, c_int, P],
     'yb_dwconv3x3_bn_relu_fwd': [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P],
 }

@@ -17,6 +17,7 @@ import os
 
 import torch
 
+from . import ddp as _ddp
 from . import ops
 
 SLOPE = 0.1
@@ -40,7 +41,12 @@ class DarknetTrainer(object):
         self.grad_scale = float(grad_scale)
         self.sums = {}       # per-unit double[2C] accumulators (self-cleaning)
         self.wd_cache = {}   # dgrad weight buffers per unit (contents re-packed every step)
-        self.on_grad = None  # optional callback(name, grad) fired as soon as a parameter gradient is enqueued (DDP overlap)
+        # data parallel: b200.ddp.GradientAllReducer attached by train.iterate; every gradient kernel writes into the reducer-visible
+        # arena and reports it (`_emit`) so the bucket's all-reduce starts while the rest of the backward chain is still running
+        self.reducer = None
+        self.arena = None
+        self._arena_key = None
+        self._main = None
         # BN batch statistics in the conv epilogue (yb_conv_bn_act_stats_fwd) instead of yb_bn_stats; YB_FUSE_STATS=0 for A/B runs
         self.fuse_stats = os.environ.get('YB_FUSE_STATS', '1') != '0'
         self._fused_stats = False
@@ -51,8 +57,39 @@ class DarknetTrainer(object):
 
     # ---- helpers -------------------------------------------------------------------------------------
     def _emit(self, name, grads):
-        if self.on_grad is not None:
-            self.on_grad(name, grads[name])
+        if self.reducer is not None:
+            dev = grads[name].device
+            side = self._side_streams.get(dev) if self._side_busy else None
+            self.reducer.on_grad(name, grads[name], streams=(self._main, side))
+
+    def grad_order(self):
+        """State-dict names of all parameters in the order the backward chain produces their gradients."""
+        eng = self.engine
+        names = ['layers3.1.conv.bias', 'layers3.1.conv.weight']
+        for key in ['layers3.0'] + list(reversed(eng._k2)) + ['passthrough'] + list(reversed(eng._k1)):
+            names += [key + '.bn.weight', key + '.bn.bias', key + '.conv.weight']
+        return names
+
+    def _ensure_arena(self, dnn, device):
+        """Persistent flat fp32 gradient buffer (b200.ddp.GradArena): gradient kernels write straight into their slots, `.grad`
+        of every parameter is a view of it, buckets of it are all-reduced in place."""
+        params = dict(dnn.named_parameters())
+        key = (str(device), tuple((n, tuple(p.shape)) for n, p in params.items()), id(self.reducer))
+        if self.arena is None or self._arena_key != key:
+            order = [n for n in self.grad_order() if n in params]
+            if set(order) != set(params):
+                raise RuntimeError('Darknet trainer: unexpected parameter set %s' % sorted(set(params) ^ set(order))[:4])
+            bucket_bytes = self.reducer.bucket_bytes if self.reducer is not None else (32 << 20)
+            self.arena = _ddp.GradArena([(n, tuple(params[n].shape)) for n in order], device, bucket_bytes)
+            self._arena_key = key
+            if self.reducer is not None:
+                self.reducer.attach(self.arena)
+        return self.arena
+
+    @property
+    def _unscale(self):
+        """Inverse loss scale, with the 1 / world of the data-parallel gradient average folded in."""
+        return 1.0 / (self.grad_scale * (self.reducer.grad_divisor if self.reducer is not None else 1.0))
 
     def _sums(self, key, channels, device):
         t = self.sums.get(key)
@@ -210,8 +247,8 @@ class DarknetTrainer(object):
         with torch.cuda.stream(side) if side is not None else _NullCtx():
             dw_krsc = torch.empty(cout, k, k, cin, dtype=torch.float32, device=dev)
             ops.call('yb_conv_wgrad', ain, dz, dw_krsc, b, hh, ww, cin, cout, k, ain.shape[-1], dz.shape[-1])
-            dw = torch.empty(cout, cin, k, k, dtype=torch.float32, device=dev)
-            ops.call('yb_unpack_wgrad', dw_krsc, dw, cout, cin, k, 1.0 / self.grad_scale)      # layout change + inverse loss scale
+            dw = self.arena.views[name + '.conv.weight']                                  # [cout, cin, k, k] slot of the gradient arena
+            ops.call('yb_unpack_wgrad', dw_krsc, dw, cout, cin, k, self._unscale)            # layout change + inverse loss scale (/ world)
             grads[name + '.conv.weight'] = dw
             self._emit(name + '.conv.weight', grads)
 
@@ -243,11 +280,11 @@ class DarknetTrainer(object):
         args = (s.z, s.z.shape[-1], s.mean, s.invstd, bnw, bnb, SLOPE, da, 0 if da is None else da.shape[-1], da_off, dap,
                 0 if dap is None else dap.shape[-1], dap_off, b, s.h, s.w, c, window, sums)
         ops.call('yb_bn_act_bwd', 0, *args, None, 0, 1)
-        dgamma = torch.empty(c, dtype=torch.float32, device=dev)
-        dbeta = torch.empty(c, dtype=torch.float32, device=dev)
+        dgamma = self.arena.views[key + '.bn.weight']
+        dbeta = self.arena.views[key + '.bn.bias']
         dz = torch.empty(b, s.h, s.w, c, dtype=torch.float16, device=dev)
         ops.call('yb_bn_act_bwd', 1, *args, dz, c, 1)
-        ops.call('yb_bn_param_grad', sums, c, dgamma, dbeta, 1, 1.0 / self.grad_scale)     # un-scales, then clears the accumulators
+        ops.call('yb_bn_param_grad', sums, c, dgamma, dbeta, 1, self._unscale)     # un-scales (/ world), then clears the accumulators
         grads[key + '.bn.weight'] = dgamma
         grads[key + '.bn.bias'] = dbeta
         self._emit(key + '.bn.weight', grads)
@@ -260,22 +297,25 @@ class DarknetTrainer(object):
         one, zero = self._ones(u.cin, dev)
         return ops.conv_bn_act(dz, self._wd(key, u), one, zero, 1.0)
 
-    def backward(self, saved, dfeature):
-        """dfeature: fp32 NCHW gradient of the loss w.r.t. the head output.  Returns {state_dict key: fp32 grad}."""
+    def backward(self, saved, dfeature, dnn=None):
+        """dfeature: fp32 NCHW gradient of the loss w.r.t. the head output.  Returns {state_dict key: fp32 grad}: views of the
+        persistent gradient arena, already averaged over the data-parallel ranks when a reducer is attached."""
         eng = self.engine
         b = saved.b
         grads = {}
         dev = dfeature.device
+        self._ensure_arena(dnn if dnn is not None else self._dnn, dev)
+        self._main = torch.cuda.current_stream(dev)
         u30, u31 = eng.units3
         h32, w32 = saved.h32, saved.w32
         chead = u31.cout
         cpad = (chead + 31) // 32 * 32
         # head: bias gradient from the unscaled fp32 gradient, dz scaled into fp16
         dzh = torch.empty(b, h32, w32, cpad, dtype=torch.float16, device=dev)
-        dbias = torch.empty(chead, dtype=torch.float32, device=dev)
+        dbias = self.arena.views['layers3.1.conv.bias']
         scaled = (dfeature.contiguous().float() * self.grad_scale)
         ops.call('yb_head_grad_prepare', scaled, dzh, dbias, b, chead, cpad, h32 * w32)
-        grads['layers3.1.conv.bias'] = dbias.mul_(1.0 / self.grad_scale)
+        grads['layers3.1.conv.bias'] = dbias.mul_(self._unscale)
         self._emit('layers3.1.conv.bias', grads)
         self._wgrad(u31, saved.a30, dzh, b, h32, w32, grads, 'layers3.1', cout=chead)
         one, zero = self._ones(u31.cin, dev)
@@ -305,9 +345,11 @@ class DarknetTrainer(object):
         # layers1.0: weight gradient straight from the fp32 image
         s0 = saved.units['layers1.0']
         dz0 = self._unit_backward('layers1.0', s0, b, grads, da=g_da, dap=g_dap)
-        dw0 = torch.empty_like(eng.units1[0].conv.weight, dtype=torch.float32)
+        dw0 = self.arena.views['layers1.0.conv.weight']
         ops.call('yb_conv0_wgrad', saved.x, dz0, dw0, b, saved.h, saved.w)
-        grads['layers1.0.conv.weight'] = dw0.mul_(1.0 / self.grad_scale)
+        grads['layers1.0.conv.weight'] = dw0.mul_(self._unscale)
         self._emit('layers1.0.conv.weight', grads)
         self._join(dev)
+        if self.reducer is not None:
+            self.reducer.finish()          # main stream waits for every bucket's all-reduce (no host wait)
         return grads

@@ -99,6 +99,12 @@ int eval_match(const float*, const float*, const int*, const int*, const float*,
                unsigned char*, cudaStream_t);
 int unpack_wgrad(const float*, float*, int, int, int, float, cudaStream_t);
 int conv_wgrad_forward(const void*, const void*, float*, int, int, int, int, int, int, int, int, cudaStream_t);
+int comm_version(int*);
+int comm_unique_id(void*);
+int comm_init(void**, int, const void*, int);
+int comm_destroy(void*);
+int allreduce_bucket(void*, void*, long long, int, cudaStream_t);
+int broadcast_buffer(void*, void*, long long, int, int, cudaStream_t);
 int mb_conv0(const float*, const float*, const float*, const float*, void*, int, int, int, cudaStream_t);
 int dwconv3x3(const void*, const float*, const float*, const float*, void*, int, int, int, int, int, cudaStream_t);
 
@@ -321,6 +327,22 @@ int yb_mb_conv0_bn_relu_fwd(const float* x_nchw, const float* w_oihw, const floa
 int yb_dwconv3x3_bn_relu_fwd(const void* x, const float* w_c9, const float* scale, const float* shift, void* y, int batch, int height,
                              int width, int channels, int stride, yb_stream_t stream) {
   return yb::dwconv3x3(x, w_c9, scale, shift, y, batch, height, width, channels, stride, S(stream));
+}
+
+int yb_comm_version(int* nccl_version) { return yb::comm_version(nccl_version); }
+
+int yb_comm_unique_id(void* id128) { return yb::comm_unique_id(id128); }
+
+int yb_comm_init(void** comm, int nranks, const void* id128, int rank) { return yb::comm_init(comm, nranks, id128, rank); }
+
+int yb_comm_destroy(void* comm) { return yb::comm_destroy(comm); }
+
+int yb_allreduce_bucket(void* comm, void* buf, long long count, int dtype, yb_stream_t stream) {
+  return yb::allreduce_bucket(comm, buf, count, dtype, S(stream));
+}
+
+int yb_broadcast_buffer(void* comm, void* buf, long long count, int dtype, int root, yb_stream_t stream) {
+  return yb::broadcast_buffer(comm, buf, count, dtype, root, S(stream));
 }
 
 }  // extern "C"

@@ -93,13 +93,17 @@ class _DarknetTrainFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dfeature):
-        grads = ctx.dnn.trainer.backward(ctx.saved, dfeature)
+        dnn = ctx.dnn
+        grads = dnn.trainer.backward(ctx.saved, dfeature, dnn)
         ctx.saved = None
-        out = []
-        for name, p in ctx.dnn.named_parameters():
-            g = grads.get(name)
-            out.append(g.view_as(p) if g is not None else None)
-        return (None, None) + tuple(out)
+        # The gradients live in the trainer's persistent arena (b200.ddp.GradArena; in data-parallel runs its buckets are being
+        # all-reduced in place right now).  `.grad` is bound to those views directly -- handing them to autograd instead would let
+        # AccumulateGrad clone them whenever it cannot steal the tensor, silently detaching `.grad` from the reduced buffer.
+        # Like the reference (zero_grad before every backward, train.py:350), gradients are not accumulated across calls.
+        params = list(dnn.named_parameters())
+        for name, p in params:
+            p.grad = grads[name]
+        return (None, None) + (None,) * len(params)
 
 
 class Darknet(nn.Module):

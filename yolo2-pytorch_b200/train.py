@@ -30,11 +30,24 @@ def norm_data(data, height, width, rows, cols, keys='yx_min, yx_max'):
 
 
 def ensure_model(module):
-    """reference train.py:65-71: move to the GPU.  Replication is per process here, so nothing is wrapped; the
-    gradient exchange is attached by `iterate` when torch.distributed is initialised."""
+    """reference train.py:65-71: move to the GPU; with more than one GPU the reference wraps the module in nn.DataParallel,
+    which re-replicates GPU 0's parameters and buffers on every step.  Here replication is one process per GPU
+    (torch.distributed): nothing is wrapped, every rank's parameters and buffers are made equal to rank 0's once, and the
+    gradient exchange (b200.ddp) is attached by `iterate`."""
     if not torch.cuda.is_available():
         raise RuntimeError('train (B200): a CUDA device is required; there is no CPU fallback')
-    return module.cuda()
+    module = module.cuda()
+    reducer = _ddp.default_reducer()
+    if reducer is not None:
+        sync_replicas(module, reducer)
+    return module
+
+
+def sync_replicas(module, reducer):
+    """Broadcast rank 0's parameters and buffers (once per module per reducer)."""
+    if getattr(module, '_yb_synced_with', None) is not reducer:
+        reducer.broadcast_module(module)
+        module._yb_synced_with = reducer
 
 
 def build_optimizer(config, params, lr):
@@ -53,9 +66,13 @@ def iterate(inference, optimizer, anchors, config, data, reducer=None):
         tensor = transform.to_tensor(tensor)
     height, width = tensor.shape[-2:]
     dnn = inference.dnn
-    if reducer is None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        reducer = _ddp.GradientAllReducer()
-    dnn.trainer.on_grad = reducer.on_grad if reducer is not None else None
+    if reducer is None:
+        reducer = _ddp.default_reducer()          # torch.distributed initialised with world > 1: data parallel
+    elif _ddp.default_reducer(create=False) is None:
+        _ddp.set_default_reducer(reducer)          # model.loss normalises the class term through the same communicator
+    if reducer is not None:
+        sync_replicas(inference, reducer)          # unseeded ranks would otherwise train different models on averaged gradients
+    dnn.trainer.reducer = reducer
     pred = model._inference(inference, tensor)
     rows, cols = pred['feature'].shape[-2:]
     cross_entropy = config.getboolean('train', 'cross_entropy') if config.has_option('train', 'cross_entropy') else True
@@ -63,9 +80,7 @@ def iterate(inference, optimizer, anchors, config, data, reducer=None):
     loss_hparam = {key: loss[key] * config.getfloat('hparam', key) for key in loss}
     loss_total = sum(loss_hparam.values())
     optimizer.zero_grad()
-    loss_total.backward()
-    if reducer is not None:
-        reducer.finish()
+    loss_total.backward()          # ends with the main stream joined to the gradient all-reduces (b200.train_engine.backward)
     try:
         clip = config.getfloat('train', 'clip')
         nn.utils.clip_grad_norm_(inference.parameters(), clip)
