@@ -398,7 +398,8 @@ def test_conv_split_precision_vs_oracle(ops, case):
     full = (got_hi + got_lo).permute(0, 3, 1, 2)
     err = rel_err(full, ref)
     assert err <= 2e-5, 'hi + lo rel err %.3e' % err
-    assert torch.equal(got_hi.permute(0, 3, 1, 2).half(), full.half()), 'hi is not the fp16 rounding of hi + lo'
+    # hi is the fp16 rounding of the result: the residual is at most half an ulp of hi (2^-11 relative; 2^-25 absolute below the normal range)
+    assert bool((got_lo.abs() <= got_hi.abs() * 2.0 ** -11 * 1.001 + 2.0 ** -25).all()), 'lo exceeds half an ulp of hi'
     # fp32 NCHW output of the same operands (the head's mode)
     y32 = torch.empty(b, cout, h, w, dtype=torch.float32, device=DEV)
     ops.conv_bn_act_split(src, w16, scale, shift, 0.1, y32, a_channels=cin * (2 if split_a else 1), out_mode=ops.OUT_F32_NCHW)

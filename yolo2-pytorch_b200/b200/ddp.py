@@ -249,11 +249,27 @@ class GradientAllReducer(object):
 
 
 _DEFAULT = None
+_LOCAL_ONLY = 0
+
+
+class local_only(object):
+    """Context: this rank steps on its own shard with no collective at all (compute-only timing of a data-parallel step)."""
+
+    def __enter__(self):
+        global _LOCAL_ONLY
+        _LOCAL_ONLY += 1
+
+    def __exit__(self, *exc):
+        global _LOCAL_ONLY
+        _LOCAL_ONLY -= 1
+        return False
 
 
 def default_reducer(create=True):
     """Process-wide reducer used by `train.iterate` / `model.loss` when torch.distributed is initialised with world > 1."""
     global _DEFAULT
+    if _LOCAL_ONLY:
+        return None
     if _DEFAULT is None and create and _dist_ready() and dist.get_world_size() > 1:
         _DEFAULT = GradientAllReducer()
     return _DEFAULT
@@ -284,7 +300,7 @@ def global_mean_factor(local_count, process_group=None):
     `local_count`: 0-dim tensor.  CUDA tensors use the library communicator of the default reducer (capturable);
     CPU tensors torch.distributed (gloo).  Returns a float32 0-dim tensor."""
     n = local_count.detach().to(torch.float32).reshape(())
-    if not _dist_ready() or dist.get_world_size(process_group) == 1:
+    if _LOCAL_ONLY or not _dist_ready() or dist.get_world_size(process_group) == 1:
         return torch.ones_like(n)
     total = n.clone()
     if n.is_cuda:

@@ -45,7 +45,7 @@ class DarknetTrainer(object):
         # arena and reports it (`_emit`) so the bucket's all-reduce starts while the rest of the backward chain is still running
         self.reducer = None
         self.arena = None
-        self._arena_key = None
+        self._arenas = {}      # one per (device, parameter set, reducer): CUDA graphs keep writing the arena they were captured with
         self._main = None
         # BN batch statistics in the conv epilogue (yb_conv_bn_act_stats_fwd) instead of yb_bn_stats; YB_FUSE_STATS=0 for A/B runs
         self.fuse_stats = os.environ.get('YB_FUSE_STATS', '1') != '0'
@@ -75,13 +75,13 @@ class DarknetTrainer(object):
         of every parameter is a view of it, buckets of it are all-reduced in place."""
         params = dict(dnn.named_parameters())
         key = (str(device), tuple((n, tuple(p.shape)) for n, p in params.items()), id(self.reducer))
-        if self.arena is None or self._arena_key != key:
+        self.arena = self._arenas.get(key)
+        if self.arena is None:
             order = [n for n in self.grad_order() if n in params]
             if set(order) != set(params):
                 raise RuntimeError('Darknet trainer: unexpected parameter set %s' % sorted(set(params) ^ set(order))[:4])
             bucket_bytes = self.reducer.bucket_bytes if self.reducer is not None else (32 << 20)
-            self.arena = _ddp.GradArena([(n, tuple(params[n].shape)) for n in order], device, bucket_bytes)
-            self._arena_key = key
+            self.arena = self._arenas[key] = _ddp.GradArena([(n, tuple(params[n].shape)) for n in order], device, bucket_bytes)
             if self.reducer is not None:
                 self.reducer.attach(self.arena)
         return self.arena

@@ -66,6 +66,9 @@ def iterate(inference, optimizer, anchors, config, data, reducer=None):
         tensor = transform.to_tensor(tensor)
     height, width = tensor.shape[-2:]
     dnn = inference.dnn
+    if reducer is False:                           # this rank alone, no collective (compute-only timing of a data-parallel step)
+        with _ddp.local_only():
+            return iterate(inference, optimizer, anchors, config, data, None)
     if reducer is None:
         reducer = _ddp.default_reducer()          # torch.distributed initialised with world > 1: data parallel
     elif _ddp.default_reducer(create=False) is None:
@@ -145,6 +148,9 @@ class GraphedStep(object):
         from b200 import ops as _ops
         static = {k: data[k].to(dev).clone() for k in self.keys}
         self.anchors = self.anchors.detach().to(device=dev, dtype=torch.float32).contiguous()   # no host->device copy inside the capture
+        red = None if self.reducer is False else (self.reducer if self.reducer is not None else _ddp.default_reducer())
+        if red is not None:
+            sync_replicas(self.inference, red)      # before the snapshot: the restore below must not undo rank 0's broadcast
         snap = self._snapshot()
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
@@ -179,3 +185,8 @@ class GraphedStep(object):
     def finish(self):
         """Drop operand caches that the graph kept current on its own buffers (see the class docstring)."""
         self.inference.dnn.engine.invalidate()
+
+    def close(self):
+        """Destroy the captured graphs (required before the NCCL communicator whose collectives they captured is destroyed)."""
+        self.finish()
+        self.graphs.clear()
