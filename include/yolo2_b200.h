@@ -219,6 +219,11 @@ int yb_conv_wgrad(const void* x, const void* dz, float* dw_krsc, int batch, int 
 /* fp32 [Cout][k][k][Cin] (yb_conv_wgrad's layout) -> the reference's OIHW parameter-gradient layout, multiplied by `scale`. */
 int yb_unpack_wgrad(const float* dw_krsc, float* dw_oihw, int cout, int cin, int ksize, float scale, yb_stream_t stream);
 
+/* Guard of the fp16 / static-loss-scale backward (the reference trains in fp32 and has no such failure mode): found_inf[0] (device
+ * float) = 1 if any of the `count` fp32 gradient values is inf / NaN, else 0; with zero_if_found the whole buffer is cleared in that case
+ * so the optimizer takes a null step instead of absorbing the overflow into its state.  Asynchronous, no host sync, capturable. */
+int yb_grad_guard(float* grads, long long count, float* found_inf, int zero_if_found, yb_stream_t stream);
+
 /* ---- GPU input pipeline (transform/resize/image.py:23-24, transform/resize/label.py:25-31, transform/image.py:27-29) ----
  * A batch of decoded uint8 HWC frames of DIFFERENT sizes -> [B,height,width,3] uint8 in one launch: cv2.resize(image, (width, height))
  * (8-bit INTER_LINEAR, bit-exact) + optional BGR->RGB swap.  src = packed frames, image i starts at byte src_off[i] and is

@@ -67,6 +67,21 @@ def make_config(fix):
     return config
 
 
+def box_indices(all_yx_min, all_yx_max, det_yx_min, det_yx_max):
+    """Index (among the image's predictions) of every detection the reference returned: postprocess copies box rows, so the rows are
+    bit-identical to exactly one prediction."""
+    table = {}
+    a, b = all_yx_min.numpy(), all_yx_max.numpy()
+    for i in range(a.shape[0]):
+        table.setdefault(a[i].tobytes() + b[i].tobytes(), []).append(i)
+    out = []
+    for lo, hi in zip(det_yx_min.numpy(), det_yx_max.numpy()):
+        hit = table[lo.tobytes() + hi.tobytes()]
+        assert len(hit) == 1, 'ambiguous box'
+        out.append(hit[0])
+    return np.array(out, dtype=np.int64)
+
+
 def build_ref_darknet(model, sd):
     config = make_config(1)
     anchors = O.anchors_yolo_voc()

@@ -42,6 +42,7 @@ def main():
     if res is not None:
         for name, t in zip(('iou', 'yx_min', 'yx_max', 'cls', 'score'), res):
             out['det_' + name] = t.numpy()
+        out['det_box'] = G.box_indices(yx_min, yx_max, res[1], res[2])     # which of the 845 predictions each detection is a copy of
     path = os.path.join(HERE, 'c1_image.npz')
     np.savez_compressed(path, **out)
     print('c1_image.npz %.1f KB, detections: %s' % (os.path.getsize(path) / 1024, None if res is None else len(res[3])))

@@ -4,7 +4,7 @@ reference's own modules on CPU: model.yolo2.Darknet (eval) -> model.Inference ->
 32-image synthetic batch (oracle generator, seed 32; weights: the oracle's deterministic state_dict).
 
 Stored: the head feature of images 0, 15 and 31 in full, max|feature| of every image, and for every image the detections the reference
-returns (boxes, classes, scores, objectness of the kept boxes) as ragged arrays -- the GPU test computes the whole batch and compares.
+returns (boxes, classes, scores, objectness of the kept boxes, and for every detection the index of the box among the image's 845 predictions it is a copy of) as ragged arrays -- the GPU test computes the whole batch and compares.
 
     python tests/golden/make_golden_c2.py          # build container only (needs /root/reference)
 """
@@ -32,7 +32,7 @@ def main():
     inference = model.Inference(config, dnn, anchors)
     inference.eval()
     out = dict(images=np.array(KEEP), batch=np.array(BATCH), seed=np.array(SEED))
-    det = dict(iou=[], yx_min=[], yx_max=[], cls=[], score=[])
+    det = dict(iou=[], yx_min=[], yx_max=[], cls=[], score=[], box=[])
     n_keep, n_det = [], []
     with torch.no_grad():
         pred = model._inference(inference, x)
@@ -47,6 +47,7 @@ def main():
             n_keep.append(len(res[0])); n_det.append(len(res[3]))
             for name, t in zip(('iou', 'yx_min', 'yx_max', 'cls', 'score'), res):
                 det[name].append(t.numpy())
+            det['box'].append(G.box_indices(yx_min, yx_max, res[1], res[2]))
     feature = pred['feature'].numpy()
     out['feature'] = feature[list(KEEP)]
     out['feature_absmax'] = np.abs(feature).reshape(BATCH, -1).max(1)

@@ -298,3 +298,19 @@ def test_header_is_plain_c(tmp_path):
     gxx = shutil.which('g++')
     if gxx is not None:
         subprocess.run([gxx, '-std=c++11', '-fsyntax-only', '-x', 'c++', '-I', inc, str(src)], check=True)
+
+
+def test_save_darknet_weights_accepts_partial_header(tmp_path):
+    """`{'seen': N}` (the natural way to carry the image counter over) must not collide with the defaults."""
+    import struct
+    from utils import darknet_weights as dw
+    sd = {'layers.0.conv.weight': torch.randn(8, 3, 3, 3), 'layers.0.bn.weight': torch.rand(8), 'layers.0.bn.bias': torch.randn(8),
+          'layers.0.bn.running_mean': torch.randn(8), 'layers.0.bn.running_var': torch.rand(8) + 0.5,
+          'layers.1.conv.weight': torch.randn(10, 8, 1, 1), 'layers.1.conv.bias': torch.randn(10)}
+    path = str(tmp_path / 'x.weights')
+    dw.save_darknet_weights(path, sd, 2, header={'seen': 12345})
+    assert struct.unpack('<4i', open(path, 'rb').read(16)) == (0, 1, 0, 12345)
+    dw.save_darknet_weights(path, sd, 2)
+    assert struct.unpack('<4i', open(path, 'rb').read(16)) == (0, 1, 0, 0)
+    dw.save_darknet_weights(path, sd, 2, header=dict(major=0, minor=2, revision=0, seen=7))
+    assert struct.unpack('<4i', open(path, 'rb').read(16)) == (0, 2, 0, 7)

@@ -51,6 +51,7 @@ SIGNATURES = {
     'yb_conv0_wgrad': [P, P, P, c_int, c_int, c_int, P],
     'yb_conv_wgrad': [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P],
     'yb_unpack_wgrad': [P, P, c_int, c_int, c_int, c_float, P],
+    'yb_grad_guard': [P, c_longlong, P, c_int, P],
     'yb_resize_batch_u8': [P, P, P, P, c_int, c_int, c_int, c_int, P, P, c_int, P],
     'yb_totensor_u8': [P, P, c_int, c_int, c_int, P],
     'yb_eval_match': [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_float, c_float, P, P],

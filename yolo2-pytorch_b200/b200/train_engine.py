@@ -45,6 +45,7 @@ class DarknetTrainer(object):
         # arena and reports it (`_emit`) so the bucket's all-reduce starts while the rest of the backward chain is still running
         self.reducer = None
         self.arena = None
+        self.found_inf = None  # device float[1]: 1 when the last backward produced a non-finite gradient (then zeroed), see backward()
         self._arenas = {}      # one per (device, parameter set, reducer): CUDA graphs keep writing the arena they were captured with
         self._main = None
         # BN batch statistics in the conv epilogue (yb_conv_bn_act_stats_fwd) instead of yb_bn_stats; YB_FUSE_STATS=0 for A/B runs
@@ -352,4 +353,9 @@ class DarknetTrainer(object):
         self._join(dev)
         if self.reducer is not None:
             self.reducer.finish()          # main stream waits for every bucket's all-reduce (no host wait)
+        # fp16 gradient overflow guard (after the exchange, so every rank takes the same decision): `found_inf` is raised and the
+        # gradients are zeroed instead of poisoning the optimizer state; train.iterate hands the flag to optimizers that can skip
+        if self.found_inf is None or self.found_inf.device != dev:
+            self.found_inf = torch.zeros((), dtype=torch.float32, device=dev)      # 0-dim like GradScaler's (fused optimizers subtract it from their step counters)
+        ops.call('yb_grad_guard', self.arena.flat, self.arena.flat.numel(), self.found_inf, 1)
         return grads

@@ -98,6 +98,7 @@ int totensor_u8(const void*, float*, int, int, int, cudaStream_t);
 int eval_match(const float*, const float*, const int*, const int*, const float*, const float*, const int*, const int*, int, int, int, float, float,
                unsigned char*, cudaStream_t);
 int unpack_wgrad(const float*, float*, int, int, int, float, cudaStream_t);
+int grad_guard(float*, long long, float*, int, cudaStream_t);
 int conv_wgrad_forward(const void*, const void*, float*, int, int, int, int, int, int, int, int, cudaStream_t);
 int comm_version(int*);
 int comm_unique_id(void*);
@@ -301,6 +302,10 @@ int yb_conv_wgrad(const void* x, const void* dz, float* dw_krsc, int batch, int 
 
 int yb_unpack_wgrad(const float* dw_krsc, float* dw_oihw, int cout, int cin, int ksize, float scale, yb_stream_t stream) {
   return yb::unpack_wgrad(dw_krsc, dw_oihw, cout, cin, ksize, scale, S(stream));
+}
+
+int yb_grad_guard(float* grads, long long count, float* found_inf, int zero_if_found, yb_stream_t stream) {
+  return yb::grad_guard(grads, count, found_inf, zero_if_found, S(stream));
 }
 
 int yb_resize_batch_u8(const void* src, const long long* src_off, const int* src_hw, void* dst, int batch, int height, int width, int swap_rb,

@@ -715,6 +715,48 @@ __global__ void __launch_bounds__(128) unpack_wgrad_kernel(const float* __restri
   for (int j = t; j < nci * k2; j += 128) dst[j] = tile[j % k2][j / k2] * scale;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Gradient guard.  Activation gradients travel in fp16 under a static loss scale; an overflow there (huge hparams, a tiny
+// running_var) would write inf / NaN into the parameter gradients and poison the optimizer state for good.  Pass 1 raises
+// found[0] (float, zeroed here first) if any of the `count` fp32 values is not finite; pass 2 (zero_if_found) clears the
+// whole buffer in that case, so a plain optimizer takes a null step.  Optimizers that understand `found_inf` (torch's fused
+// Adam / SGD) can skip the step outright from the same flag.  No host synchronisation; capturable.
+__global__ void grad_guard_detect_kernel(const float4* __restrict__ buf, long long count4, const float* __restrict__ tail, int ntail,
+                                         float* __restrict__ found) {
+  bool bad = false;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < count4; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 v = __ldg(buf + i);
+    // x - x is 0 for finite x and NaN for inf / NaN
+    const float t = (v.x - v.x) + (v.y - v.y) + (v.z - v.z) + (v.w - v.w);
+    bad = bad || !(t == 0.f);
+  }
+  if (blockIdx.x == 0 && static_cast<int>(threadIdx.x) < ntail) {
+    const float x = tail[threadIdx.x];
+    bad = bad || !((x - x) == 0.f);
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) *found = 1.f;
+}
+
+__global__ void grad_guard_zero_kernel(float4* __restrict__ buf, long long count4, float* __restrict__ tail, int ntail, const float* __restrict__ found) {
+  if (*found == 0.f) return;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < count4; i += static_cast<long long>(gridDim.x) * blockDim.x)
+    buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (blockIdx.x == 0 && static_cast<int>(threadIdx.x) < ntail) tail[threadIdx.x] = 0.f;
+}
+
+int grad_guard(float* buf, long long count, float* found, int zero_if_found, cudaStream_t stream) {
+  YB_REQUIRE(buf && found && count > 0 && (reinterpret_cast<uintptr_t>(buf) & 15) == 0, "grad_guard: bad argument (16 B aligned buffer)");
+  YB_CUDA(cudaMemsetAsync(found, 0, sizeof(float), stream));
+  const long long count4 = count / 4;
+  const int ntail = static_cast<int>(count - count4 * 4);
+  const int grid = sm_count() * 8;
+  grad_guard_detect_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(buf), count4, buf + count4 * 4, ntail, found);
+  int rc = check_launch("grad_guard_detect_kernel");
+  if (rc || !zero_if_found) return rc;
+  grad_guard_zero_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<float4*>(buf), count4, buf + count4 * 4, ntail, found);
+  return check_launch("grad_guard_zero_kernel");
+}
+
 int unpack_wgrad(const float* g_krsc, float* out_oihw, int cout, int cin, int k, float scale, cudaStream_t stream) {
   YB_REQUIRE(g_krsc && out_oihw && cout > 0 && cin > 0 && (k == 1 || k == 3), "unpack_wgrad: bad argument");
   unpack_wgrad_kernel<<<dim3((cin + 127) / 128, cout), 128, 0, stream>>>(g_krsc, out_oihw, cout, cin, k, scale);

@@ -89,6 +89,11 @@ def iterate(inference, optimizer, anchors, config, data, reducer=None):
         nn.utils.clip_grad_norm_(inference.parameters(), clip)
     except (configparser.NoOptionError, configparser.NoSectionError):
         pass
+    if getattr(optimizer, '_step_supports_amp_scaling', False):
+        # fused torch.optim optimizers skip the update (state untouched) when found_inf is raised -- the overflow guard of the fp16
+        # backward (b200.train_engine.backward); the others step on the zeroed gradients
+        optimizer.found_inf = dnn.trainer.found_inf
+        optimizer.grad_scale = None
     optimizer.step()
     return dict(height=height, width=width, rows=rows, cols=cols, data=data, pred=pred, debug=debug, loss_total=loss_total, loss=loss,
                 loss_hparam=loss_hparam)

@@ -97,7 +97,9 @@ def load_darknet_weights(path, template_state_dict, num_anchors):
 
 def save_darknet_weights(path, state_dict, num_anchors, header=None):
     """Inverse of `load_darknet_weights`: write `state_dict` (ours) as a Darknet `.weights` file."""
-    header = dict(major=0, minor=1, revision=0, seen=0, **(header or {})) if header is None or 'major' not in header else header
+    hdr = dict(major=0, minor=1, revision=0, seen=0)
+    hdr.update(header or {})          # partial headers (e.g. {'seen': N}) keep the defaults for the rest
+    header = hdr
     units = _units({k: v for k, v in state_dict.items() if not k.endswith('num_batches_tracked')})
     names = list(units)
     with open(path, 'wb') as f:
