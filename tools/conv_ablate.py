@@ -17,12 +17,17 @@ CASES = [  # h, cin, cout, k, bn, mt, pair  (bn 0 = no forcing: the small-K kern
     (26, 256, 512, 3, 256, 1, 1), (104, 64, 128, 3, 128, 2, 1), (208, 32, 64, 3, 64, 2, 1),
     (26, 512, 256, 1, 256, 1, 1),
 ]
+# `python tools/conv_ablate.py net`: every distinct Darknet-19 layer shape at batch 32 with the library's own tile choice
+NET_CASES = [(208, 32, 64, 3, 0, 0, 0), (104, 64, 128, 3, 0, 0, 0), (104, 128, 64, 1, 0, 0, 0), (52, 128, 256, 3, 0, 0, 0), (52, 256, 128, 1, 0, 0, 0),
+             (26, 256, 512, 3, 0, 0, 0), (26, 512, 256, 1, 0, 0, 0), (26, 512, 64, 1, 0, 0, 0), (13, 512, 1024, 3, 0, 0, 0), (13, 1024, 512, 1, 0, 0, 0),
+             (13, 1024, 1024, 3, 0, 0, 0), (13, 1280, 1024, 3, 0, 0, 0)]
 ABL = [(0, 'full'), (8, 'no-store'), (1, 'no-A'), (2, 'no-B'), (3, 'no-A,B'), (4, 'no-MMA'), (12, 'no-MMA,store'), (7, 'none(A,B,MMA)'), (15, 'empty')]
 
 
 def main():
     b = 32
-    for h, cin, cout, k, bn, mt, pr in CASES:
+    cases = NET_CASES if len(sys.argv) > 1 and sys.argv[1] == 'net' else CASES
+    for h, cin, cout, k, bn, mt, pr in cases:
         xs = [torch.randn(b, h, h, cin, device='cuda').half() for _ in range(3)]
         w = (torch.randn(cout, k, k, cin, device='cuda') * 0.05).half()
         sc, sh = torch.ones(cout, device='cuda'), torch.zeros(cout, device='cuda')
@@ -39,7 +44,10 @@ def main():
                 ops.conv_bn_act(xs[i % 3], w, sc, sh, 0.1, out=out, flags=flags)
             e.record()
             torch.cuda.synchronize()
-            line += '%s=%.0f  ' % (name, s.elapsed_time(e) * 100)
+            us = s.elapsed_time(e) * 100
+            line += '%s=%.0f  ' % (name, us)
+            if code == 0:
+                line += '(%.0f TF/s)  ' % (2.0 * b * h * h * cin * cout * k * k / us / 1e6)
         print(line, flush=True)
 
 

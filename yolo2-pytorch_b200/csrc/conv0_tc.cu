@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(128, 4) conv0_tc_kernel(const Conv0Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  pdl_trigger();        // lets a PDL successor (the next conv) set up while this grid drains
 
   const int wy = tid >> 4, wx = tid & 15;        // this thread's pool window inside the tile
   const int oh = p.height >> 1, ow = p.width >> 1;

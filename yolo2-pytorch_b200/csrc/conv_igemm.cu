@@ -192,6 +192,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   if (kPair) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the tail of the previous kernel of the
+  // stream; nothing below may run before that kernel's outputs (our activations / the stream-K workspace) are complete
+  pdl_trigger();
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -805,6 +809,7 @@ conv_c32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();        // an ordinary launch itself; lets a PDL successor set up while this grid drains
 
   if (warp == 0) {
     if (lane == 0) {
@@ -999,13 +1004,21 @@ static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const ConvP
   const int tiles = p.m_tiles * p.n_tiles;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
+  int nattr = 0;
+  // programmatic dependent launch: this kernel's prologue may overlap the previous kernel's tail (YB_PDL=0 switches it off for A/B runs)
+  static const int use_pdl = getenv("YB_PDL") ? atoi(getenv("YB_PDL")) : 1;
+  if (use_pdl) {
+    attr[nattr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[nattr].val.programmaticStreamSerializationAllowed = 1;
+    ++nattr;
+  }
   if (kPair) {
     const int pairs = sm_count() / 2;
     cfg.gridDim = dim3(2 * (tiles < pairs ? tiles : pairs));
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[nattr].id = cudaLaunchAttributeClusterDimension;
+    attr[nattr].val.clusterDim.x = 2; attr[nattr].val.clusterDim.y = 1; attr[nattr].val.clusterDim.z = 1;
+    ++nattr;
   } else if (p.streamk) {
     cfg.gridDim = dim3(sm_count());          // sk_base / sk_rem were computed for exactly this many CTAs
   } else {
@@ -1014,6 +1027,7 @@ static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const ConvP
   cfg.blockDim = dim3(kNumThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
+  cfg.attrs = attr; cfg.numAttrs = nattr;
   YB_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BN, BK, MT, kPair>, ta, tb, p));
   return check_launch("conv_igemm_kernel");
 }

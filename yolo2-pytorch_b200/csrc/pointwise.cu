@@ -124,6 +124,7 @@ __device__ __forceinline__ uint4 hmax8(uint4 a, uint4 b) {
 // thread = 8 channels of one output pixel
 __global__ void maxpool2x2_kernel(const __half* __restrict__ x, __half* __restrict__ y, int batch, int height, int width, int channels,
                                   int x_ld) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: the conv that follows may start its prologue now
   const int c8 = channels >> 3;
   const int oh = height >> 1, ow = width >> 1;
   const long long total = static_cast<long long>(batch) * oh * ow * c8;
