@@ -1006,8 +1006,11 @@ static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const ConvP
   memset(&cfg, 0, sizeof(cfg));
   cudaLaunchAttribute attr[2];
   int nattr = 0;
-  // programmatic dependent launch: this kernel's prologue may overlap the previous kernel's tail (YB_PDL=0 switches it off for A/B runs)
-  static const int use_pdl = getenv("YB_PDL") ? atoi(getenv("YB_PDL")) : 1;
+  // Programmatic dependent launch: this kernel's prologue may overlap the previous kernel's tail.  OFF by default -- measured on B200
+  // (profiles/r02_pdl_ab.md): one batch in flight 24.30 k vs 24.43 k img/s (no gain: the prologue is ~2 us of a 20-130 us kernel), two
+  // batches in flight 29.3 k vs 31.2 k img/s (early-resident CTAs spinning in griddepcontrol.wait take the SMs the other lane's kernels
+  // would have used).  YB_PDL=1 switches it on for A/B runs.
+  static const int use_pdl = getenv("YB_PDL") ? atoi(getenv("YB_PDL")) : 0;
   if (use_pdl) {
     attr[nattr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[nattr].val.programmaticStreamSerializationAllowed = 1;

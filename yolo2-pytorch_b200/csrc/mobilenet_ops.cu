@@ -67,51 +67,99 @@ int mb_conv0(const float* x, const float* w, const float* scale, const float* sh
   return check_launch("mb_conv0_kernel");
 }
 
-// w: fp32 [C][9] (the [C,1,3,3] depthwise weight), scale/shift: folded BN
-__global__ void __launch_bounds__(256) dwconv3x3_kernel(const __half* __restrict__ x, const float* __restrict__ w, const float* __restrict__ scale,
+// w: fp32 [C][9] (the [C,1,3,3] depthwise weight), scale/shift: folded BN.
+// One thread = 8 channels (16 B) of TX consecutive output pixels of one row.  Its 72 weights are 288 contiguous bytes (18 x LDG.128,
+// once), the 3 x 3 input window slides along the row in registers (3 new 16 B loads per output pixel at stride 1, 6 at stride 2), so
+// the kernel issues ~1/4 of the load instructions of the one-pixel-per-thread form (which ncu showed issue-bound at 0.10 of HBM peak).
+template <int STRIDE, int TX>
+__global__ void __launch_bounds__(128) dwconv3x3_kernel(const __half* __restrict__ x, const float* __restrict__ w, const float* __restrict__ scale,
                                                         const float* __restrict__ shift, __half* __restrict__ y, int batch, int height, int width,
-                                                        int channels, int stride) {
+                                                        int channels) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int c8 = channels >> 3;
-  const int oh = height / stride, ow = width / stride;
-  const long long total = static_cast<long long>(batch) * oh * ow * c8;
+  const int oh = height / STRIDE, ow = width / STRIDE;
+  const int strips = (ow + TX - 1) / TX;
+  const long long total = static_cast<long long>(batch) * oh * strips * c8;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int cg = static_cast<int>(idx % c8);
   long long t = idx / c8;
-  const int px = static_cast<int>(t % ow); t /= ow;
+  const int strip = static_cast<int>(t % strips); t /= strips;
   const int py = static_cast<int>(t % oh);
   const int img = static_cast<int>(t / oh);
-  float acc[8];
+  float wr[72];
+  {
+    const float4* wp = reinterpret_cast<const float4*>(w + static_cast<long long>(cg) * 72);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  const float* wc = w + static_cast<long long>(cg) * 8 * 9;
-#pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    const int iy = py * stride - 1 + r;
-    if (iy < 0 || iy >= height) continue;
-#pragma unroll
-    for (int s = 0; s < 3; ++s) {
-      const int ix = px * stride - 1 + s;
-      if (ix < 0 || ix >= width) continue;
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + ((static_cast<long long>(img) * height + iy) * width + ix) * channels + cg * 8));
-      const __half2* h = reinterpret_cast<const __half2*>(&v);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = __half22float2(h[e]);
-        acc[2 * e] = fmaf(f.x, __ldg(wc + (2 * e) * 9 + r * 3 + s), acc[2 * e]);
-        acc[2 * e + 1] = fmaf(f.y, __ldg(wc + (2 * e + 1) * 9 + r * 3 + s), acc[2 * e + 1]);
-      }
+    for (int i = 0; i < 18; ++i) {
+      const float4 v = __ldg(wp + i);
+      wr[4 * i] = v.x; wr[4 * i + 1] = v.y; wr[4 * i + 2] = v.z; wr[4 * i + 3] = v.w;
     }
   }
-  uint4 pk;
-  __half2* h = reinterpret_cast<__half2*>(&pk);
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const int c = cg * 8 + 2 * e;
-    h[e] = __floats2half2_rn(fmaxf(acc[2 * e] * __ldg(scale + c) + __ldg(shift + c), 0.f),
-                             fmaxf(acc[2 * e + 1] * __ldg(scale + c + 1) + __ldg(shift + c + 1), 0.f));
+  float sc[8], sh[8];
+  {
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(scale + cg * 8)), a1 = __ldg(reinterpret_cast<const float4*>(scale + cg * 8) + 1);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(shift + cg * 8)), b1 = __ldg(reinterpret_cast<const float4*>(shift + cg * 8) + 1);
+    sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
+    sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
   }
-  reinterpret_cast<uint4*>(y)[idx] = pk;
+  const int px0 = strip * TX;
+  const int iy0 = py * STRIDE - 1;
+  const __half* xrow[3];
+  bool rok[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int iy = iy0 + r;
+    rok[r] = iy >= 0 && iy < height;
+    xrow[r] = x + ((static_cast<long long>(img) * height + (rok[r] ? iy : 0)) * width) * channels + cg * 8;
+  }
+  auto load_col = [&](int ix, uint4 (&col)[3]) {
+    const bool cok = ix >= 0 && ix < width;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+      col[r] = (cok && rok[r]) ? __ldg(reinterpret_cast<const uint4*>(xrow[r] + static_cast<long long>(ix) * channels)) : make_uint4(0u, 0u, 0u, 0u);
+  };
+  uint4 win[3][3];                                   // [column s][row r]
+  load_col(px0 * STRIDE - 1, win[0]);
+  if (STRIDE == 1) load_col(px0 * STRIDE, win[1]);
+#pragma unroll
+  for (int j = 0; j < TX; ++j) {
+    const int px = px0 + j;
+    if (px >= ow) break;
+    if (STRIDE == 1) {
+      load_col(px + 1, win[2]);
+    } else {
+      load_col(2 * px, win[1]);
+      load_col(2 * px + 1, win[2]);
+    }
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const __half2* h = reinterpret_cast<const __half2*>(&win[s][r]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(h[e]);
+          acc[2 * e] = fmaf(f.x, wr[(2 * e) * 9 + r * 3 + s], acc[2 * e]);
+          acc[2 * e + 1] = fmaf(f.y, wr[(2 * e + 1) * 9 + r * 3 + s], acc[2 * e + 1]);
+        }
+      }
+    uint4 pk;
+    __half2* ho = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      ho[e] = __floats2half2_rn(fmaxf(acc[2 * e] * sc[2 * e] + sh[2 * e], 0.f), fmaxf(acc[2 * e + 1] * sc[2 * e + 1] + sh[2 * e + 1], 0.f));
+    *reinterpret_cast<uint4*>(y + ((static_cast<long long>(img) * oh + py) * ow + px) * channels + cg * 8) = pk;
+    // slide: stride 1 keeps two columns, stride 2 keeps one
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      if (STRIDE == 1) { win[0][r] = win[1][r]; win[1][r] = win[2][r]; }
+      else win[0][r] = win[2][r];
+    }
+  }
 }
 
 int dwconv3x3(const void* x, const float* w, const float* scale, const float* shift, void* y, int batch, int height, int width, int channels,
@@ -119,9 +167,22 @@ int dwconv3x3(const void* x, const float* w, const float* scale, const float* sh
   YB_REQUIRE(x && w && scale && shift && y && batch > 0 && channels % 8 == 0 && (stride == 1 || stride == 2) && height % stride == 0 &&
                  width % stride == 0,
              "dwconv3x3: bad argument");
-  const long long total = static_cast<long long>(batch) * (height / stride) * (width / stride) * (channels / 8);
-  dwconv3x3_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const __half*>(x), w, scale, shift,
-                                                                                   reinterpret_cast<__half*>(y), batch, height, width, channels, stride);
+  YB_REQUIRE((reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(scale) & 15) == 0 && (reinterpret_cast<uintptr_t>(shift) & 15) == 0,
+             "dwconv3x3: weights / scale / shift must be 16 B aligned");
+  const int oh = height / stride, ow = width / stride;
+  // pixels per thread: long strips amortise the 72-weight preload, but the grid must still cover the SMs on the 13 x 13 layers
+  const int tx = ow >= 52 ? 8 : 4;
+  const long long total = static_cast<long long>(batch) * oh * ((ow + tx - 1) / tx) * (channels / 8);
+  const unsigned grid = static_cast<unsigned>((total + 127) / 128);
+  const __half* xp = reinterpret_cast<const __half*>(x);
+  __half* yp = reinterpret_cast<__half*>(y);
+  if (stride == 1) {
+    if (tx == 8) dwconv3x3_kernel<1, 8><<<grid, 128, 0, stream>>>(xp, w, scale, shift, yp, batch, height, width, channels);
+    else dwconv3x3_kernel<1, 4><<<grid, 128, 0, stream>>>(xp, w, scale, shift, yp, batch, height, width, channels);
+  } else {
+    if (tx == 8) dwconv3x3_kernel<2, 8><<<grid, 128, 0, stream>>>(xp, w, scale, shift, yp, batch, height, width, channels);
+    else dwconv3x3_kernel<2, 4><<<grid, 128, 0, stream>>>(xp, w, scale, shift, yp, batch, height, width, channels);
+  }
   return check_launch("dwconv3x3_kernel");
 }
 
