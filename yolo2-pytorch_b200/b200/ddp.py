@@ -61,23 +61,54 @@ class Communicator(object):
             _l.check(lib.yb_comm_init(ctypes.byref(handle), self.world, ident, self.rank), 'yb_comm_init')
         self.handle = handle
         self.bytes_reduced = 0
+        # Every collective of this communicator is issued on ONE dedicated stream; callers on other streams are ordered against it with
+        # CUDA events (fork / join).  NCCL then never has to serialise the communicator across streams itself, which is what keeps
+        # eager use, CUDA-graph capture and their mixture legal (a captured collective must not depend on uncaptured work elsewhere).
+        self.stream = torch.cuda.Stream(device=self.device)
 
     def _stream(self, stream):
-        st = torch.cuda.current_stream(self.device) if stream is None else stream
-        return ctypes.c_void_p(st.cuda_stream)
+        return ctypes.c_void_p(self.stream.cuda_stream)
+
+    def _fork(self, caller):
+        ev = torch.cuda.Event()
+        ev.record(caller)
+        self.stream.wait_event(ev)
+
+    def _join(self, caller):
+        ev = torch.cuda.Event()
+        ev.record(self.stream)
+        caller.wait_event(ev)
 
     def all_reduce(self, tensor, stream=None):
-        """In-place sum over ranks, asynchronous on `stream` (default: torch's current stream)."""
+        """In-place sum over ranks.  stream=None: ordered after the work already enqueued on torch's current stream, and that stream
+        waits for the result (asynchronously).  stream=self.stream: the caller has done the ordering itself (gradient buckets)."""
         if not (tensor.is_cuda and tensor.is_contiguous()):
             raise RuntimeError('Communicator.all_reduce: contiguous CUDA tensor required')
+        caller = None
+        if stream is not self.stream:
+            caller = torch.cuda.current_stream(self.device) if stream is None else stream
+            self._fork(caller)
         _l.check(_l.load().yb_allreduce_bucket(self.handle, ctypes.c_void_p(tensor.data_ptr()), tensor.numel(), _DTYPES[tensor.dtype],
-                                               self._stream(stream)), 'yb_allreduce_bucket')
+                                               self._stream(None)), 'yb_allreduce_bucket')
+        if caller is not None:
+            tensor.record_stream(self.stream)
+            self._join(caller)
         self.bytes_reduced += tensor.numel() * tensor.element_size()
         return tensor
 
     def broadcast(self, tensor, root=0, stream=None):
+        """Rank `root`'s values into `tensor` on every rank; ordered against torch's current stream like all_reduce(stream=None)."""
         if not (tensor.is_cuda and tensor.is_contiguous()):
             raise RuntimeError('Communicator.broadcast: contiguous CUDA tensor required')
+        caller = torch.cuda.current_stream(self.device)
+        self._fork(caller)
+        try:
+            return self._broadcast(tensor, root)
+        finally:
+            self._join(caller)
+
+    def _broadcast(self, tensor, root):
+        stream = None
         t = tensor
         if t.dtype not in _DTYPES:                      # e.g. int64 num_batches_tracked: ship the raw words
             t = t.view(torch.int32) if t.element_size() % 4 == 0 and t.dim() > 0 else None
@@ -157,7 +188,7 @@ class GradientAllReducer(object):
         if self.comm is None and self.world > 1:
             self.comm = Communicator(arena.flat.device, self.group)
         self.arena = arena
-        self.comm_stream = torch.cuda.Stream(device=arena.flat.device)
+        self.comm_stream = self.comm.stream if self.comm is not None else torch.cuda.Stream(device=arena.flat.device)
         self._reset()
 
     def _reset(self):

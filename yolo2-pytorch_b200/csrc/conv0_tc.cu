@@ -15,6 +15,7 @@
 // bytes.  Persistent CTAs (4 per SM), weights (B operand) built once per CTA.
 #include "yb_common.h"
 #include "yb_ptx.cuh"
+#include <stdlib.h>
 
 namespace yb {
 
@@ -244,16 +245,200 @@ __global__ void __launch_bounds__(128, 4) conv0_tc_kernel(const Conv0Params p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Second form of the same layer: NO thread-built im2col rows.  The first form above spends its time writing four 64-byte im2col rows
+// per thread (ncu: SM 61 %, tensor pipe 6 %, DRAM 14 % -- issue-bound at 0.27 of the HBM roofline).  Here the haloed input patch is
+// kept in shared memory as fp16 pixels of 4 channels (r, g, b, 0 = 8 bytes) and the tensor core reads every operand IN PLACE through
+// un-swizzled K-major descriptors: one filter ROW (3 taps x 4 channels = 12, padded to K = 16) of output pixel (y, x) is the 32
+// contiguous bytes starting at patch pixel (y + r, x); pixels two columns apart are 16 bytes apart, which is exactly the row pitch of
+// an 8 x 16 B core matrix.  So with M-tile (dy, dx) = pixel (dy, dx) of every 2x2 pool window, the 8 windows of a window row form one
+// core matrix (LBO = 16 B to the second K chunk, which overlaps the next window's first -- it is only ever read), the next window row
+// is two patch rows further (SBO = 288 B), and a second copy of the patch shifted by one pixel gives the odd columns their 16-byte
+// alignment.  3 MMAs (one per filter row, K = 16) per accumulator instead of 2, and the threads only convert + store 8 B per pixel.
+// K-pad lanes read the neighbouring pixel and meet zero weights (finite inputs assumed; an inf / NaN pixel would reach x - 3 .. x + 1
+// instead of x - 1 .. x + 1).
+constexpr int kV2Rows = 32, kV2Cols = 16;                       // conv pixels per tile = 16 x 8 pool windows
+constexpr int kV2PR = kV2Rows + 2, kV2PC = kV2Cols + 2;         // 34 x 18 pixel patch
+constexpr int kV2Pitch = kV2PC * 8;                             // 144 B per patch row
+constexpr int kV2Copy = kV2PR * kV2Pitch;                       // 4896 B
+constexpr int kV2Pixels = kV2PR * kV2PC;                        // 612
+constexpr int kV2Iters = (kV2Pixels + 127) / 128;               // 5 pixels per thread
+
+template <bool kU8>
+__global__ void __launch_bounds__(128, 4) conv0_k16_kernel(const Conv0Params p) {
+  __shared__ __align__(128) uint8_t patch_e[kV2Copy + 48];      // pixel (r, c) at (r * 18 + c) * 8: even columns 16 B aligned
+  __shared__ __align__(128) uint8_t patch_o[kV2Copy + 48];      // the same pixels at + 8 B: odd columns 16 B aligned
+  __shared__ __align__(128) uint8_t b_smem[3 * 1024];           // per filter row: [n / 8][k / 8][n % 8][k % 8] fp16 (32 x 16)
+  __shared__ __align__(16) float sc[kC0Out], sh[kC0Out];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t e_base = smem_u32(patch_e), o_base = smem_u32(patch_o), b_base = smem_u32(b_smem), bar_addr = smem_u32(&bar);
+
+  if (tid == 0) {
+    mbar_init(bar_addr, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(smem_u32(&tmem_slot), 128);
+    tmem_relinquish();
+  }
+  if (tid < kC0Out) { sc[tid] = p.scale[tid]; sh[tid] = p.shift[tid]; }
+  // the bytes past the last patch pixel are read by the K-pad lanes of the last row: keep them finite
+  if (tid < 12) {
+    reinterpret_cast<uint32_t*>(patch_e + kV2Copy)[tid] = 0u;
+    reinterpret_cast<uint32_t*>(patch_o + kV2Copy)[tid] = 0u;
+  }
+  if (tid < 2) reinterpret_cast<uint32_t*>(patch_o)[tid] = 0u;
+  {
+    // B operand, filter row r: element (n, k = s * 4 + c) = w[n][c][r][s] for s, c < 3, else 0
+    const int n = tid >> 2, s4 = tid & 3;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      float v[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) v[c] = (s4 < 3 && c < 3) ? __ldg(p.w + n * 27 + c * 9 + r * 3 + s4) : 0.f;
+      const uint2 pk = make_uint2(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]));
+      *reinterpret_cast<uint2*>(b_smem + r * 1024 + (n >> 3) * 256 + (s4 >> 1) * 128 + (n & 7) * 16 + (s4 & 1) * 8) = pk;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  pdl_trigger();
+
+  const int wy = tid >> 3, wx = tid & 7;         // this thread's pool window inside the tile (its TMEM lane)
+  const int oh = p.height >> 1, ow = p.width >> 1;
+  uint32_t phase = 0;
+  constexpr uint32_t idesc = make_idesc_f16(128, kC0Out);
+
+  auto prefetch = [&](int t, float (&v)[kV2Iters][3]) {
+    const int ptx = t % p.tiles_x;
+    const int pt2 = t / p.tiles_x;
+    const int pty = pt2 % p.tiles_y;
+    const int pimg = pt2 / p.tiles_y;
+    const int y0 = pty * kV2Rows - 1, x0 = ptx * kV2Cols - 1;
+#pragma unroll
+    for (int k = 0; k < kV2Iters; ++k) {
+      const int i = tid + k * 128;
+      const int r = i / kV2PC, c = i - r * kV2PC;
+      const int iy = y0 + r, ix = x0 + c;
+      const bool ok = i < kV2Pixels && iy >= 0 && iy < p.height && ix >= 0 && ix < p.width;
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        float val = 0.f;
+        if (ok) {
+          if (kU8) val = static_cast<float>(__ldg(reinterpret_cast<const uint8_t*>(p.x) + ((static_cast<long long>(pimg) * p.height + iy) * p.width + ix) * 3 + ch)) * (1.f / 255.f);
+          else val = __ldg(reinterpret_cast<const float*>(p.x) + ((static_cast<long long>(pimg) * 3 + ch) * p.height + iy) * p.width + ix);
+        }
+        v[k][ch] = val;
+      }
+    }
+  };
+  float pre[kV2Iters][3];
+  if (static_cast<int>(blockIdx.x) < p.num_tiles) prefetch(blockIdx.x, pre);
+
+  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    const int tx = tile % p.tiles_x;
+    const int t2 = tile / p.tiles_x;
+    const int ty = t2 % p.tiles_y;
+    const int img = t2 / p.tiles_y;
+    // ---- 1. the patch, twice (8 B per pixel each) ----
+#pragma unroll
+    for (int k = 0; k < kV2Iters; ++k) {
+      const int i = tid + k * 128;
+      if (i < kV2Pixels) {
+        const uint2 pk = make_uint2(pack_h2(pre[k][0], pre[k][1]), pack_h2(pre[k][2], 0.f));
+        *reinterpret_cast<uint2*>(patch_e + i * 8) = pk;
+        *reinterpret_cast<uint2*>(patch_o + 8 + i * 8) = pk;
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    // ---- 2. MMA: accumulator (dy, dx) += sum over filter rows, operands read in place ----
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int dy = j >> 1, dx = j & 1;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const uint32_t a_addr = (dx ? o_base + 8 : e_base) + ((dy + r) * kV2PC + dx) * 8;
+          umma_f16(tmem_base + j * kC0Out, make_kmajor_desc_noswz(a_addr, 16, 2 * kV2Pitch), make_kmajor_desc_noswz(b_base + r * 1024, 128, 256), idesc,
+                   r != 0);
+        }
+      }
+      umma_commit(bar_addr);
+    }
+    {
+      const int next = tile + gridDim.x;
+      if (next < p.num_tiles) prefetch(next, pre);
+    }
+    mbar_wait(bar_addr, phase, p.dbg, 0x510);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- 3. epilogue: as the first form, window (wy, wx) = TMEM lane ----
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const int py = ty * (kV2Rows / 2) + wy, px = tx * (kV2Cols / 2) + wx;
+    __half* dst = p.y + ((static_cast<long long>(img) * oh + py) * ow + px) * kC0Out;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint32_t v[4][8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) tmem_ld_32x32b_x8(lane_addr + j * kC0Out + g * 8, v[j]);
+      tmem_ld_wait();
+      if (p.raw) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int yy = ty * kV2Rows + 2 * wy + (j >> 1), xx = tx * kV2Cols + 2 * wx + (j & 1);
+          *reinterpret_cast<uint4*>(p.y + ((static_cast<long long>(img) * p.height + yy) * p.width + xx) * kC0Out + g * 8) =
+              make_uint4(pack_h2(__uint_as_float(v[j][0]), __uint_as_float(v[j][1])), pack_h2(__uint_as_float(v[j][2]), __uint_as_float(v[j][3])),
+                         pack_h2(__uint_as_float(v[j][4]), __uint_as_float(v[j][5])), pack_h2(__uint_as_float(v[j][6]), __uint_as_float(v[j][7])));
+        }
+        continue;
+      }
+      float m[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float s = sc[g * 8 + e], b = sh[g * 8 + e];
+        float best = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float t = __uint_as_float(v[j][e]) * s + b;
+          t = t > 0.f ? t : t * p.slope;
+          best = fmaxf(best, t);
+        }
+        m[e] = best;
+      }
+      *reinterpret_cast<uint4*>(dst + g * 8) = make_uint4(pack_h2(m[0], m[1]), pack_h2(m[2], m[3]), pack_h2(m[4], m[5]), pack_h2(m[6], m[7]));
+    }
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 128);
+  }
+}
+
 int conv0_tc_forward(const void* x, int x_is_u8, const float* w, const float* scale, const float* shift, float slope, void* y, int batch,
                      int height, int width, int cout, int raw, cudaStream_t stream) {
   YB_REQUIRE(x && w && y && (raw || (scale && shift)), "conv0: null pointer");
   YB_REQUIRE(cout == kC0Out, "conv0: Cout=%d unsupported (32)", cout);
   YB_REQUIRE(batch > 0 && height > 0 && width > 0 && height % kT0Rows == 0 && width % kT0Cols == 0,
              "conv0: H must be a multiple of %d and W of %d (got %dx%d)", kT0Rows, kT0Cols, height, width);
+  // operands-in-place form when the shape tiles 32 x 16 (every multiple of 32, i.e. every Darknet input); YB_CONV0_V1=1 forces the first form
+  static const int force_v1 = getenv("YB_CONV0_V1") ? atoi(getenv("YB_CONV0_V1")) : 0;
+  const bool v2 = !force_v1 && height % kV2Rows == 0 && width % kV2Cols == 0;
   Conv0Params p;
   p.x = x; p.w = w; p.scale = scale; p.shift = shift; p.slope = slope; p.y = reinterpret_cast<__half*>(y);
   p.batch = batch; p.height = height; p.width = width;
-  p.tiles_x = width / kT0Cols; p.tiles_y = height / kT0Rows;
+  p.tiles_x = v2 ? width / kV2Cols : width / kT0Cols;
+  p.tiles_y = v2 ? height / kV2Rows : height / kT0Rows;
   const long long tiles = static_cast<long long>(p.tiles_x) * p.tiles_y * batch;
   YB_REQUIRE(tiles < (1ll << 31), "conv0: too many tiles");
   p.num_tiles = static_cast<int>(tiles);
@@ -262,6 +447,11 @@ int conv0_tc_forward(const void* x, int x_is_u8, const float* w, const float* sc
   p.dbg = debug_word_device();
   const int max_ctas = sm_count() * 4;
   const int grid = p.num_tiles < max_ctas ? p.num_tiles : max_ctas;
+  if (v2) {
+    if (x_is_u8) conv0_k16_kernel<true><<<grid, 128, 0, stream>>>(p);
+    else conv0_k16_kernel<false><<<grid, 128, 0, stream>>>(p);
+    return check_launch("conv0_k16_kernel");
+  }
   if (x_is_u8) conv0_tc_kernel<true><<<grid, 128, 0, stream>>>(p);
   else conv0_tc_kernel<false><<<grid, 128, 0, stream>>>(p);
   return check_launch("conv0_tc_kernel");

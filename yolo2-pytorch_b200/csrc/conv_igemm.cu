@@ -62,6 +62,10 @@ struct ConvParams {
   // `lo_off` != 0: the epilogue also stores lo = fp16(v - fp32(fp16(v))) at y + lo_off (fp16 NHWC only).
   int a_wrap;
   long long lo_off;
+  // fp16 NHWC output through shared memory + TMA store (tmap_y): the epilogue stages 128 rows x 64 channels (128B-swizzled) and one
+  // thread ships them with a single bulk store.  The per-thread 16 B stores it replaces write 32 half-used sectors per instruction
+  // (lanes = pixels, 2*y_ld bytes apart) and cost 15-30 % of the 104x104 / 1x1 layers (tools/conv_ablate.py: full vs no-store).
+  int tma_store;
 };
 
 // role 0 = TMA producer, 1 = MMA issuer, 2 = epilogue thread 0; slot = running event index of that role
@@ -136,13 +140,16 @@ struct ConvCfg {
   static constexpr int kRowsPerCta = BM * MT;
   static constexpr bool kMergedA = (MT == 2 && !kPair);        // A tile fetched by one 256-pixel TMA box
   static constexpr int kRowsPerTile = kRowsPerCta * (kPair ? 2 : 1);
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 2 * 2 * BN * 4 /*scale/shift x2*/ + 2 * BN * 4 /*stats*/ + 256 /*barriers*/;
+  static constexpr int kOutBytes = BM * 128;                   // TMA-store staging: 128 rows x 64 channels fp16
+  static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 /*align slack*/ + 2 * 2 * BN * 4 /*scale/shift x2*/ + 2 * BN * 4 /*stats*/ + 256 /*barriers*/;
+  static_assert(kSmemBytes <= 232448, "shared memory budget");
   static_assert(kAccCols <= 512, "accumulator does not fit TMEM");
 };
 
 template <int BN, int BK, int MT, bool kPair>
 __global__ void __launch_bounds__(kNumThreads, 1)
-conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const ConvParams p) {
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const __grid_constant__ CUtensorMap tmap_y, const ConvParams p) {
   using Cfg = ConvCfg<BN, BK, MT, kPair>;
   constexpr int kAccStages = Cfg::kAccStages;
   constexpr int kStages = Cfg::kStages;
@@ -153,7 +160,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t smem_a = smem_base;
   const uint32_t smem_b = smem_base + kStages * Cfg::kABytes;
-  float* ep_scale = reinterpret_cast<float*>(smem_gen + kStages * Cfg::kStageBytes);  // [2][BN]
+  const uint32_t smem_o = smem_base + kStages * Cfg::kStageBytes;                       // 1024-aligned: stage sizes are multiples of 1 KB
+  float* ep_scale = reinterpret_cast<float*>(smem_gen + kStages * Cfg::kStageBytes + Cfg::kOutBytes);  // [2][BN]
   float* ep_shift = ep_scale + 2 * BN;                                                  // [2][BN]
   float* ep_stats = ep_shift + 2 * BN;                                                  // [2][BN] sum, sum of squares of this tile
   uint64_t* bars = reinterpret_cast<uint64_t*>(ep_stats + 2 * BN);
@@ -183,6 +191,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     fence_proxy_async_smem();
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (p.tma_store) tma_prefetch_desc(&tmap_y);
   }
   if (warp == 1) {
     if (kPair) { tmem_alloc_pair(smem_u32(tmem_slot), Cfg::kTmemCols); tmem_relinquish_pair(); }
@@ -401,6 +410,89 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * Cfg::kAccCols + t * BN;
         int img = 0, pix = 0;
         if (p.out_mode == 1) { img = row / p.hw; pix = row - img * p.hw; }
+        if (p.tma_store) {
+          // ---- fp16 NHWC through the staging buffer: 64 channels (two TMEM loads) per bulk store ----
+#pragma unroll 1
+          for (int c2 = 0; c2 < BN / 64; ++c2) {
+            if (n0 + c2 * 64 >= p.cout) break;        // uniform over the 128 epilogue threads
+            uint4 pk[8];
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const int cc = c2 * 2 + hh;
+              uint32_t v[32];
+              tmem_ld_32x32b_x32(taddr + cc * 32, v);
+              tmem_ld_wait();
+              const int cbase = n0 + cc * 32;
+              if (sk_collect && cbase < p.cout) {
+                for (int j = sk_lo; j < static_cast<int>(blockIdx.x); ++j) {
+                  const float4* src = reinterpret_cast<const float4*>(p.ws + static_cast<size_t>(j) * (MT * BN * 128) +
+                                                                      (static_cast<size_t>(t * (BN / 32) + cc) * 128 + q * 32 + lane) * 32);
+#pragma unroll
+                  for (int g = 0; g < 8; ++g) {
+                    const float4 a = __ldcg(src + g);
+                    v[4 * g] = __float_as_uint(__uint_as_float(v[4 * g]) + a.x);
+                    v[4 * g + 1] = __float_as_uint(__uint_as_float(v[4 * g + 1]) + a.y);
+                    v[4 * g + 2] = __float_as_uint(__uint_as_float(v[4 * g + 2]) + a.z);
+                    v[4 * g + 3] = __float_as_uint(__uint_as_float(v[4 * g + 3]) + a.w);
+                  }
+                }
+              }
+              float f[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                float x = __uint_as_float(v[j]) * sc[cc * 32 + j] + sh[cc * 32 + j];
+                f[j] = x > 0.f ? x : x * p.slope;
+              }
+              if (p.stats != nullptr && cbase < p.cout) {
+                float a1[32], a2[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  const float r = row_ok ? __half2float(__float2half_rn(f[j])) : 0.f;
+                  a1[j] = r; a2[j] = r * r;
+                }
+#pragma unroll
+                for (int s = 16; s >= 1; s >>= 1) {
+                  const bool up = (lane & s) != 0;
+#pragma unroll
+                  for (int j = 0; j < s; ++j) {
+                    const float k1 = up ? a1[j + s] : a1[j], g1 = up ? a1[j] : a1[j + s];
+                    const float k2 = up ? a2[j + s] : a2[j], g2 = up ? a2[j] : a2[j + s];
+                    a1[j] = k1 + __shfl_xor_sync(0xffffffffu, g1, s);
+                    a2[j] = k2 + __shfl_xor_sync(0xffffffffu, g2, s);
+                  }
+                }
+                atomicAdd(&ep_stats[cc * 32 + lane], a1[0]);
+                atomicAdd(&ep_stats[BN + cc * 32 + lane], a2[0]);
+              }
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                __half2 h0 = __floats2half2_rn(f[g * 8 + 0], f[g * 8 + 1]);
+                __half2 h1 = __floats2half2_rn(f[g * 8 + 2], f[g * 8 + 3]);
+                __half2 h2 = __floats2half2_rn(f[g * 8 + 4], f[g * 8 + 5]);
+                __half2 h3 = __floats2half2_rn(f[g * 8 + 6], f[g * 8 + 7]);
+                pk[hh * 4 + g].x = *reinterpret_cast<uint32_t*>(&h0);
+                pk[hh * 4 + g].y = *reinterpret_cast<uint32_t*>(&h1);
+                pk[hh * 4 + g].z = *reinterpret_cast<uint32_t*>(&h2);
+                pk[hh * 4 + g].w = *reinterpret_cast<uint32_t*>(&h3);
+              }
+            }
+            // one staging buffer: the previous bulk store must have drained it (that wait overlapped the TMEM loads / math above)
+            if (et == 0) tma_store_wait_read<0>();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            {
+              const int r = q * 32 + lane;
+#pragma unroll
+              for (int c = 0; c < 8; ++c) st_shared_v4(smem_o + r * 128 + ((c ^ (r & 7)) << 4), pk[c]);
+            }
+            fence_proxy_async_smem();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (et == 0 && !(p.skip & 8)) {
+              tma_store_2d(&tmap_y, smem_o, n0 + c2 * 64, m_cta + t * BM);      // rows >= M and channels >= Cout are clipped by the tensor map
+              tma_store_commit();
+            }
+          }
+          continue;
+        }
 #pragma unroll 1
         for (int cc = 0; cc < BN / 32; ++cc) {
           uint32_t v[32];
@@ -522,6 +614,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
+    if (p.tma_store && et == 0) tma_store_wait<0>();       // every bulk store has landed before the CTA's shared memory goes away
   }
 
   tc_fence_before();
@@ -994,7 +1087,7 @@ static int get_encoders(EncodeTiledFn* tiled, EncodeIm2colFn* im2col) {
 int get_tensor_map_encoders(EncodeTiledFn* tiled, EncodeIm2colFn* im2col) { return get_encoders(tiled, im2col); }
 
 template <int BN, int BK, int MT, bool kPair>
-static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, cudaStream_t stream) {
+static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty, const ConvParams& p, cudaStream_t stream) {
   using Cfg = ConvCfg<BN, BK, MT, kPair>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -1031,20 +1124,20 @@ static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const ConvP
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
   cfg.attrs = attr; cfg.numAttrs = nattr;
-  YB_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BN, BK, MT, kPair>, ta, tb, p));
+  YB_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BN, BK, MT, kPair>, ta, tb, ty, p));
   return check_launch("conv_igemm_kernel");
 }
 
 template <int BK, bool kPair>
-static int dispatch_conv(int bn, int mt, const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, cudaStream_t stream) {
+static int dispatch_conv(int bn, int mt, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty, const ConvParams& p, cudaStream_t stream) {
   if (mt == 1) {
-    if (bn == 64) return launch_conv<64, BK, 1, kPair>(ta, tb, p, stream);
-    if (bn == 128) return launch_conv<128, BK, 1, kPair>(ta, tb, p, stream);
-    return launch_conv<256, BK, 1, kPair>(ta, tb, p, stream);
+    if (bn == 64) return launch_conv<64, BK, 1, kPair>(ta, tb, ty, p, stream);
+    if (bn == 128) return launch_conv<128, BK, 1, kPair>(ta, tb, ty, p, stream);
+    return launch_conv<256, BK, 1, kPair>(ta, tb, ty, p, stream);
   }
-  if (bn == 64) return launch_conv<64, BK, 2, kPair>(ta, tb, p, stream);
-  if (bn == 128) return launch_conv<128, BK, 2, kPair>(ta, tb, p, stream);
-  return launch_conv<256, BK, 2, kPair>(ta, tb, p, stream);
+  if (bn == 64) return launch_conv<64, BK, 2, kPair>(ta, tb, ty, p, stream);
+  if (bn == 128) return launch_conv<128, BK, 2, kPair>(ta, tb, ty, p, stream);
+  return launch_conv<256, BK, 2, kPair>(ta, tb, ty, p, stream);
 }
 
 static int conv_c32_forward(const void* x, const void* w, const float* scale, const float* shift, float slope, void* y, int batch,
@@ -1232,6 +1325,7 @@ int conv_igemm_forward(const void* x, const void* w, const float* scale, const f
   p.skip = (flags >> 24) & 0xF;
   p.streamk = streamk;
   p.stats = stats;
+  p.tma_store = 0;
   p.a_wrap = a_channels;
   p.lo_off = lo_ch_off >= 0 ? static_cast<long long>(lo_ch_off - y_ch_off) : 0;
   p.sk_base = 0; p.sk_rem = 0; p.ws = nullptr; p.flags = nullptr;
@@ -1309,12 +1403,26 @@ int conv_igemm_forward(const void* x, const void* w, const float* scale, const f
     conv_smallk_kernel<64><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, ty, p, tma_store);
     return check_launch("conv_smallk_kernel");
   }
-  if (pair) {
-    if (bk == 64) return dispatch_conv<64, true>(bn, mt, ta, tb, p, stream);
-    return dispatch_conv<32, true>(bn, mt, ta, tb, p, stream);
+  // output tensor map of the TMA-store epilogue (fp16 NHWC, no residual output); flags bit 29 (YB_CONV_PLAIN_STORE) keeps the
+  // per-thread stores for A/B runs
+  alignas(64) CUtensorMap ty;
+  memset(&ty, 0, sizeof(ty));
+  p.tma_store = (out_mode == 0 && lo_ch_off < 0 && ((flags >> 29) & 1) == 0) ? 1 : 0;
+  if (p.tma_store) {
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cout), static_cast<cuuint64_t>(p.m_total)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(y_ld) * 2};
+    const cuuint32_t box[2] = {64, BM};
+    const cuuint32_t estr[2] = {1, 1};
+    cr = enc_tiled(&ty, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, static_cast<__half*>(y) + y_ch_off, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(YB_ERR_DRIVER, "cuTensorMapEncodeTiled(Y) failed (%d)", static_cast<int>(cr));
   }
-  if (bk == 64) return dispatch_conv<64, false>(bn, mt, ta, tb, p, stream);
-  return dispatch_conv<32, false>(bn, mt, ta, tb, p, stream);
+  if (pair) {
+    if (bk == 64) return dispatch_conv<64, true>(bn, mt, ta, tb, ty, p, stream);
+    return dispatch_conv<32, true>(bn, mt, ta, tb, ty, p, stream);
+  }
+  if (bk == 64) return dispatch_conv<64, false>(bn, mt, ta, tb, ty, p, stream);
+  return dispatch_conv<32, false>(bn, mt, ta, tb, ty, p, stream);
 }
 
 // ---------------------------------------------------------------------------------------------
