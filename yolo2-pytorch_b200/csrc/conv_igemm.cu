@@ -416,12 +416,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           for (int c2 = 0; c2 < BN / 64; ++c2) {
             if (n0 + c2 * 64 >= p.cout) break;        // uniform over the 128 epilogue threads
             uint4 pk[8];
+            // both 32-column halves in flight before the single wait (a TMEM load is a few hundred cycles of latency)
+            uint32_t vv[2][32];
+            tmem_ld_32x32b_x32(taddr + (c2 * 2) * 32, vv[0]);
+            tmem_ld_32x32b_x32(taddr + (c2 * 2 + 1) * 32, vv[1]);
+            tmem_ld_wait();
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
               const int cc = c2 * 2 + hh;
-              uint32_t v[32];
-              tmem_ld_32x32b_x32(taddr + cc * 32, v);
-              tmem_ld_wait();
+              uint32_t (&v)[32] = vv[hh];
               const int cbase = n0 + cc * 32;
               if (sk_collect && cbase < p.cout) {
                 for (int j = sk_lo; j < static_cast<int>(blockIdx.x); ++j) {
