@@ -210,12 +210,18 @@ class GradientAllReducer(object):
     def _launch(self, bi, streams):
         dev = self.arena.flat.device
         streams = [s for s in streams if s is not None] or [torch.cuda.current_stream(dev)]
-        for st in streams:
-            ev = torch.cuda.Event()
-            ev.record(st)
-            self.comm_stream.wait_event(ev)
-        buf = self.arena.bucket_tensor(bi)
-        self.comm.all_reduce(buf, stream=self.comm_stream)
+        what = 'start'
+        try:
+            for i, st in enumerate(streams):
+                what = 'event on producing stream %d of %d (%r)' % (i, len(streams), st)
+                ev = torch.cuda.Event()
+                ev.record(st)
+                self.comm_stream.wait_event(ev)
+            buf = self.arena.bucket_tensor(bi)
+            what = 'all-reduce'
+            self.comm.all_reduce(buf, stream=self.comm_stream)
+        except Exception as ex:
+            raise RuntimeError('gradient bucket %d: %s failed (capturing: %s): %s' % (bi, what, torch.cuda.is_current_stream_capturing(), ex)) from ex
         self.bytes_reduced += buf.numel() * 4
         self._launched += 1
 

@@ -239,9 +239,12 @@ class DarknetTrainer(object):
         side = self._side(dev)
         if side is not None:
             main = torch.cuda.current_stream(dev)
-            fork = torch.cuda.Event()
-            fork.record(main)
-            side.wait_event(fork)
+            try:
+                fork = torch.cuda.Event()
+                fork.record(main)
+                side.wait_event(fork)
+            except Exception as ex:
+                raise RuntimeError('weight-gradient fork for %s failed (main %r, side %r): %s' % (name, main, side, ex)) from ex
             dz.record_stream(side)          # dz / ain are main-stream allocations still read by the side stream
             ain.record_stream(side)
             self._side_busy = True
