@@ -414,7 +414,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           // ---- fp16 NHWC through the staging buffer: 64 channels (two TMEM loads) per bulk store ----
 #pragma unroll 1
           for (int c2 = 0; c2 < BN / 64; ++c2) {
-            if (n0 + c2 * 64 >= p.cout) break;        // uniform over the 128 epilogue threads
+            if (n0 + c2 * 64 >= p.cout) break;
             uint4 pk[8];
             // both 32-column halves in flight before the single wait (a TMEM load is a few hundred cycles of latency)
             uint32_t vv[2][32];
@@ -479,18 +479,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 pk[hh * 4 + g].w = *reinterpret_cast<uint32_t*>(&h3);
               }
             }
-            // one staging buffer: the previous bulk store must have drained it (that wait overlapped the TMEM loads / math above)
-            if (et == 0) tma_store_wait_read<0>();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            // Each epilogue warp ships its own 32 rows (4 KB of the staging tile) with its own bulk store: no block-level barrier in the
+            // epilogue, so while one warp waits for TMEM the others convert / store.  The warp's previous store must have drained its
+            // slice (that wait overlapped the TMEM loads and the math above).
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
             {
-              const int r = q * 32 + lane;
+              const uint32_t slice = smem_o + q * 4096 + lane * 128;
 #pragma unroll
-              for (int c = 0; c < 8; ++c) st_shared_v4(smem_o + r * 128 + ((c ^ (r & 7)) << 4), pk[c]);
+              for (int c = 0; c < 8; ++c) st_shared_v4(slice + ((c ^ (lane & 7)) << 4), pk[c]);
             }
             fence_proxy_async_smem();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (et == 0 && !(p.skip & 8)) {
-              tma_store_2d(&tmap_y, smem_o, n0 + c2 * 64, m_cta + t * BM);      // rows >= M and channels >= Cout are clipped by the tensor map
+            __syncwarp();
+            if (lane == 0 && !(p.skip & 8)) {
+              tma_store_2d(&tmap_y, smem_o + q * 4096, n0 + c2 * 64, m_cta + t * BM + q * 32);      // rows >= M and channels >= Cout are clipped by the tensor map
               tma_store_commit();
             }
           }
@@ -617,7 +619,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
-    if (p.tma_store && et == 0) tma_store_wait<0>();       // every bulk store has landed before the CTA's shared memory goes away
+    if (p.tma_store && lane == 0) tma_store_wait<0>();     // every bulk store of this warp has landed before the CTA's shared memory goes away
   }
 
   tc_fence_before();
@@ -1414,7 +1416,7 @@ int conv_igemm_forward(const void* x, const void* w, const float* scale, const f
   if (p.tma_store) {
     const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cout), static_cast<cuuint64_t>(p.m_total)};
     const cuuint64_t strides[1] = {static_cast<cuuint64_t>(y_ld) * 2};
-    const cuuint32_t box[2] = {64, BM};
+    const cuuint32_t box[2] = {64, 32};                 // one epilogue warp's rows
     const cuuint32_t estr[2] = {1, 1};
     cr = enc_tiled(&ty, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, static_cast<__half*>(y) + y_ch_off, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
