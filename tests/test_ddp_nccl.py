@@ -73,22 +73,10 @@ def _worker(rank, port, out):
     start = {k: v.detach().clone() for k, v in dnn.state_dict().items()}
     shard = _shard(_batch(), rank)
     opt = torch.optim.SGD(dnn.parameters(), LR)
-    variant = os.environ.get('YB_DDP_TEST_VARIANT', '')
-    if variant == 'side':
-        st = torch.cuda.Stream()
-        st.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(st):
-            res = yb_train.iterate(inference, opt, anchors, cfg, shard)
-        torch.cuda.current_stream().wait_stream(st)
-    else:
-        res = yb_train.iterate(inference, opt, anchors, cfg, shard)
+    res = yb_train.iterate(inference, opt, anchors, cfg, shard)       # kept alive on purpose: iterate() must not hand out the autograd graph
     torch.cuda.synchronize()
     grads = {n: p.grad.detach().float().cpu() for n, p in dnn.named_parameters()}
     after = {k: v.detach().float().cpu() for k, v in dnn.state_dict().items()}
-    if variant == 'delres':
-        res = dict(loss={k: v.detach() for k, v in res['loss'].items()}, debug=dict(pos_count=res['debug']['pos_count'].detach().clone()))
-        import gc
-        gc.collect()
     # the same step from the same start, whole iteration (collectives included) replayed as one CUDA graph
     dnn.load_state_dict(start)
     opt2 = torch.optim.SGD(dnn.parameters(), LR)

@@ -95,8 +95,15 @@ def iterate(inference, optimizer, anchors, config, data, reducer=None):
         optimizer.found_inf = dnn.trainer.found_inf
         optimizer.grad_scale = None
     optimizer.step()
-    return dict(height=height, width=width, rows=rows, cols=cols, data=data, pred=pred, debug=debug, loss_total=loss_total, loss=loss,
-                loss_hparam=loss_hparam)
+    # What is returned is for summaries / logging only (the reference reads .data / float() of it, train.py:353-362), so it is detached:
+    # a caller that keeps the dict must not keep the autograd graph -- and with it the parameters' AccumulateGrad nodes, which remember
+    # the stream they were created on -- alive: a later CUDA-graph capture of the step would then have to synchronise with that
+    # uncaptured stream (cudaErrorStreamCaptureIsolation; found with tests/test_ddp_nccl.py).
+    def _d(v):
+        return v.detach() if torch.is_tensor(v) else v
+
+    return dict(height=height, width=width, rows=rows, cols=cols, data=data, pred={k: _d(v) for k, v in pred.items()}, debug=debug,
+                loss_total=loss_total.detach(), loss={k: _d(v) for k, v in loss.items()}, loss_hparam={k: _d(v) for k, v in loss_hparam.items()})
 
 
 class GraphedStep(object):
