@@ -1296,6 +1296,59 @@ def test_resize_batch_bit_exact_vs_cv2_golden(golden_dir):
     assert rel_err(f_u8, f_f32) <= 2e-3
 
 
+def test_flip_and_random_crop_bit_exact_vs_executed_reference(golden_dir):
+    """The training-side resize (reference `flip_horizontally` -> `random_crop` -> `rescale`, executed with cv2 by
+    tests/golden/make_golden_augment.py): every output frame bit-identical (SHA-256), boxes equal in float32, through the batched launch,
+    through the single-image mirrors with the reference's own random draws, and the stand-alone flip."""
+    import hashlib
+    import configparser
+    import transform
+    import transform.augmentation
+    import transform.resize.label
+    g = np.load(os.path.join(golden_dir, 'augment.npz'))
+    cfg = configparser.ConfigParser()
+    cfg.read_dict({'augmentation': {'random_crop': '1', 'random_flip_horizontally': '0.5'}})
+    by_size = {}
+    for seed, h0, w0, h, w, flip in g['cases'].tolist():
+        src = O.synth_frame(seed, h0, w0)
+        yx_min, yx_max = g['c%d_yx_min_in' % seed], g['c%d_yx_max_in' % seed]
+        # boxes after the flip decide the window (the reference crops the flipped image)
+        fmin, fmax = yx_min.copy(), yx_max.copy()
+        if flip:
+            t = w0 - fmin[:, 1]
+            fmin[:, 1] = w0 - fmax[:, 1]
+            fmax[:, 1] = t
+        window, margin = transform.resize.label.crop_window(1.0, fmin, fmax, (h0, w0), g['c%d_draws' % seed])
+        out, a, b = transform.resize_batch([torch.from_numpy(src)], h, w, bgr2rgb=False, yx_min=torch.from_numpy(yx_min)[None], yx_max=torch.from_numpy(yx_max)[None],
+                                           flip=[bool(flip)], crop=[window], margin=[margin.tolist()])
+        assert hashlib.sha256(out[0].cpu().numpy().tobytes()).digest() == g['c%d_sha' % seed].tobytes(), 'case %d pixels' % seed
+        assert np.array_equal(a[0].cpu().numpy(), g['c%d_yx_min' % seed]) and np.array_equal(b[0].cpu().numpy(), g['c%d_yx_max' % seed]), 'case %d boxes' % seed
+        by_size.setdefault((h, w), []).append((seed, src, yx_min, yx_max, bool(flip), window, margin))
+        # the single-image mirror with the reference's own np.random draw
+        image, bmin, bmax = src, yx_min.copy(), yx_max.copy()
+        if flip:
+            image, bmin, bmax = transform.augmentation.flip_horizontally(image, bmin, bmax)
+        np.random.seed(200 + seed)
+        image, bmin, bmax = transform.resize.label.random_crop(cfg, image, bmin, bmax, h, w)
+        assert hashlib.sha256(image.cpu().numpy().tobytes()).digest() == g['c%d_sha' % seed].tobytes(), 'case %d (mirror)' % seed
+        assert np.array_equal(bmin.cpu().numpy(), g['c%d_yx_min' % seed])
+    # several ragged frames of one target size in ONE launch
+    (h, w), group = max(by_size.items(), key=lambda kv: len(kv[1]))
+    slots = max(len(c[2]) for c in group)
+    pmin = torch.zeros(len(group), slots, 2)
+    pmax = torch.zeros(len(group), slots, 2)
+    for i, c in enumerate(group):
+        pmin[i, :len(c[2])], pmax[i, :len(c[3])] = torch.from_numpy(c[2]), torch.from_numpy(c[3])
+    out, a, b = transform.resize_batch([torch.from_numpy(c[1]) for c in group], h, w, bgr2rgb=False, yx_min=pmin, yx_max=pmax,
+                                       flip=[c[4] for c in group], crop=[c[5] for c in group], margin=[c[6].tolist() for c in group])
+    for i, c in enumerate(group):
+        assert hashlib.sha256(out[i].cpu().numpy().tobytes()).digest() == g['c%d_sha' % c[0]].tobytes()
+        assert np.array_equal(a[i, :len(c[2])].cpu().numpy(), g['c%d_yx_min' % c[0]])
+    # stand-alone flip
+    f, a, b = transform.augmentation.flip_horizontally(g['flip_src'], g['flip_min_in'].copy(), g['flip_max_in'].copy())
+    assert np.array_equal(f.cpu().numpy(), g['flip_out']) and np.array_equal(a.cpu().numpy(), g['flip_min']) and np.array_equal(b.cpu().numpy(), g['flip_max'])
+
+
 def test_collate_gpu_batch_and_training_step_from_uint8_frames():
     """utils.data.Collate: a list of decoded BGR frames of different sizes + ragged labels -> one GPU batch at the scheduled
     size (frames bit-identical to cv2.resize + BGR2RGB, boxes scaled like transform.resize.label.rescale, labels zero-padded

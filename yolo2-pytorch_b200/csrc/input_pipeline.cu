@@ -96,6 +96,89 @@ __global__ void totensor_u8_kernel(const uint8_t* __restrict__ src, float* __res
   for (int c = 0; c < 3; ++c) d[static_cast<long long>(c) * hw] = __fdiv_rn(static_cast<float>(s[c]), 255.f);
 }
 
+// Augmented form (the default training resize `resize_train = transform.resize.label.RandomCrop`, config.ini:48, after the optional
+// `transform.augmentation.RandomFlipHorizontally`, config.ini:47): out = cv2.resize(crop(flip(image))).  Both are pure index transforms on
+// the SOURCE of the same bit-exact resize: a flipped image's column j is column (w - 1 - j) (cv2.flip(image, 1), augmentation.py:87-95),
+// the crop image[y0:y1, x0:x1] (resize/label.py:73) an offset window.  crop: int[B][4] = (y0, x0, y1, x1) in the (flipped) frame or NULL;
+// flip: uint8[B] or NULL.
+__global__ void __launch_bounds__(256) resize_aug_u8_kernel(const uint8_t* __restrict__ src, const long long* __restrict__ src_off,
+                                                            const int* __restrict__ src_hw, const int* __restrict__ crop,
+                                                            const uint8_t* __restrict__ flip, uint8_t* __restrict__ dst, int height, int width,
+                                                            int swap_rb) {
+  const int img = blockIdx.y;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= height * width) return;
+  const int dy = idx / width, dx = idx - dy * width;
+  const int sw = src_hw[2 * img + 1];
+  int y0 = 0, x0 = 0, eh = src_hw[2 * img], ew = sw;
+  if (crop != nullptr) { y0 = crop[4 * img]; x0 = crop[4 * img + 1]; eh = crop[4 * img + 2] - y0; ew = crop[4 * img + 3] - x0; }
+  const bool fl = flip != nullptr && flip[img] != 0;
+  const uint8_t* s = src + src_off[img];
+  const ResizeCoef cx = resize_coef(dx, width, ew, true);
+  const ResizeCoef cy = resize_coef(dy, height, eh, false);
+  const uint8_t* r0 = s + static_cast<long long>(y0 + cy.s0) * sw * 3;
+  const uint8_t* r1 = s + static_cast<long long>(y0 + cy.s1) * sw * 3;
+  const int c0 = fl ? sw - 1 - (x0 + cx.s0) : x0 + cx.s0;
+  const int c1 = fl ? sw - 1 - (x0 + cx.s1) : x0 + cx.s1;
+  uint8_t out[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int h0 = static_cast<int>(r0[c0 * 3 + c]) * cx.a0 + static_cast<int>(r0[c1 * 3 + c]) * cx.a1;
+    const int h1 = static_cast<int>(r1[c0 * 3 + c]) * cx.a0 + static_cast<int>(r1[c1 * 3 + c]) * cx.a1;
+    int v = (((cy.a0 * (h0 >> 4)) >> 16) + ((cy.a1 * (h1 >> 4)) >> 16) + 2) >> 2;
+    v = v < 0 ? 0 : (v > 255 ? 255 : v);
+    out[c] = static_cast<uint8_t>(v);
+  }
+  uint8_t* d = dst + (static_cast<long long>(img) * height * width + idx) * 3;
+  d[0] = swap_rb ? out[2] : out[0];
+  d[1] = out[1];
+  d[2] = swap_rb ? out[0] : out[2];
+}
+
+// boxes, in the reference's order and float32 arithmetic: flip (x' = w - x, min / max swapped; augmentation.py:91-94), crop
+// (yx -= margin, the UN-truncated float32 margin; resize/label.py:74), scale by (height / crop_h, width / crop_w) (resize/label.py:27-30)
+__global__ void augment_boxes_kernel(float* __restrict__ yx_min, float* __restrict__ yx_max, const int* __restrict__ src_hw, const int* __restrict__ crop,
+                                     const float* __restrict__ margin, const uint8_t* __restrict__ flip, int batch, int slots, int height, int width) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch * slots) return;
+  const int img = i / slots;
+  float ymin = yx_min[2 * i], xmin = yx_min[2 * i + 1], ymax = yx_max[2 * i], xmax = yx_max[2 * i + 1];
+  const int sw = src_hw[2 * img + 1];
+  int eh = src_hw[2 * img], ew = sw;
+  if (flip != nullptr && flip[img] != 0) {
+    const float w = static_cast<float>(sw);
+    const float t = __fsub_rn(w, xmin);
+    xmin = __fsub_rn(w, xmax);
+    xmax = t;
+  }
+  if (crop != nullptr) {
+    eh = crop[4 * img + 2] - crop[4 * img]; ew = crop[4 * img + 3] - crop[4 * img + 1];
+    const float my = margin[2 * img], mx = margin[2 * img + 1];
+    ymin = __fsub_rn(ymin, my); xmin = __fsub_rn(xmin, mx); ymax = __fsub_rn(ymax, my); xmax = __fsub_rn(xmax, mx);
+  }
+  const float sy = static_cast<float>(static_cast<double>(height) / static_cast<double>(eh));
+  const float sx = static_cast<float>(static_cast<double>(width) / static_cast<double>(ew));
+  yx_min[2 * i] = __fmul_rn(ymin, sy); yx_min[2 * i + 1] = __fmul_rn(xmin, sx);
+  yx_max[2 * i] = __fmul_rn(ymax, sy); yx_max[2 * i + 1] = __fmul_rn(xmax, sx);
+}
+
+int resize_aug_batch_u8(const void* src, const long long* src_off, const int* src_hw, const int* crop, const float* margin, const unsigned char* flip,
+                        void* dst, int batch, int height, int width, int swap_rb, float* yx_min, float* yx_max, int slots, cudaStream_t stream) {
+  YB_REQUIRE(src && src_off && src_hw && dst && batch > 0 && height > 0 && width > 0, "resize_aug_batch_u8: bad argument");
+  YB_REQUIRE((yx_min == nullptr) == (yx_max == nullptr) && slots >= 0, "resize_aug_batch_u8: boxes come as a (yx_min, yx_max) pair");
+  YB_REQUIRE(crop == nullptr || margin != nullptr || yx_min == nullptr, "resize_aug_batch_u8: cropping boxes needs the float margins");
+  const int pixels = height * width;
+  resize_aug_u8_kernel<<<dim3((pixels + 255) / 256, batch), 256, 0, stream>>>(static_cast<const uint8_t*>(src), src_off, src_hw, crop, flip,
+                                                                              static_cast<uint8_t*>(dst), height, width, swap_rb);
+  int rc = check_launch("resize_aug_u8_kernel");
+  if (rc) return rc;
+  if (yx_min != nullptr && slots > 0) {
+    augment_boxes_kernel<<<(batch * slots + 127) / 128, 128, 0, stream>>>(yx_min, yx_max, src_hw, crop, margin, flip, batch, slots, height, width);
+    rc = check_launch("augment_boxes_kernel");
+  }
+  return rc;
+}
+
 int totensor_u8(const void* src, float* dst, int batch, int height, int width, cudaStream_t stream) {
   YB_REQUIRE(src && dst && batch > 0 && height > 0 && width > 0, "totensor_u8: bad argument");
   const long long total = static_cast<long long>(batch) * height * width;
