@@ -289,13 +289,14 @@ def filter_nms(score, yx_min, yx_max, prob, mode, threshold, threshold_cls, over
     num_cls = prob.shape[-1] if prob is not None else 1
     dev = score.device
     i32 = dict(dtype=torch.int32, device=dev)
-    res = dict(n_filtered=torch.zeros(b, **i32), n_keep=torch.zeros(b, **i32),
+    # every count is written by the image's CTA on every path (csrc/nms.cu), so no zero-fill launches precede the kernel
+    res = dict(n_filtered=torch.empty(b, **i32), n_keep=torch.empty(b, **i32),
                keep_idx=torch.empty(b, limit, **i32), keep_box=torch.empty(b, limit, **i32))
     n_det = det_keep = det_cls = det_score = None
     det_cap = 0
     if expand:
         det_cap = limit * num_cls
-        n_det = res['n_det'] = torch.zeros(b, **i32)
+        n_det = res['n_det'] = torch.empty(b, **i32)
         det_keep = res['det_keep'] = torch.empty(b, det_cap, **i32)
         det_cls = res['det_cls'] = torch.empty(b, det_cap, **i32)
         det_score = res['det_score'] = torch.empty(b, det_cap, dtype=torch.float32, device=dev)

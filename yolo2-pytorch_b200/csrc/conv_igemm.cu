@@ -866,8 +866,10 @@ struct C32Cfg {
   static constexpr int kBBytes = 9 * kBTap;                       // 36 KB resident
   static constexpr int kOutBytes = 128 * 128;                     // staging tile for the TMA store (2 per epilogue group)
   static constexpr int kAccStages = 4;
-  static constexpr int kThreads = 64 + 256;
-  static constexpr int kSmemBytes = 1024 + kBBytes + 4 * kOutBytes + kStages * kHalo + 2 * BN * 4 + 256;
+  static constexpr int kGroups = 3;                               // epilogue groups of four warps (tools/conv_ablate.py: the per-tile epilogue chain, not the MMA, bounds this kernel)
+  static constexpr int kEpiThreads = kGroups * 128;
+  static constexpr int kThreads = 64 + kEpiThreads;
+  static constexpr int kSmemBytes = 1024 + kBBytes + 2 * kGroups * kOutBytes + kStages * kHalo + 2 * BN * 4 + 256;
 };
 
 __global__ void __launch_bounds__(C32Cfg::kThreads, 1)
@@ -880,8 +882,8 @@ conv_c32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t smem_b = smem_base;
   const uint32_t smem_o = smem_b + Cfg::kBBytes;
-  const uint32_t smem_h = smem_o + 4 * Cfg::kOutBytes;
-  float* ep_scale = reinterpret_cast<float*>(smem_gen + Cfg::kBBytes + 4 * Cfg::kOutBytes + Cfg::kStages * Cfg::kHalo);
+  const uint32_t smem_h = smem_o + 2 * Cfg::kGroups * Cfg::kOutBytes;
+  float* ep_scale = reinterpret_cast<float*>(smem_gen + Cfg::kBBytes + 2 * Cfg::kGroups * Cfg::kOutBytes + Cfg::kStages * Cfg::kHalo);
   float* ep_shift = ep_scale + BN;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ep_shift + BN);
   const uint32_t bar_full = smem_u32(bars);
@@ -961,19 +963,19 @@ conv_c32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       }
     }
   } else {
-    // Two independent epilogue groups of four warps take alternate tiles: one tile's epilogue is a chain of latencies
+    // Independent epilogue groups of four warps take the tiles round-robin: one tile's epilogue is a chain of latencies
     // (tcgen05.ld, two named barriers, the async-proxy fence, the TMA store issue -- ~1300 cycles even with nothing else
-    // running, see profiles/r01_conv_trace.txt), so two of them in flight roughly double the tile rate.
+    // running, see profiles/r01_conv_trace.txt), so kGroups of them in flight multiply the tile rate.
     const int q = warp & 3;                 // TMEM lane quarter: tile rows 4q .. 4q+3
     const int grp = (warp - 2) >> 2;
     const int gt = (threadIdx.x - 64) & 127;
     const int et = threadIdx.x - 64;
     int tr = 0;
-    for (int i = et; i < BN; i += 256) {
+    for (int i = et; i < BN; i += Cfg::kEpiThreads) {
       ep_scale[i] = (i < p.cout) ? __ldg(p.scale + i) : 0.f;
       ep_shift[i] = (i < p.cout) ? __ldg(p.shift + i) : 0.f;
     }
-    asm volatile("bar.sync 3, 256;" ::: "memory");
+    asm volatile("bar.sync 8, %0;" :: "n"(Cfg::kEpiThreads) : "memory");
     const int m = q * 32 + lane;            // tile-local pixel: row m >> 3, column m & 7
     int srow = m;
     bool writer = true;
@@ -983,7 +985,7 @@ conv_c32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     }
     int local = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
-      if ((local & 1) != grp) continue;
+      if (local % Cfg::kGroups != grp) continue;
       const int acc = local & 3;
       const uint32_t acc_phase = (local >> 2) & 1;
       const int tw = tile % p.tiles_w;
@@ -1029,16 +1031,16 @@ conv_c32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           pk[half * 4 + g].z = *reinterpret_cast<uint32_t*>(&h2); pk[half * 4 + g].w = *reinterpret_cast<uint32_t*>(&h3);
         }
       }
-      const uint32_t obuf = smem_o + (grp * 2 + ((local >> 1) & 1)) * Cfg::kOutBytes;
+      const uint32_t obuf = smem_o + (grp * 2 + ((local / Cfg::kGroups) & 1)) * Cfg::kOutBytes;
       if (gt == 0) tma_store_wait_read<1>();      // this group's store from two of its tiles ago has drained the buffer
-      if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+      asm volatile("bar.sync %0, 128;" :: "r"(1 + grp) : "memory");
       if (et == 0) { YB_TRACE(2, tr); ++tr; }
       if (writer) {
 #pragma unroll
         for (int c = 0; c < 8; ++c) st_shared_v4(obuf + srow * 128 + ((c ^ (srow & 7)) << 4), pk[c]);
       }
       fence_proxy_async_smem();
-      if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+      asm volatile("bar.sync %0, 128;" :: "r"(1 + grp) : "memory");
       if (gt == 0 && !(p.skip & 8)) {
         if (p.pool) tma_store_4d(&tmap_y, obuf, 0, tw * (Cfg::TW / 2), th * (Cfg::TH / 2), n);
         else tma_store_4d(&tmap_y, obuf, 0, tw * Cfg::TW, th * Cfg::TH, n);
