@@ -35,6 +35,15 @@ def extract(path, names):
     return ns
 
 
+def extract_with_classes(path, names, extra):
+    tree = ast.parse(open(path).read())
+    nodes = [n for n in tree.body if isinstance(n, (ast.FunctionDef, ast.ClassDef)) and n.name in names]
+    ns = dict(np=np, cv2=cv2, inspect=inspect)
+    ns.update(extra)
+    exec(compile(ast.Module(body=nodes, type_ignores=[]), path, 'exec'), ns)
+    return ns
+
+
 def main():
     lab = extract(os.path.join(REF, 'transform', 'resize', 'label.py'), ('rescale', 'resize', 'random_crop'))
     aug = extract(os.path.join(REF, 'transform', 'augmentation.py'), ('flip_horizontally',))
@@ -62,6 +71,29 @@ def main():
     bmin, bmax = np.array([[3.0, 5.0], [10.0, 20.5]], np.float32), np.array([[30.0, 40.0], [33.25, 50.0]], np.float32)
     f, a, b = aug['flip_horizontally'](small, bmin.copy(), bmax.copy())
     out['flip_src'], out['flip_out'], out['flip_min_in'], out['flip_max_in'], out['flip_min'], out['flip_max'] = small, f, bmin, bmax, a, b
+    # rotation (transform/augmentation.py:28-76): the reference's Rotator + random_rotate executed with cv2, angles drawn by random.uniform
+    import random
+    rot = extract_with_classes(os.path.join(REF, 'transform', 'augmentation.py'), ('Rotator', 'random_rotate'), dict(random=random))
+    cfg_rot = configparser.ConfigParser()
+    cfg_rot.read_dict({'augmentation': {'random_rotate': '-7 7'}})
+    for seed, h0, w0 in ((0, 120, 160), (1, 333, 500), (2, 97, 61), (3, 416, 416)):
+        src = O.synth_frame(20 + seed, h0, w0)
+        g = np.random.RandomState(300 + seed)
+        yx_min = (g.rand(3, 2) * np.array([h0 * 0.5, w0 * 0.5])).astype(np.float32)
+        yx_max = (yx_min + g.rand(3, 2) * np.array([h0 * 0.4, w0 * 0.4]) + 2).astype(np.float32)
+        random.seed(400 + seed)
+        image, a, b = rot['random_rotate'](cfg_rot, src, yx_min.copy(), yx_max.copy())
+        out['r%d_dims' % seed] = np.array([h0, w0, image.shape[0], image.shape[1]])
+        out['r%d_sha' % seed] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(image).tobytes()).digest(), np.uint8)
+        out['r%d_yx_min_in' % seed], out['r%d_yx_max_in' % seed], out['r%d_yx_min' % seed], out['r%d_yx_max' % seed] = yx_min, yx_max, a, b
+    out['rot_cases'] = np.array([0, 1, 2, 3])
+    # `fixed` (transform/resize/image.py:36-46), shrinking cases (warpAffine runs INTER_AREA as INTER_LINEAR)
+    fx = extract(os.path.join(REF, 'transform', 'resize', 'image.py'), ('fixed',))
+    for seed, h0, w0, h, w in ((0, 375, 500, 320, 320), (1, 480, 640, 416, 416), (2, 900, 500, 416, 608)):
+        src = O.synth_frame(30 + seed, h0, w0)
+        r = fx['fixed'](src, h, w)
+        out['f%d_dims' % seed] = np.array([h0, w0, h, w])
+        out['f%d_sha' % seed] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(r).tobytes()).digest(), np.uint8)
     path = os.path.join(HERE, 'augment.npz')
     np.savez_compressed(path, **out)
     print('augment.npz %.1f KB' % (os.path.getsize(path) / 1024))

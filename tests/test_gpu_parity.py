@@ -1349,6 +1349,35 @@ def test_flip_and_random_crop_bit_exact_vs_executed_reference(golden_dir):
     assert np.array_equal(f.cpu().numpy(), g['flip_out']) and np.array_equal(a.cpu().numpy(), g['flip_min']) and np.array_equal(b.cpu().numpy(), g['flip_max'])
 
 
+def test_rotate_and_fixed_bit_exact_vs_executed_reference(golden_dir):
+    """cv2.warpAffine's 8-bit bilinear path on the device (yb_warp_affine_u8): the reference's `random_rotate` (Rotator: canvas grown to the
+    rotated hull, zero fill, box hulls) with its own `random.uniform` draw, and `transform.resize.image.fixed` when it shrinks -- frames
+    bit-identical (SHA-256) to the reference functions executed with cv2 (tests/golden/make_golden_augment.py), boxes equal in float32."""
+    import hashlib
+    import random
+    import configparser
+    import transform.augmentation
+    import transform.resize.image
+    g = np.load(os.path.join(golden_dir, 'augment.npz'))
+    cfg = configparser.ConfigParser()
+    cfg.read_dict({'augmentation': {'random_rotate': '-7 7'}})
+    for seed in g['rot_cases'].tolist():
+        h0, w0, h1, w1 = g['r%d_dims' % seed].tolist()
+        src = O.synth_frame(20 + seed, h0, w0)
+        random.seed(400 + seed)
+        image, a, b = transform.augmentation.random_rotate(cfg, src, g['r%d_yx_min_in' % seed].copy(), g['r%d_yx_max_in' % seed].copy())
+        assert tuple(image.shape) == (h1, w1, 3), (seed, image.shape)
+        assert hashlib.sha256(image.cpu().numpy().tobytes()).digest() == g['r%d_sha' % seed].tobytes(), 'rotation case %d pixels' % seed
+        assert np.array_equal(a, g['r%d_yx_min' % seed]) and np.array_equal(b, g['r%d_yx_max' % seed]), 'rotation case %d boxes' % seed
+    for seed in range(3):
+        h0, w0, h, w = g['f%d_dims' % seed].tolist()
+        r = transform.resize.image.fixed(O.synth_frame(30 + seed, h0, w0), h, w)
+        assert tuple(r.shape) == (h, w, 3)
+        assert hashlib.sha256(r.cpu().numpy().tobytes()).digest() == g['f%d_sha' % seed].tobytes(), 'fixed case %d' % seed
+    with pytest.raises(NotImplementedError):
+        transform.resize.image.fixed(O.synth_frame(1, 100, 100), 416, 416)
+
+
 def test_collate_gpu_batch_and_training_step_from_uint8_frames():
     """utils.data.Collate: a list of decoded BGR frames of different sizes + ragged labels -> one GPU batch at the scheduled
     size (frames bit-identical to cv2.resize + BGR2RGB, boxes scaled like transform.resize.label.rescale, labels zero-padded

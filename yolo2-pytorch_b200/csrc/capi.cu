@@ -95,6 +95,7 @@ int head_grad_prepare(const float*, void*, float*, int, int, int, int, cudaStrea
 int conv0_wgrad(const float*, const void*, float*, int, int, int, cudaStream_t);
 int resize_batch_u8(const void*, const long long*, const int*, void*, int, int, int, int, float*, float*, int, cudaStream_t);
 int totensor_u8(const void*, float*, int, int, int, cudaStream_t);
+int warp_affine_u8(const void*, int, int, void*, int, int, const double*, const int*, cudaStream_t);
 int resize_aug_batch_u8(const void*, const long long*, const int*, const int*, const float*, const unsigned char*, void*, int, int, int, int, float*, float*,
                         int, cudaStream_t);
 int eval_match(const float*, const float*, const int*, const int*, const float*, const float*, const int*, const int*, int, int, int, float, float,
@@ -318,6 +319,11 @@ int yb_resize_batch_u8(const void* src, const long long* src_off, const int* src
 int yb_resize_aug_batch_u8(const void* src, const long long* src_off, const int* src_hw, const int* crop, const float* margin, const unsigned char* flip,
                            void* dst, int batch, int height, int width, int swap_rb, float* yx_min, float* yx_max, int slots, yb_stream_t stream) {
   return yb::resize_aug_batch_u8(src, src_off, src_hw, crop, margin, flip, dst, batch, height, width, swap_rb, yx_min, yx_max, slots, S(stream));
+}
+
+int yb_warp_affine_u8(const void* src, int src_h, int src_w, void* dst, int dst_h, int dst_w, const double* inverse_matrix6, const int* fill3,
+                      yb_stream_t stream) {
+  return yb::warp_affine_u8(src, src_h, src_w, dst, dst_h, dst_w, inverse_matrix6, fill3, S(stream));
 }
 
 int yb_totensor_u8(const void* src_nhwc_u8, float* dst_nchw_f32, int batch, int height, int width, yb_stream_t stream) {

@@ -179,6 +179,65 @@ int resize_aug_batch_u8(const void* src, const long long* src_off, const int* sr
   return rc;
 }
 
+// ------------------------------------------------------------------------------------------------
+// cv2.warpAffine(image, M, (dw, dh), flags=INTER_LINEAR, borderMode=BORDER_CONSTANT, borderValue=fill) for uint8 HWC frames, bit-exact:
+// the arithmetic of the reference's `Rotator.__call__` (transform/augmentation.py:46-49, used by `random_rotate` :61-76) and of
+// `transform.resize.image.fixed` (transform/resize/image.py:36-46; INTER_AREA is INTER_LINEAR inside warpAffine).  It lives in the
+// reference's third-party dependency, so it is restated from OpenCV's published algorithm (imgproc imgwarp.cpp: warpAffine + remapBilinear,
+// 8-bit fixed-point path) and pinned by fixtures made with cv2 itself:
+//   the caller passes the INVERTED matrix (double); X0 = cvRound((m01*y + m02)*1024) + 16, adelta = cvRound(m00*x*1024) (likewise Y);
+//   X = (X0 + adelta) >> 5; source pixel sx = X >> 5 with the 5-bit fraction X & 31; bilinear weights (32-fy)(32-fx)*32 ... as int16
+//   (saturated to 32767, the remainder added to the last tap so they sum to 32768); out = (sum + 2^14) >> 15; taps outside the
+//   frame read `fill`.
+__global__ void __launch_bounds__(256) warp_affine_u8_kernel(const uint8_t* __restrict__ src, int sh, int sw, uint8_t* __restrict__ dst, int dh, int dw,
+                                                             double m00, double m01, double m02, double m10, double m11, double m12, int fill0,
+                                                             int fill1, int fill2) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= dh * dw) return;
+  const int y = idx / dw, x = idx - y * dw;
+  auto sat = [](double v) -> long long {
+    const long long r = __double2ll_rn(v);
+    return r < -2147483648ll ? -2147483648ll : (r > 2147483647ll ? 2147483647ll : r);
+  };
+  const long long X0 = sat((m01 * static_cast<double>(y) + m02) * 1024.0) + 16;
+  const long long Y0 = sat((m11 * static_cast<double>(y) + m12) * 1024.0) + 16;
+  const long long X = (X0 + sat(m00 * static_cast<double>(x) * 1024.0)) >> 5;
+  const long long Y = (Y0 + sat(m10 * static_cast<double>(x) * 1024.0)) >> 5;
+  long long sxl = X >> 5, syl = Y >> 5;
+  sxl = sxl < -32768 ? -32768 : (sxl > 32767 ? 32767 : sxl);
+  syl = syl < -32768 ? -32768 : (syl > 32767 ? 32767 : syl);
+  const int sx = static_cast<int>(sxl), sy = static_cast<int>(syl);
+  const int fx = static_cast<int>(X & 31), fy = static_cast<int>(Y & 31);
+  int w[4] = {(32 - fy) * (32 - fx) * 32, (32 - fy) * fx * 32, fy * (32 - fx) * 32, fy * fx * 32};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) w[k] = w[k] > 32767 ? 32767 : w[k];
+  w[3] += 32768 - (w[0] + w[1] + w[2] + w[3]);
+  const int fill[3] = {fill0, fill1, fill2};
+  int acc[3] = {0, 0, 0};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int yy = sy + (k >> 1), xx = sx + (k & 1);
+    const bool inside = yy >= 0 && yy < sh && xx >= 0 && xx < sw;
+    const uint8_t* sp = src + (static_cast<long long>(inside ? yy : 0) * sw + (inside ? xx : 0)) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) acc[c] += (inside ? static_cast<int>(sp[c]) : fill[c]) * w[k];
+  }
+  uint8_t* d = dst + static_cast<long long>(idx) * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    int v = (acc[c] + (1 << 14)) >> 15;
+    d[c] = static_cast<uint8_t>(v < 0 ? 0 : (v > 255 ? 255 : v));
+  }
+}
+
+int warp_affine_u8(const void* src, int sh, int sw, void* dst, int dh, int dw, const double* minv, const int* fill, cudaStream_t stream) {
+  YB_REQUIRE(src && dst && minv && fill && sh > 0 && sw > 0 && dh > 0 && dw > 0 && static_cast<long long>(dh) * dw < (1ll << 31), "warp_affine_u8: bad argument");
+  const int pixels = dh * dw;
+  warp_affine_u8_kernel<<<(pixels + 255) / 256, 256, 0, stream>>>(static_cast<const uint8_t*>(src), sh, sw, static_cast<uint8_t*>(dst), dh, dw, minv[0], minv[1],
+                                                                 minv[2], minv[3], minv[4], minv[5], fill[0], fill[1], fill[2]);
+  return check_launch("warp_affine_u8_kernel");
+}
+
 int totensor_u8(const void* src, float* dst, int batch, int height, int width, cudaStream_t stream) {
   YB_REQUIRE(src && dst && batch > 0 && height > 0 && width > 0, "totensor_u8: bad argument");
   const long long total = static_cast<long long>(batch) * height * width;

@@ -3,7 +3,8 @@
 `transform.image.BGR2RGB`, and the batched `transform.resize_batch` that does all three for a whole batch of decoded
 frames in one launch -- optionally through the horizontal flip and the random-crop window of the reference's training pipeline
 (`transform.augmentation.flip_horizontally`, `transform.resize.label.random_crop`), which are index transforms on the source of the same
-resize.  `random_rotate` and the photometric augmentations of `transform/image.py` are not part of this build."""
+resize; `transform.augmentation.random_rotate` / `Rotator` and `transform.resize.image.fixed` (shrinking) run cv2.warpAffine's bilinear path in
+one kernel.  The photometric augmentations of `transform/image.py` (blur / hue / saturation / brightness / gamma) are not part of this build."""
 import torch
 
 from b200 import ops as _ops
