@@ -559,11 +559,11 @@ def make_tiny_state_dict(seed=0, num_anchors=5, num_cls=20):
     return sd
 
 
-def tiny_forward(sd, x, num_anchors=5, num_cls=20, collect=None):
+def tiny_forward(sd, x, num_anchors=5, num_cls=20, collect=None, train=False, stats=None):
     """model/yolo2.py:167-168 (`self.layers(x)`): conv units, MaxPool2d(2) x5, then ConstantPad2d((0,1,0,1), float32
     min) + MaxPool2d(2, stride=1) after the sixth conv.  `collect` receives every conv unit's (pre-pool) output."""
     for l in tiny_layers(num_anchors, num_cls):
-        x = conv_unit(x, sd, l['key'], l['k'], l['bn'], l['act'])
+        x = conv_unit(x, sd, l['key'], l['k'], l['bn'], l['act'], train, stats)
         if collect is not None:
             collect[l['key']] = x
         if l['after'] == 'pool':

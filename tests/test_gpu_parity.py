@@ -1213,6 +1213,92 @@ def test_tiny_plugin_vs_reference_golden(golden_dir):
 # ------------------------------------------------------------------------------------------------
 # Evaluation matching on the device (reference eval.py:57-75)
 # ------------------------------------------------------------------------------------------------
+def test_maxpool_stride1_backward_vs_torch(ops):
+    """yb_maxpool2x2_s1_bwd_f16 (training of Tiny): gradient routed to the first maximum of every window, vs torch autograd through
+    F.pad(-inf-like) + max_pool2d(2, stride=1) on fp16-representable data with deliberate ties."""
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(3, 13, 13, 64, generator=gen).half()
+    x[0, :4, :4, :16] = 0.5                                  # ties: the first element of the window wins
+    dy = torch.randn(3, 13, 13, 64, generator=gen).half()
+    xr = x.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    y = torch.nn.functional.max_pool2d(torch.nn.functional.pad(xr, (0, 1, 0, 1), value=float(np.finfo(np.float32).min)), 2, stride=1)
+    y.backward(dy.float().permute(0, 3, 1, 2))
+    dx = torch.empty_like(x, device=DEV)
+    ops.call('yb_maxpool2x2_s1_bwd_f16', x.to(DEV), dy.to(DEV), dx, 3, 13, 13, 64)
+    ref = xr.grad.permute(0, 2, 3, 1)
+    assert rel_err(dx, ref) <= 2e-3                          # sums of up to four fp16 gradients, rounded once to fp16
+
+
+def test_tiny_training_step_vs_oracle_and_descent():
+    """model.yolo2.Tiny in train() mode (the reference's default `model/dnn`, config.ini:25; model/yolo2.py:140-173): one step --
+    train-mode forward (batch-statistics BN, the 16-filter first layer on the zero-padded 32-filter kernels, MaxPool2d(2) x5, pad + stride-1
+    pool), region loss, full backward -- against the oracle's arithmetic with torch autograd on CPU: feature, losses, every parameter
+    gradient (cosine / relative L2; 8 BatchNorm layers amplify fp16 roundings far less than Darknet-19's 22), running statistics; the
+    padding channels stay exactly zero; and 15 SGD steps on one batch reduce the loss."""
+    import model
+    import model.yolo2
+    import train as yb_train
+    cfg = make_config(1)
+    cfg.read_dict({'model': {'threshold': '0.6'}, 'hparam': {'foreground': '5', 'background': '1', 'center': '1', 'size': '1', 'cls': '1'},
+                   'train': {'cross_entropy': '1'}})
+    anchors = O.anchors_yolo_voc()
+    sd0 = O.make_tiny_state_dict(0)
+    b, size = 8, 160
+    s = size // 32
+    x = O.synth_images(b, size, size, seed=70)
+    data = O.norm_data(O.synth_targets(b, size, size, slots=5, seed=71), size, size, s, s)
+    # oracle step
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'running' not in k else v.clone()) for k, v in sd0.items()}
+    stats = {}
+    f_ref = O.tiny_forward(sd, x, train=True, stats=stats)
+    l_ref, _ = O.loss(anchors, data, O.decode(f_ref, anchors), 0.6)
+    O.loss_total(l_ref).backward()
+    # CUDA step
+    dnn = model.yolo2.Tiny(model.ConfigChannels(cfg), anchors, 20)
+    dnn.load_state_dict(sd0, strict=False)
+    dnn = dnn.to(DEV).train()
+    inference = model.Inference(cfg, dnn, anchors).train()
+    pred = model._inference(inference, x.to(DEV))
+    losses, _ = model.loss(anchors, {k: v.to(DEV) for k, v in data.items()}, pred, 0.6)
+    sum(losses[k] * O.HPARAM_DEFAULT[k] for k in losses).backward()
+    e_f = rel_err(pred['feature'], f_ref)
+    e_loss = {k: abs(losses[k].item() - l_ref[k].item()) / abs(l_ref[k].item()) for k in losses}
+    worst_cos, worst_rel = (1.0, None), (0.0, None)
+    for name, p in dnn.named_parameters():
+        assert p.grad is not None and bool(torch.isfinite(p.grad).all()), name
+        g, r = p.grad.detach().float().cpu().flatten(), sd[name].grad.flatten()
+        cos = (torch.dot(g, r) / (g.norm() * r.norm() + 1e-30)).item()
+        rel = ((g - r).norm() / (r.norm() + 1e-30)).item()
+        if cos < worst_cos[0]:
+            worst_cos = (cos, name)
+        if rel > worst_rel[0]:
+            worst_rel = (rel, name)
+    e_run = 0.0
+    for key, (mean, var) in stats.items():
+        rm = dict(dnn.named_buffers())[key + '.bn.running_mean'].cpu()
+        exp = 0.99 * sd0[key + '.bn.running_mean'] + 0.01 * mean.detach()
+        e_run = max(e_run, rel_err(rm, exp))
+    record('tiny_train_step', dict(feature=e_f, losses=e_loss, worst_grad_cosine=worst_cos, worst_grad_rel_l2=worst_rel, running_mean=e_run))
+    tr = dnn.trainer
+    assert bool((tr._zero_bufs[('z0', b, size, size)][..., 16:] == 0).all()) and bool((tr._zero_bufs[('a0', b, size, size)][..., 16:] == 0).all())
+    assert e_f <= 3e-2, e_f
+    for k, v in e_loss.items():
+        assert v <= 2e-2, (k, v)
+    assert worst_cos[0] >= 0.95, worst_cos
+    assert worst_rel[0] <= 0.3, worst_rel
+    assert e_run <= 1e-3, e_run
+    # descent on one batch
+    opt = torch.optim.SGD(dnn.parameters(), 1e-3, momentum=0.9)
+    batch = dict(tensor=x, yx_min=O.synth_targets(b, size, size, slots=5, seed=71)['yx_min'], yx_max=O.synth_targets(b, size, size, slots=5, seed=71)['yx_max'],
+                 cls=O.synth_targets(b, size, size, slots=5, seed=71)['cls'])
+    hist = [float(yb_train.iterate(inference, opt, anchors, cfg, batch)['loss_total'].item()) for _ in range(15)]
+    assert hist[-1] < 0.9 * hist[0], hist
+    # and back to inference on the trained weights (operand caches are dropped by train(False))
+    dnn.eval()
+    f = dnn(x[:2].to(DEV))
+    assert f.shape == (2, 125, s, s) and bool(torch.isfinite(f).all())
+
+
 def test_eval_matching_vs_reference_golden(golden_dir):
     """yb_eval_match (one launch for the whole ragged batch) and the per-class drop-in eval.matching: true-positive
     flags bit-identical to the reference's, incl. images without ground truth / without detections."""

@@ -362,3 +362,191 @@ class DarknetTrainer(object):
             self.found_inf = torch.zeros((), dtype=torch.float32, device=dev)      # 0-dim like GradScaler's (fused optimizers subtract it from their step counters)
         ops.call('yb_grad_guard', self.arena.flat, self.arena.flat.numel(), self.found_inf, 1)
         return grads
+
+
+class TinyTrainer(DarknetTrainer):
+    """Training-mode forward / backward of `model.yolo2.Tiny` (reference model/yolo2.py:140-173) on the same kernels: a plain chain of
+    conv units, five of them followed by MaxPool2d(2) (fused into the normalise kernel), the sixth by ConstantPad2d + MaxPool2d(2, stride 1).
+
+    The 16-channel first layer rides on the 32-filter first-layer kernels: its weights are zero-padded to 32 outputs, BatchNorm runs over the
+    16 real channels of the 32-wide buffers (the kernels take the channel count and the pixel pitch separately), the padding channels stay
+    exactly zero, and the second unit's weights are zero-padded on the input side to match (its weight gradient is cut back to 16 inputs)."""
+
+    def __init__(self, dnn, grad_scale=16384.0):
+        DarknetTrainer.__init__(self, _TinyEngineView(dnn), grad_scale)
+        self.dnn = dnn
+        self._zero_bufs = {}
+
+    def grad_order(self):
+        keys = [key for key, _, _ in self.dnn.unit_keys()]
+        names = [keys[-1] + '.conv.bias', keys[-1] + '.conv.weight']
+        for key in reversed(keys[:-1]):
+            names += [key + '.bn.weight', key + '.bn.bias', key + '.conv.weight']
+        return names
+
+    def _zeros(self, tag, shape, device):
+        """Persistent zero-initialised fp16 buffer whose padding channels are never written."""
+        t = self._zero_bufs.get(tag)
+        if t is None or tuple(t.shape) != tuple(shape) or t.device != device:
+            t = torch.zeros(shape, dtype=torch.float16, device=device)
+            self._zero_bufs[tag] = t
+        return t
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise RuntimeError('Tiny (B200) training: input must be a CUDA tensor')
+        b, _, h, w = x.shape
+        x = x.contiguous().float()
+        dev = x.device
+        plan = self.dnn.unit_keys()
+        units = [u for _, u, _ in plan]
+        for i, u in enumerate(units):
+            u.refresh(first_layer=(i == 0), force=True)
+            if u.bn is None and i != len(units) - 1:
+                raise NotImplementedError('training path requires batch_norm/enable = 1')
+        saved = _Saved()
+        saved.x, saved.b, saved.h, saved.w, saved.units, saved.order = x, b, h, w, {}, []
+        # unit 0: 3 -> C0 (<= 32) on the first-layer kernel, filters zero-padded to 32
+        key0, u0, after0 = plan[0]
+        c0 = u0.cout
+        if c0 > 32 or after0 != 'pool':
+            raise RuntimeError('Tiny (B200): the first unit must have <= 32 filters and be followed by MaxPool2d(2)')
+        w0 = torch.zeros(32, 3, 3, 3, dtype=torch.float32, device=dev)
+        w0[:c0].copy_(u0.conv.weight.detach())
+        z = self._zeros(('z0', b, h, w), (b, h, w, 32), dev)
+        ops.call('yb_conv0_raw_fwd', x, w0, z, b, h, w, 32)
+        mean, invstd = self._bn_forward(key0, u0, z, b * h * w)
+        cur = self._zeros(('a0', b, h, w), (b, h // 2, w // 2, 32), dev)
+        self._apply(u0, z, mean, invstd, b, h, w, True, out=cur)
+        s = _Saved()
+        s.u, s.ain, s.z, s.mean, s.invstd, s.h, s.w, s.pooled = u0, None, z, mean, invstd, h, w, True
+        saved.units[key0] = s
+        saved.order.append((key0, after0))
+        hh, ww, chan = h // 2, w // 2, 32
+        for key, u, after in plan[1:-1]:
+            if u.cin != chan:
+                # input side zero-padded to the producer's buffer width (unit 1: 16 -> 32)
+                wp = torch.zeros(u.cout, chan, u.ksize, u.ksize, dtype=torch.float32, device=dev)
+                wp[:, :u.cin].copy_(u.conv.weight.detach())
+                w16 = ops.pack_weight_f16(wp, 0)
+            else:
+                w16 = u.w16
+            one, zero = self._ones(u.cout, dev)
+            if self.fuse_stats and not (chan == 32 and u.ksize == 3 and u.cout <= 64):
+                z = ops.conv_bn_act_stats(cur, w16, one, zero, 1.0, self._sums(('f', key), u.cout, dev))
+                self._fused_stats = True
+            else:
+                z = ops.conv_bn_act(cur, w16, one, zero, 1.0)
+                self._fused_stats = False
+            mean, invstd = self._bn_forward(key, u, z, b * hh * ww)
+            a = self._apply(u, z, mean, invstd, b, hh, ww, after == 'pool')
+            s = _Saved()
+            s.u, s.ain, s.z, s.mean, s.invstd, s.h, s.w, s.pooled, s.cin_pad = u, cur, z, mean, invstd, hh, ww, after == 'pool', chan
+            if after == 'pool':
+                hh, ww = hh // 2, ww // 2
+            elif after == 'pool_s1':
+                s.a_unpooled = a
+                a = ops.maxpool2x2_s1(a)
+            saved.units[key] = s
+            saved.order.append((key, after))
+            cur, chan = a, u.cout
+        key_h, u_h, _ = plan[-1]
+        feature = ops.conv_bn_act(cur, u_h.w16, u_h.scale, u_h.shift, 1.0, out_mode=ops.OUT_F32_NCHW)
+        saved.a_last, saved.hh, saved.ww, saved.head = cur, hh, ww, (key_h, u_h)
+        return feature, saved
+
+    def backward(self, saved, dfeature, dnn=None):
+        b = saved.b
+        grads = {}
+        dev = dfeature.device
+        self._ensure_arena(self.dnn, dev)
+        self._main = torch.cuda.current_stream(dev)
+        self._x = saved.x
+        key_h, u_h = saved.head
+        hh, ww = saved.hh, saved.ww
+        chead = u_h.cout
+        cpad = (chead + 31) // 32 * 32
+        dzh = torch.empty(b, hh, ww, cpad, dtype=torch.float16, device=dev)
+        dbias = self.arena.views[key_h + '.conv.bias']
+        ops.call('yb_head_grad_prepare', dfeature.contiguous().float() * self.grad_scale, dzh, dbias, b, chead, cpad, hh * ww)
+        grads[key_h + '.conv.bias'] = dbias.mul_(self._unscale)
+        self._emit(key_h + '.conv.bias', grads)
+        self._wgrad(u_h, saved.a_last, dzh, b, hh, ww, grads, key_h, cout=chead)
+        one, zero = self._ones(u_h.cin, dev)
+        g = ops.conv_bn_act(dzh, self._wd(key_h, u_h, cpad), one, zero, 1.0)
+        for key, after in reversed(saved.order):
+            s = saved.units[key]
+            u = s.u
+            if after == 'pool_s1':
+                da = torch.empty_like(s.a_unpooled)
+                ops.call('yb_maxpool2x2_s1_bwd_f16', s.a_unpooled, g, da, b, s.h, s.w, u.cout)
+                g = da
+            pooled = after == 'pool'
+            if s.ain is None:
+                # first layer: dz into the 32-wide zero-padded buffer the first-layer weight-gradient kernel reads
+                g = self._tiny_unit0_backward(key, s, b, grads, g)
+                break
+            if getattr(s, 'cin_pad', u.cin) != u.cin:
+                g = self._tiny_padded_unit_backward(key, s, b, grads, g, pooled)
+            else:
+                g = self._unit_backward(key, s, b, grads, da=None if pooled else g, dap=g if pooled else None)
+        self._join(dev)
+        if self.reducer is not None:
+            self.reducer.finish()
+        if self.found_inf is None or self.found_inf.device != dev:
+            self.found_inf = torch.zeros((), dtype=torch.float32, device=dev)
+        ops.call('yb_grad_guard', self.arena.flat, self.arena.flat.numel(), self.found_inf, 1)
+        return grads
+
+    def _bn_backward(self, key, s, b, grads, da, dap, dz, ld_dz):
+        u = s.u
+        c = u.cout
+        dev = s.z.device
+        sums = self._sums(('b', key), c, dev)
+        args = (s.z, s.z.shape[-1], s.mean, s.invstd, u.bn.weight.detach(), u.bn.bias.detach(), SLOPE, da, 0 if da is None else da.shape[-1], 0, dap,
+                0 if dap is None else dap.shape[-1], 0, b, s.h, s.w, c, 1 if dap is not None else 0, sums)
+        ops.call('yb_bn_act_bwd', 0, *args, None, 0, 1)
+        ops.call('yb_bn_act_bwd', 1, *args, dz, ld_dz, 1)
+        dgamma, dbeta = self.arena.views[key + '.bn.weight'], self.arena.views[key + '.bn.bias']
+        ops.call('yb_bn_param_grad', sums, c, dgamma, dbeta, 1, self._unscale)
+        grads[key + '.bn.weight'], grads[key + '.bn.bias'] = dgamma, dbeta
+        self._emit(key + '.bn.weight', grads)
+        self._emit(key + '.bn.bias', grads)
+
+    def _tiny_unit0_backward(self, key, s, b, grads, g):
+        dev = s.z.device
+        dz = self._zeros(('dz0', b, s.h, s.w), (b, s.h, s.w, 32), dev)          # channels >= cout stay zero
+        self._bn_backward(key, s, b, grads, None, g, dz, 32)
+        dw32 = torch.empty(32, 3, 3, 3, dtype=torch.float32, device=dev)
+        ops.call('yb_conv0_wgrad', self._x, dz, dw32, b, s.h, s.w)
+        dw = self.arena.views[key + '.conv.weight']
+        dw.copy_(dw32[:s.u.cout]).mul_(self._unscale)
+        grads[key + '.conv.weight'] = dw
+        self._emit(key + '.conv.weight', grads)
+        return None
+
+    def _tiny_padded_unit_backward(self, key, s, b, grads, g, pooled):
+        """Unit whose input buffer is wider than its Cin (zero-padded): the weight gradient is computed over the padded width and cut back."""
+        u = s.u
+        dev = s.z.device
+        dz = torch.empty(b, s.h, s.w, u.cout, dtype=torch.float16, device=dev)
+        self._bn_backward(key, s, b, grads, None if pooled else g, g if pooled else None, dz, u.cout)
+        k, cp = u.ksize, s.cin_pad
+        dw_krsc = torch.empty(u.cout, k, k, cp, dtype=torch.float32, device=dev)
+        ops.call('yb_conv_wgrad', s.ain, dz, dw_krsc, b, s.h, s.w, cp, u.cout, k, s.ain.shape[-1], dz.shape[-1])
+        full = torch.empty(u.cout, cp, k, k, dtype=torch.float32, device=dev)
+        ops.call('yb_unpack_wgrad', dw_krsc, full, u.cout, cp, k, self._unscale)
+        dw = self.arena.views[key + '.conv.weight']
+        dw.copy_(full[:, :u.cin])
+        grads[key + '.conv.weight'] = dw
+        self._emit(key + '.conv.weight', grads)
+        one, zero = self._ones(u.cin, dev)
+        return ops.conv_bn_act(dz, self._wd(key, u), one, zero, 1.0)      # [B, h, w, Cin]: the producer's real channels
+
+
+class _TinyEngineView(object):
+    """The two things DarknetTrainer reads from an engine, for a plain chain."""
+    precision = 'fast'
+
+    def __init__(self, dnn):
+        self._dnn = dnn

@@ -73,6 +73,7 @@ int bn_fold(const float*, const float*, const float*, const float*, float, float
 int conv0_tc_forward(const void*, int, const float*, const float*, const float*, float, void*, int, int, int, int, int, cudaStream_t);
 int maxpool2x2(const void*, void*, int, int, int, int, int, cudaStream_t);
 int maxpool2x2_s1(const void*, void*, int, int, int, int, int, cudaStream_t);
+int maxpool2x2_s1_bwd(const void*, const void*, void*, int, int, int, int, cudaStream_t);
 int reorg_nhwc(const void*, void*, int, int, int, int, int, int, int, cudaStream_t);
 int reorg_nchw(const float*, float*, int, int, int, int, int, int, cudaStream_t);
 int decode_forward(const float*, const float*, float*, float*, float*, float*, float*, float*, float*, int, int, int, int, int,
@@ -202,6 +203,10 @@ int yb_maxpool2x2_f16(const void* x, void* y, int batch, int height, int width, 
 
 int yb_maxpool2x2_s1_f16(const void* x, void* y, int batch, int height, int width, int channels, int x_ld, yb_stream_t stream) {
   return yb::maxpool2x2_s1(x, y, batch, height, width, channels, x_ld, S(stream));
+}
+
+int yb_maxpool2x2_s1_bwd_f16(const void* x, const void* dy, void* dx, int batch, int height, int width, int channels, yb_stream_t stream) {
+  return yb::maxpool2x2_s1_bwd(x, dy, dx, batch, height, width, channels, S(stream));
 }
 
 int yb_reorg_f16(const void* x, void* y, int batch, int height, int width, int channels, int x_ld, int y_ld, int y_ch_off,

@@ -235,6 +235,81 @@ int maxpool2x2_s1(const void* x, void* y, int batch, int height, int width, int 
   return check_launch("maxpool2x2_s1_kernel");
 }
 
+// Backward of the same pad + stride-1 pooling (training of model.yolo2.Tiny): dx[p] = sum of dy over the (up to four) windows that contain
+// p and whose FIRST maximum (scan order (0,0), (0,1), (1,0), (1,1), as torch's max_pool2d records it) is p.  thread = 8 channels of one pixel.
+__global__ void maxpool2x2_s1_bwd_kernel(const __half* __restrict__ x, const __half* __restrict__ dy, __half* __restrict__ dx, int batch, int height,
+                                         int width, int channels) {
+  const int c8 = channels >> 3;
+  const long long total = static_cast<long long>(batch) * height * width * c8;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cg = static_cast<int>(idx % c8);
+  long long t = idx / c8;
+  const int px = static_cast<int>(t % width); t /= width;
+  const int py = static_cast<int>(t % height);
+  const long long img = t / height;
+  const __half* xb = x + img * height * width * channels + cg * 8;
+  const __half* gb = dy + img * height * width * channels + cg * 8;
+  // the 3 x 3 neighbourhood of p (values outside the frame = -inf, they never win)
+  float v[3][3][8];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int yy = py - 1 + r, xx = px - 1 + c;
+      if (yy >= 0 && yy < height && xx >= 0 && xx < width) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(xb + (static_cast<long long>(yy) * width + xx) * channels));
+        const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(h[e]); v[r][c][2 * e] = f.x; v[r][c][2 * e + 1] = f.y; }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[r][c][e] = -INFINITY;
+      }
+    }
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  // window with top-left (py - dy, px - dx): p sits at position (dy, dx) of it
+#pragma unroll
+  for (int dyy = 0; dyy < 2; ++dyy)
+#pragma unroll
+    for (int dxx = 0; dxx < 2; ++dxx) {
+      const int wy = py - dyy, wx = px - dxx;
+      if (wy < 0 || wx < 0) continue;
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(gb + (static_cast<long long>(wy) * width + wx) * channels));
+      const __half2* h = reinterpret_cast<const __half2*>(&q);
+      float g[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(h[e]); g[2 * e] = f.x; g[2 * e + 1] = f.y; }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        // neighbourhood coordinates of the window's four elements: rows (1 - dyy) + {0, 1}, columns (1 - dxx) + {0, 1}
+        float best = -INFINITY;
+        int arg = -1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float val = v[1 - dyy + (k >> 1)][1 - dxx + (k & 1)][e];
+          if (arg < 0 || val > best) { best = val; arg = k; }      // first maximum wins
+        }
+        if (arg == dyy * 2 + dxx) acc[e] += g[e];
+      }
+    }
+  uint4 out;
+  __half2* ho = reinterpret_cast<__half2*>(&out);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) ho[e] = __floats2half2_rn(acc[2 * e], acc[2 * e + 1]);
+  reinterpret_cast<uint4*>(dx)[idx] = out;
+}
+
+int maxpool2x2_s1_bwd(const void* x, const void* dy, void* dx, int batch, int height, int width, int channels, cudaStream_t stream) {
+  YB_REQUIRE(x && dy && dx && batch > 0 && height > 0 && width > 0 && channels % 8 == 0, "maxpool2x2_s1_bwd: bad argument");
+  const long long total = static_cast<long long>(batch) * height * width * (channels / 8);
+  maxpool2x2_s1_bwd_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 0, stream>>>(
+      reinterpret_cast<const __half*>(x), reinterpret_cast<const __half*>(dy), reinterpret_cast<__half*>(dx), batch, height, width, channels);
+  return check_launch("maxpool2x2_s1_bwd_kernel");
+}
+
 // ------------------------------------------------------------------------------------------
 // reorg on fp16 NHWC: out[b, h', w', y_ch_off + (sh*2+sw)*C + c] = in[b, 2h'+sh, 2w'+sw, c]
 __global__ void reorg_nhwc_kernel(const __half* __restrict__ x, __half* __restrict__ y, int batch, int height, int width, int channels,

@@ -233,7 +233,7 @@ class MaxPool2dStride1(nn.Module):
 
 class Tiny(nn.Module):
     """Tiny YOLOv2 backbone plugin (reference model/yolo2.py:140-173; the repo's default `model/dnn`, config.ini:25),
-    inference on the B200 kernels.  Same constructor contract `Tiny(config_channels, anchors, num_cls, channels=16)`, same
+    inference and training on the B200 kernels.  Same constructor contract `Tiny(config_channels, anchors, num_cls, channels=16)`, same
     state_dict keys (`layers.{0,2,4,6,8,10,13,14,15}.conv.*`, `.bn.*`), `init()` (xavier-normal, :159-165), `scope()`
     (:170-171) and forward contract x[B,3,H,W] fp32 -> [B, A*(5+C), H/32, W/32] fp32.
 
@@ -262,6 +262,26 @@ class Tiny(nn.Module):
         self.init()
         self._units = None
         self._pad_cache = {}
+        self._trainer = None
+
+    @property
+    def trainer(self):
+        if self._trainer is None:
+            self._trainer = _train.TinyTrainer(self)
+        return self._trainer
+
+    def unit_keys(self):
+        """[(state_dict prefix 'layers.N', ConvUnit, followed_by)] in network order."""
+        keys = ['layers.%d' % i for i, m in enumerate(self.layers) if not m.is_pool]
+        return [(k, u, after) for k, (u, after) in zip(keys, self._plan())]
+
+    def train(self, mode=True):
+        """nn.Module.train + drop cached kernel operands (fused optimizers update parameters behind torch's version counters)."""
+        if getattr(self, '_units', None) is not None and bool(mode) != self.training:
+            self._pad_cache = {}
+            for u, _ in self._units:
+                u._wver = u._bver = None
+        return nn.Module.train(self, mode)
 
     def init(self):
         for m in self.modules():
@@ -311,7 +331,8 @@ class Tiny(nn.Module):
 
     def forward(self, x):
         if self.training:
-            raise NotImplementedError('Tiny (B200): inference only; call .eval()')
+            # batch-statistics BatchNorm + autograd through the explicit backward chain (b200.train_engine.TinyTrainer)
+            return _DarknetTrainFunction.apply(self, x, *[p for _, p in self.named_parameters()])
         if not x.is_cuda:
             raise RuntimeError('Tiny (B200): input must be a CUDA tensor; there is no CPU fallback')
         b, c, h, w = x.shape
