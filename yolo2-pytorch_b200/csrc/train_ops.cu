@@ -405,7 +405,7 @@ static int grid_for_groups(long long work_items, int c8) {
 }
 
 int bn_stats(const void* z, long long ld, long long rows, int channels, double* sums, cudaStream_t stream) {
-  YB_REQUIRE(z && sums && rows > 0 && channels >= 32 && channels % 8 == 0 && channels <= 2048 && kTrainThreads % (channels / 8) == 0 && ld % 8 == 0,
+  YB_REQUIRE(z && sums && rows > 0 && channels >= 8 && channels % 8 == 0 && channels <= 2048 && kTrainThreads % (channels / 8) == 0 && ld % 8 == 0,
              "bn_stats: unsupported shape (C=%d)", channels);
   const int rpi = kTrainThreads / (channels / 8);
   long long blocks = (rows + static_cast<long long>(rpi) * 16 - 1) / (static_cast<long long>(rpi) * 16);   // >= 16 rows per thread: 2C double atomics per block
