@@ -498,10 +498,16 @@ def make_mobilenet_state_dict(seed=0, num_anchors=5, num_cls=20):
     return sd
 
 
-def mobilenet_forward(sd, x, collect=None):
-    """model/mobilenet.py:84-85 in eval mode: conv_bn (:25-30) -> 13 x [conv_dw (:33-38), conv_pw (:41-46)] -> 1x1 head with bias."""
+def mobilenet_forward(sd, x, collect=None, train=False, stats=None):
+    """model/mobilenet.py:84-85: conv_bn (:25-30) -> 13 x [conv_dw (:33-38), conv_pw (:41-46)] -> 1x1 head with bias; eval mode by default,
+    `train=True` uses batch statistics (and records them in `stats`), as nn.BatchNorm2d does in train()."""
     def bn_relu(y, prefix):
-        y = F.batch_norm(y, sd[prefix + '.running_mean'], sd[prefix + '.running_var'], sd[prefix + '.weight'], sd[prefix + '.bias'], False, 0.0, 1e-5)
+        if train:
+            if stats is not None:
+                stats[prefix] = (y.mean(dim=(0, 2, 3)), y.var(dim=(0, 2, 3), unbiased=False))
+            y = F.batch_norm(y, None, None, sd[prefix + '.weight'], sd[prefix + '.bias'], True, 0.0, 1e-5)
+        else:
+            y = F.batch_norm(y, sd[prefix + '.running_mean'], sd[prefix + '.running_var'], sd[prefix + '.weight'], sd[prefix + '.bias'], False, 0.0, 1e-5)
         return F.relu(y)
 
     x = bn_relu(F.conv2d(x, sd['layers.0.conv.weight'], None, 2, 1), 'layers.0.bn')

@@ -1152,6 +1152,105 @@ def test_c5_mobilenet_batch32_vs_oracle():
     assert len(results) == 32
 
 
+def test_mobilenet_training_kernels_vs_torch(ops):
+    """The three training kernels of the MobileNet plugin against torch autograd on fp16-representable data: depthwise data gradient and
+    weight gradient (stride 1 and 2), first-layer (stride-2) weight gradient."""
+    for (b, h, c, stride) in ((2, 12, 64, 1), (2, 12, 64, 2), (1, 26, 256, 2), (3, 13, 1024, 1)):
+        gen = torch.Generator().manual_seed(h + c + stride)
+        a = torch.randn(b, c, h, h, generator=gen).half().float()
+        w = (torch.randn(c, 1, 3, 3, generator=gen) * 0.3)
+        dz = torch.randn(b, c, h // stride, h // stride, generator=gen).half().float()
+        ar, wr = a.clone().requires_grad_(True), w.clone().requires_grad_(True)
+        torch.nn.functional.conv2d(ar, wr, None, stride, 1, groups=c).backward(dz)
+        a16 = a.permute(0, 2, 3, 1).contiguous().half().to(DEV)
+        dz16 = dz.permute(0, 2, 3, 1).contiguous().half().to(DEV)
+        w9 = w.view(c, 9).contiguous().to(DEV)
+        da = torch.empty(b, h, h, c, dtype=torch.float16, device=DEV)
+        ops.call('yb_dwconv3x3_dgrad', dz16, w9, da, b, h, h, c, stride)
+        assert rel_err(da.permute(0, 3, 1, 2), ar.grad) <= 2e-3, (b, h, c, stride)
+        dw = torch.full((c, 9), 7.0, dtype=torch.float32, device=DEV)
+        ops.call('yb_dwconv3x3_wgrad', a16, dz16, dw, b, h, h, c, stride)
+        assert rel_err(dw.view(c, 1, 3, 3), wr.grad) <= 1e-4, (b, h, c, stride)
+        # raw forward = the conv itself
+        z = torch.empty(b, h // stride, h // stride, c, dtype=torch.float16, device=DEV)
+        ops.call('yb_dwconv3x3_raw_fwd', a16, w9, z, b, h, h, c, stride)
+        ref = torch.nn.functional.conv2d(a, w, None, stride, 1, groups=c)
+        assert rel_err(z.permute(0, 3, 1, 2), ref) <= 1e-3
+    gen = torch.Generator().manual_seed(3)
+    x = torch.rand(2, 3, 32, 48, generator=gen)
+    w0 = torch.randn(32, 3, 3, 3, generator=gen) * 0.2
+    dz = torch.randn(2, 32, 16, 24, generator=gen).half().float()
+    wr = w0.clone().requires_grad_(True)
+    torch.nn.functional.conv2d(x, wr, None, 2, 1).backward(dz)
+    dw = torch.full((32, 3, 3, 3), 5.0, dtype=torch.float32, device=DEV)
+    ops.call('yb_mb_conv0_wgrad', x.to(DEV), dz.permute(0, 2, 3, 1).contiguous().half().to(DEV), dw, 2, 32, 48)
+    assert rel_err(dw, wr.grad) <= 1e-4
+    z = torch.empty(2, 16, 24, 32, dtype=torch.float16, device=DEV)
+    ops.call('yb_mb_conv0_raw_fwd', x.to(DEV), w0.to(DEV), z, 2, 32, 48)
+    assert rel_err(z.permute(0, 3, 1, 2), torch.nn.functional.conv2d(x, w0, None, 2, 1)) <= 1e-3
+
+
+def test_mobilenet_training_step_vs_oracle_and_descent():
+    """model.mobilenet.MobileNet in train() mode: one step (train-mode forward with batch statistics at momentum 0.1, region loss, full
+    backward through 27 BatchNorm layers) against the oracle's arithmetic with torch autograd on CPU -- losses, every parameter gradient,
+    running statistics -- and 15 SGD steps on one batch reduce the loss."""
+    import model
+    import model.mobilenet
+    import train as yb_train
+    cfg = make_config(1)
+    cfg.read_dict({'model': {'threshold': '0.6'}, 'hparam': {'foreground': '5', 'background': '1', 'center': '1', 'size': '1', 'cls': '1'},
+                   'train': {'cross_entropy': '1'}})
+    anchors = O.anchors_yolo_voc()
+    sd0 = O.make_mobilenet_state_dict(0)
+    b, size = 8, 160
+    s = size // 32
+    x = O.synth_images(b, size, size, seed=80)
+    tgt = O.synth_targets(b, size, size, slots=5, seed=81)
+    data = O.norm_data(tgt, size, size, s, s)
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'running' not in k else v.clone()) for k, v in sd0.items()}
+    stats = {}
+    f_ref = O.mobilenet_forward(sd, x, train=True, stats=stats)
+    l_ref, _ = O.loss(anchors, data, O.decode(f_ref, anchors), 0.6)
+    O.loss_total(l_ref).backward()
+    net = model.mobilenet.MobileNet(model.ConfigChannels(cfg), anchors, 20)
+    net.load_state_dict(sd0, strict=False)
+    net = net.to(DEV).train()
+    inference = model.Inference(cfg, net, anchors).train()
+    pred = model._inference(inference, x.to(DEV))
+    losses, _ = model.loss(anchors, {k: v.to(DEV) for k, v in data.items()}, pred, 0.6)
+    sum(losses[k] * O.HPARAM_DEFAULT[k] for k in losses).backward()
+    e_f = rel_err(pred['feature'], f_ref)
+    e_loss = {k: abs(losses[k].item() - l_ref[k].item()) / abs(l_ref[k].item()) for k in losses}
+    worst_cos, worst_rel = (1.0, None), (0.0, None)
+    for name, p in net.named_parameters():
+        assert p.grad is not None and bool(torch.isfinite(p.grad).all()), name
+        g, r = p.grad.detach().float().cpu().flatten(), sd[name].grad.flatten()
+        cos = (torch.dot(g, r) / (g.norm() * r.norm() + 1e-30)).item()
+        rel = ((g - r).norm() / (r.norm() + 1e-30)).item()
+        if cos < worst_cos[0]:
+            worst_cos = (cos, name)
+        if rel > worst_rel[0]:
+            worst_rel = (rel, name)
+    e_run = 0.0
+    bufs = dict(net.named_buffers())
+    for prefix, (mean, var) in stats.items():
+        exp = 0.9 * sd0[prefix + '.running_mean'] + 0.1 * mean.detach()          # nn.BatchNorm2d default momentum 0.1 (model/mobilenet.py:28)
+        e_run = max(e_run, rel_err(bufs[prefix + '.running_mean'].cpu(), exp))
+    record('mobilenet_train_step', dict(feature=e_f, losses=e_loss, worst_grad_cosine=worst_cos, worst_grad_rel_l2=worst_rel, running_mean=e_run))
+    assert e_f <= 1e-1, e_f
+    for k, v in e_loss.items():
+        assert v <= 5e-2, (k, v)
+    assert worst_cos[0] >= 0.8, worst_cos
+    assert e_run <= 5e-3, e_run
+    opt = torch.optim.SGD(net.parameters(), 1e-3, momentum=0.9)
+    batch = dict(tensor=x, yx_min=tgt['yx_min'], yx_max=tgt['yx_max'], cls=tgt['cls'])
+    hist = [float(yb_train.iterate(inference, opt, anchors, cfg, batch)['loss_total'].item()) for _ in range(15)]
+    assert hist[-1] < 0.9 * hist[0], hist
+    net.eval()
+    f = net(x[:2].to(DEV))
+    assert f.shape == (2, 125, s, s) and bool(torch.isfinite(f).all())
+
+
 def test_mobilenet_depthwise_vs_torch(ops):
     for (b, h, c, stride) in ((2, 13, 1024, 1), (3, 52, 128, 2), (2, 7, 64, 1), (1, 60, 32, 1)):          # strip lengths 4 and 8, ragged last strips
         gen = torch.Generator().manual_seed(h * c)

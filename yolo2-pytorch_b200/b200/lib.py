@@ -58,6 +58,11 @@ SIGNATURES = {
     'yb_warp_affine_u8': [P, c_int, c_int, P, c_int, c_int, ctypes.POINTER(ctypes.c_double * 6), ctypes.POINTER(c_int * 3), P],
     'yb_totensor_u8': [P, P, c_int, c_int, c_int, P],
     'yb_eval_match': [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_float, c_float, P, P],
+    'yb_mb_conv0_raw_fwd': [P, P, P, c_int, c_int, c_int, P],
+    'yb_mb_conv0_wgrad': [P, P, P, c_int, c_int, c_int, P],
+    'yb_dwconv3x3_raw_fwd': [P, P, P, c_int, c_int, c_int, c_int, c_int, P],
+    'yb_dwconv3x3_dgrad': [P, P, P, c_int, c_int, c_int, c_int, c_int, P],
+    'yb_dwconv3x3_wgrad': [P, P, P, c_int, c_int, c_int, c_int, c_int, P],
     'yb_comm_version': [ctypes.POINTER(c_int)],
     'yb_comm_unique_id': [P],
     'yb_comm_init': [ctypes.POINTER(P), c_int, P, c_int],

@@ -43,6 +43,7 @@ class DarknetTrainer(object):
         self.wd_cache = {}   # dgrad weight buffers per unit (contents re-packed every step)
         # data parallel: b200.ddp.GradientAllReducer attached by train.iterate; every gradient kernel writes into the reducer-visible
         # arena and reports it (`_emit`) so the bucket's all-reduce starts while the rest of the backward chain is still running
+        self.slope = SLOPE     # negative slope of the activation (LeakyReLU(0.1) for the yolo2 backbones, 0 = ReLU for MobileNet)
         self.reducer = None
         self.arena = None
         self.found_inf = None  # device float[1]: 1 when the last backward produced a non-finite gradient (then zeroed), see backward()
@@ -137,9 +138,24 @@ class DarknetTrainer(object):
         c = u.cout
         if out is None:
             out = torch.empty(b, h // 2 if pool else h, w // 2 if pool else w, c, dtype=torch.float16, device=z.device)
-        ops.call('yb_bn_act_apply', z, z.shape[-1], mean, invstd, u.bn.weight.detach(), u.bn.bias.detach(), SLOPE, out, out.shape[-1], a_off,
+        ops.call('yb_bn_act_apply', z, z.shape[-1], mean, invstd, u.bn.weight.detach(), u.bn.bias.detach(), self.slope, out, out.shape[-1], a_off,
                  b, h, w, c, int(pool))
         return out
+
+    def _bn_backward(self, key, s, b, grads, da, dap, dz, ld_dz):
+        u = s.u
+        c = u.cout
+        dev = s.z.device
+        sums = self._sums(('b', key), c, dev)
+        args = (s.z, s.z.shape[-1], s.mean, s.invstd, u.bn.weight.detach(), u.bn.bias.detach(), self.slope, da, 0 if da is None else da.shape[-1], 0, dap,
+                0 if dap is None else dap.shape[-1], 0, b, s.h, s.w, c, 1 if dap is not None else 0, sums)
+        ops.call('yb_bn_act_bwd', 0, *args, None, 0, 1)
+        ops.call('yb_bn_act_bwd', 1, *args, dz, ld_dz, 1)
+        dgamma, dbeta = self.arena.views[key + '.bn.weight'], self.arena.views[key + '.bn.bias']
+        ops.call('yb_bn_param_grad', sums, c, dgamma, dbeta, 1, self._unscale)
+        grads[key + '.bn.weight'], grads[key + '.bn.bias'] = dgamma, dbeta
+        self._emit(key + '.bn.weight', grads)
+        self._emit(key + '.bn.bias', grads)
 
     # ---- forward -------------------------------------------------------------------------------------
     def forward(self, x):
@@ -281,7 +297,7 @@ class DarknetTrainer(object):
         window = 1 if (dap is not None) else 0
         sums = self._sums(('b', key), c, dev)
         bnw, bnb = u.bn.weight.detach(), u.bn.bias.detach()
-        args = (s.z, s.z.shape[-1], s.mean, s.invstd, bnw, bnb, SLOPE, da, 0 if da is None else da.shape[-1], da_off, dap,
+        args = (s.z, s.z.shape[-1], s.mean, s.invstd, bnw, bnb, self.slope, da, 0 if da is None else da.shape[-1], da_off, dap,
                 0 if dap is None else dap.shape[-1], dap_off, b, s.h, s.w, c, window, sums)
         ops.call('yb_bn_act_bwd', 0, *args, None, 0, 1)
         dgamma = self.arena.views[key + '.bn.weight']
@@ -498,21 +514,6 @@ class TinyTrainer(DarknetTrainer):
         ops.call('yb_grad_guard', self.arena.flat, self.arena.flat.numel(), self.found_inf, 1)
         return grads
 
-    def _bn_backward(self, key, s, b, grads, da, dap, dz, ld_dz):
-        u = s.u
-        c = u.cout
-        dev = s.z.device
-        sums = self._sums(('b', key), c, dev)
-        args = (s.z, s.z.shape[-1], s.mean, s.invstd, u.bn.weight.detach(), u.bn.bias.detach(), SLOPE, da, 0 if da is None else da.shape[-1], 0, dap,
-                0 if dap is None else dap.shape[-1], 0, b, s.h, s.w, c, 1 if dap is not None else 0, sums)
-        ops.call('yb_bn_act_bwd', 0, *args, None, 0, 1)
-        ops.call('yb_bn_act_bwd', 1, *args, dz, ld_dz, 1)
-        dgamma, dbeta = self.arena.views[key + '.bn.weight'], self.arena.views[key + '.bn.bias']
-        ops.call('yb_bn_param_grad', sums, c, dgamma, dbeta, 1, self._unscale)
-        grads[key + '.bn.weight'], grads[key + '.bn.bias'] = dgamma, dbeta
-        self._emit(key + '.bn.weight', grads)
-        self._emit(key + '.bn.bias', grads)
-
     def _tiny_unit0_backward(self, key, s, b, grads, g):
         dev = s.z.device
         dz = self._zeros(('dz0', b, s.h, s.w), (b, s.h, s.w, 32), dev)          # channels >= cout stay zero
@@ -550,3 +551,149 @@ class _TinyEngineView(object):
 
     def __init__(self, dnn):
         self._dnn = dnn
+
+
+class _BNUnit(object):
+    """What the BatchNorm helpers read of a unit, for layers that are not tcgen05 conv units (first conv, depthwise)."""
+
+    def __init__(self, bn, cout):
+        self.bn, self.cout = bn, cout
+        self._bver = None
+
+
+class MobileNetTrainer(DarknetTrainer):
+    """Training-mode forward / backward of `model.mobilenet.MobileNet` (reference model/mobilenet.py:25-85): conv_bn(3, 32, stride 2), thirteen
+    [depthwise 3x3 (stride 1 or 2) + BN + ReLU, pointwise 1x1 + BN + ReLU] units, a 1x1 head with bias.  Pointwise convs, their weight /
+    data gradients and the head run on the tcgen05 kernels of the Darknet path; the depthwise and first-layer kernels are HBM-bound CUDA-core
+    kernels (csrc/mobilenet_ops.cu).  BatchNorm momentum is the PyTorch default 0.1 here (read from the modules), the activation ReLU."""
+
+    def __init__(self, dnn, grad_scale=16384.0):
+        DarknetTrainer.__init__(self, _TinyEngineView(dnn), grad_scale)
+        self.dnn = dnn
+        self.slope = 0.0
+        self._units = None
+
+    def _plan(self):
+        if self._units is None:
+            from . import engine as _engine
+            layers = list(self.dnn.layers)
+            first = layers[0]
+            plan = dict(first=_BNUnit(first.bn, first.conv.weight.shape[0]), units=[], head=layers[-1])
+            for i, unit in enumerate(layers[1:-1], 1):
+                ch = unit.dw.conv.weight.shape[0]
+                plan['units'].append(dict(key='layers.%d' % i, dw=_BNUnit(unit.dw.bn, ch), dw_conv=unit.dw.conv, stride=unit.dw.conv.stride[0],
+                                          pw=_engine.ConvUnit(unit.pw.conv, unit.pw.bn, True)))
+            self._units = plan
+        return self._units
+
+    def grad_order(self):
+        names = ['layers.14.bias', 'layers.14.weight']
+        for i in range(13, 0, -1):
+            names += ['layers.%d.pw.bn.weight' % i, 'layers.%d.pw.bn.bias' % i, 'layers.%d.pw.conv.weight' % i,
+                      'layers.%d.dw.bn.weight' % i, 'layers.%d.dw.bn.bias' % i, 'layers.%d.dw.conv.weight' % i]
+        return names + ['layers.0.bn.weight', 'layers.0.bn.bias', 'layers.0.conv.weight']
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise RuntimeError('MobileNet (B200) training: input must be a CUDA tensor')
+        b, _, h, w = x.shape
+        x = x.contiguous().float()
+        dev = x.device
+        plan = self._plan()
+        saved = _Saved()
+        saved.x, saved.b, saved.h, saved.w, saved.units = x, b, h, w, []
+        first = self.dnn.layers[0]
+        if first.conv.weight.shape[0] != 32:
+            raise ValueError('MobileNet (B200): the first layer must have 32 output channels')
+        hh, ww = h // 2, w // 2
+        z = torch.empty(b, hh, ww, 32, dtype=torch.float16, device=dev)
+        ops.call('yb_mb_conv0_raw_fwd', x, first.conv.weight.detach().contiguous(), z, b, h, w)
+        u0 = plan['first']
+        mean, invstd = self._bn_forward('layers.0', u0, z, b * hh * ww)
+        cur = self._apply(u0, z, mean, invstd, b, hh, ww, False)
+        s0 = _Saved()
+        s0.u, s0.z, s0.mean, s0.invstd, s0.h, s0.w = u0, z, mean, invstd, hh, ww
+        saved.first = s0
+        for rec in plan['units']:
+            key, stride = rec['key'], rec['stride']
+            ch = rec['dw'].cout
+            oh, ow = hh // stride, ww // stride
+            # depthwise
+            zd = torch.empty(b, oh, ow, ch, dtype=torch.float16, device=dev)
+            wd = rec['dw_conv'].weight.detach().contiguous().view(ch, 9)
+            ops.call('yb_dwconv3x3_raw_fwd', cur, wd, zd, b, hh, ww, ch, stride)
+            mean, invstd = self._bn_forward(key + '.dw', rec['dw'], zd, b * oh * ow)
+            ad = self._apply(rec['dw'], zd, mean, invstd, b, oh, ow, False)
+            sd = _Saved()
+            sd.u, sd.ain, sd.z, sd.mean, sd.invstd, sd.h, sd.w, sd.in_h, sd.in_w, sd.stride, sd.wd = rec['dw'], cur, zd, mean, invstd, oh, ow, hh, ww, stride, wd
+            # pointwise
+            up = rec['pw']
+            up.refresh(force=True)
+            zp = self._raw_conv(up, ad, key=key + '.pw')
+            mean, invstd = self._bn_forward(key + '.pw', up, zp, b * oh * ow)
+            ap = self._apply(up, zp, mean, invstd, b, oh, ow, False)
+            sp = _Saved()
+            sp.u, sp.ain, sp.z, sp.mean, sp.invstd, sp.h, sp.w, sp.pooled = up, ad, zp, mean, invstd, oh, ow, False
+            saved.units.append((key, sd, sp))
+            cur, hh, ww = ap, oh, ow
+        head = plan['head']
+        cout = head.weight.shape[0]
+        w16 = ops.pack_weight_f16(head.weight.detach().contiguous(), 0)
+        ones = torch.ones(cout, dtype=torch.float32, device=dev)
+        feature = ops.conv_bn_act(cur, w16, ones, head.bias.detach().float().contiguous(), 1.0, out_mode=ops.OUT_F32_NCHW)
+        saved.a_last, saved.hh, saved.ww = cur, hh, ww
+        return feature, saved
+
+    def backward(self, saved, dfeature, dnn=None):
+        b = saved.b
+        grads = {}
+        dev = dfeature.device
+        self._ensure_arena(self.dnn, dev)
+        self._main = torch.cuda.current_stream(dev)
+        head = self._plan()['head']
+        hh, ww = saved.hh, saved.ww
+        chead, cin = head.weight.shape[0], head.weight.shape[1]
+        cpad = (chead + 31) // 32 * 32
+        dzh = torch.empty(b, hh, ww, cpad, dtype=torch.float16, device=dev)
+        dbias = self.arena.views['layers.14.bias']
+        ops.call('yb_head_grad_prepare', dfeature.contiguous().float() * self.grad_scale, dzh, dbias, b, chead, cpad, hh * ww)
+        grads['layers.14.bias'] = dbias.mul_(self._unscale)
+        self._emit('layers.14.bias', grads)
+        # head weight gradient / data gradient (1x1)
+        dw_krsc = torch.empty(chead, 1, 1, cin, dtype=torch.float32, device=dev)
+        ops.call('yb_conv_wgrad', saved.a_last, dzh, dw_krsc, b, hh, ww, cin, chead, 1, saved.a_last.shape[-1], dzh.shape[-1])
+        dwh = self.arena.views['layers.14.weight']
+        ops.call('yb_unpack_wgrad', dw_krsc, dwh, chead, cin, 1, self._unscale)
+        grads['layers.14.weight'] = dwh
+        self._emit('layers.14.weight', grads)
+        wdh = torch.empty(cin, 1, 1, cpad, dtype=torch.float16, device=dev)
+        ops.call('yb_pack_weight_dgrad_f16', head.weight.detach().contiguous(), wdh, chead, cin, 1, cpad)
+        one, zero = self._ones(cin, dev)
+        g = ops.conv_bn_act(dzh, wdh, one, zero, 1.0)
+        for key, sd, sp in reversed(saved.units):
+            # pointwise unit: generic BN backward + tcgen05 weight / data gradient (state-dict names layers.N.pw.*)
+            g = self._unit_backward(key + '.pw', sp, b, grads, da=g)
+            # depthwise unit
+            ch = sd.u.cout
+            dz = torch.empty(b, sd.h, sd.w, ch, dtype=torch.float16, device=dev)
+            self._bn_backward(key + '.dw', sd, b, grads, g, None, dz, ch)
+            dwd = self.arena.views[key + '.dw.conv.weight']
+            ops.call('yb_dwconv3x3_wgrad', sd.ain, dz, dwd, b, sd.in_h, sd.in_w, ch, sd.stride)
+            grads[key + '.dw.conv.weight'] = dwd.mul_(self._unscale)
+            self._emit(key + '.dw.conv.weight', grads)
+            g = torch.empty(b, sd.in_h, sd.in_w, ch, dtype=torch.float16, device=dev)
+            ops.call('yb_dwconv3x3_dgrad', dz, sd.wd, g, b, sd.in_h, sd.in_w, ch, sd.stride)
+        s0 = saved.first
+        dz0 = torch.empty(b, s0.h, s0.w, 32, dtype=torch.float16, device=dev)
+        self._bn_backward('layers.0', s0, b, grads, g, None, dz0, 32)
+        dw0 = self.arena.views['layers.0.conv.weight']
+        ops.call('yb_mb_conv0_wgrad', saved.x, dz0, dw0, b, saved.h, saved.w)
+        grads['layers.0.conv.weight'] = dw0.mul_(self._unscale)
+        self._emit('layers.0.conv.weight', grads)
+        self._join(dev)
+        if self.reducer is not None:
+            self.reducer.finish()
+        if self.found_inf is None or self.found_inf.device != dev:
+            self.found_inf = torch.zeros((), dtype=torch.float32, device=dev)
+        ops.call('yb_grad_guard', self.arena.flat, self.arena.flat.numel(), self.found_inf, 1)
+        return grads

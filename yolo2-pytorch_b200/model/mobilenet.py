@@ -1,4 +1,4 @@
-"""model.mobilenet -- MobileNet backbone plugin on the B200 kernels (inference).
+"""model.mobilenet -- MobileNet backbone plugin on the B200 kernels (inference and training).
 
 Drop-in for the reference's `model/mobilenet.py` (file:line cited per item): same constructor contract
 `MobileNet(config_channels, anchors, num_cls)` (:56-77), same state_dict keys (`layers.0.conv.weight`,
@@ -16,6 +16,7 @@ import torch.nn as nn
 
 import model
 from b200 import ops as _ops
+from b200 import train_engine as _train
 
 
 def conv_bn(in_channels, out_channels, stride):
@@ -68,6 +69,19 @@ class MobileNet(nn.Module):
                 nn.init.ones_(m.weight)
                 nn.init.zeros_(m.bias)
         self._cache = {}
+        self._trainer = None
+
+    @property
+    def trainer(self):
+        if self._trainer is None:
+            self._trainer = _train.MobileNetTrainer(self)
+        return self._trainer
+
+    def train(self, mode=True):
+        """nn.Module.train + drop cached kernel operands (fused optimizers update parameters behind torch's version counters)."""
+        if bool(mode) != self.training:
+            self._cache = {}
+        return nn.Module.train(self, mode)
 
     # ---- operand preparation (cached per parameter version) ------------------------------------------
     def _fold(self, key, bn):
@@ -89,7 +103,9 @@ class MobileNet(nn.Module):
 
     def forward(self, x):
         if self.training:
-            raise NotImplementedError('MobileNet (B200): inference only (BASELINE configs[4]); call .eval()')
+            # batch-statistics BatchNorm + autograd through the explicit backward chain (b200.train_engine.MobileNetTrainer)
+            from model.yolo2 import _DarknetTrainFunction
+            return _DarknetTrainFunction.apply(self, x, *[p for _, p in self.named_parameters()])
         if not x.is_cuda:
             raise RuntimeError('MobileNet (B200): input must be a CUDA tensor; there is no CPU fallback')
         b, c, h, w = x.shape
