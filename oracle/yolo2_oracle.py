@@ -523,6 +523,93 @@ def mobilenet_forward(sd, x, collect=None, train=False, stats=None):
 
 
 # ----------------------------------------------------------------------------------------------
+# ResNet plugin (model/resnet.py:28-178), eval mode -- SURVEY 8f rank 4
+# ----------------------------------------------------------------------------------------------
+RESNET_LAYERS = {'resnet18': ('basic', (2, 2, 2, 2)), 'resnet34': ('basic', (3, 4, 6, 3)), 'resnet50': ('bottleneck', (3, 4, 6, 3))}
+
+
+def resnet_blocks(name='resnet18'):
+    """(prefix, kind, cin, width, stride, downsample) per block in forward order (model/resnet.py:111-114,124-129)."""
+    kind, counts = RESNET_LAYERS[name]
+    expansion = 4 if kind == 'bottleneck' else 1
+    out, cin = [], 64
+    for li, (width, n) in enumerate(zip((64, 128, 256, 512), counts), 1):
+        for bi in range(n):
+            stride = 2 if (bi == 0 and li > 1) else 1
+            cout = width * expansion
+            out.append(dict(prefix='layer%d.%d' % (li, bi), kind=kind, cin=cin, width=width, cout=cout, stride=stride,
+                            downsample=(stride > 1 or cin != cout)))
+            cin = cout
+    return out
+
+
+def make_resnet_state_dict(name='resnet18', seed=0, num_anchors=5, num_cls=20):
+    """Deterministic synthetic ResNet state_dict with the reference's (torchvision's) key names: kaiming-normal convs as
+    model/resnet.py:117-119, BatchNorm tensors randomised so folding is exercised; the last BN of every block gets a small
+    gamma so the residual sums stay O(1) through the stack."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def conv(key, cout, cin, k):
+        sd[key + '.weight'] = torch.randn(cout, cin, k, k, generator=g) * math.sqrt(2.0 / (cin * k * k))
+
+    def bn(prefix, c, gain=1.0):
+        sd[prefix + '.weight'] = (torch.rand(c, generator=g) + 0.5) * gain
+        sd[prefix + '.bias'] = torch.randn(c, generator=g) * 0.1
+        sd[prefix + '.running_mean'] = torch.randn(c, generator=g) * 0.1
+        sd[prefix + '.running_var'] = torch.rand(c, generator=g) + 0.5
+
+    conv('conv1', 64, 3, 7)
+    bn('bn1', 64)
+    cin = 64
+    for b in resnet_blocks(name):
+        p = b['prefix']
+        if b['kind'] == 'basic':
+            conv(p + '.conv1', b['width'], b['cin'], 3); bn(p + '.bn1', b['width'])
+            conv(p + '.conv2', b['width'], b['width'], 3); bn(p + '.bn2', b['width'], 0.5)
+        else:
+            conv(p + '.conv1', b['width'], b['cin'], 1); bn(p + '.bn1', b['width'])
+            conv(p + '.conv2', b['width'], b['width'], 3); bn(p + '.bn2', b['width'])
+            conv(p + '.conv3', b['cout'], b['width'], 1); bn(p + '.bn3', b['cout'], 0.5)
+        if b['downsample']:
+            conv(p + '.downsample.0', b['cout'], b['cin'], 1); bn(p + '.downsample.1', b['cout'], 0.5)
+        cin = b['cout']
+    ch = num_anchors * (5 + num_cls) if num_cls > 1 else num_anchors * 5
+    sd['conv.weight'] = torch.randn(ch, cin, 1, 1, generator=g) * math.sqrt(1.0 / cin)
+    sd['conv.bias'] = torch.randn(ch, generator=g) * 0.1
+    return sd
+
+
+def resnet_forward(sd, x, name='resnet18', collect=None):
+    """model/resnet.py:131-142 (stem :107-110, BasicBlock.forward :44-61, Bottleneck.forward :82-103), eval mode."""
+    def bn(y, prefix):
+        return F.batch_norm(y, sd[prefix + '.running_mean'], sd[prefix + '.running_var'], sd[prefix + '.weight'], sd[prefix + '.bias'], False, 0.0, 1e-5)
+
+    x = F.relu(bn(F.conv2d(x, sd['conv1.weight'], None, 2, 3), 'bn1'))
+    if collect is not None:
+        collect['stem'] = x
+    x = F.max_pool2d(x, 3, 2, 1)
+    if collect is not None:
+        collect['maxpool'] = x
+    for b in resnet_blocks(name):
+        p = b['prefix']
+        residual = x
+        if b['kind'] == 'basic':
+            out = F.relu(bn(F.conv2d(x, sd[p + '.conv1.weight'], None, b['stride'], 1), p + '.bn1'))
+            out = bn(F.conv2d(out, sd[p + '.conv2.weight'], None, 1, 1), p + '.bn2')
+        else:
+            out = F.relu(bn(F.conv2d(x, sd[p + '.conv1.weight']), p + '.bn1'))
+            out = F.relu(bn(F.conv2d(out, sd[p + '.conv2.weight'], None, b['stride'], 1), p + '.bn2'))
+            out = bn(F.conv2d(out, sd[p + '.conv3.weight']), p + '.bn3')
+        if b['downsample']:
+            residual = bn(F.conv2d(x, sd[p + '.downsample.0.weight'], None, b['stride']), p + '.downsample.1')
+        x = F.relu(out + residual)
+        if collect is not None:
+            collect[p] = x
+    return F.conv2d(x, sd['conv.weight'], sd['conv.bias'])
+
+
+# ----------------------------------------------------------------------------------------------
 # Tiny YOLOv2 backbone (model/yolo2.py:140-173) -- SURVEY 8f rank 4
 # ----------------------------------------------------------------------------------------------
 FLOAT32_MIN = -3.4028234663852886e+38          # np.finfo(np.float32).min, the ConstantPad2d value (yolo2.py:150)

@@ -1125,6 +1125,87 @@ def test_mobilenet_plugin_vs_reference_golden(golden_dir):
     assert len(detect.postprocess_batch(cfg, pred)) == 3
 
 
+def test_resnet_kernels_vs_torch(ops):
+    """Stem 7x7 s2 + BN + ReLU, max-pool 3x3 s2 p1 (bit-exact), x[::2, ::2] (bit-exact) and relu(a + b) against torch on the same fp16 inputs;
+    and the identity the stride-2 blocks rely on: conv3x3(stride 1)[::2, ::2] == conv3x3(stride 2)."""
+    g = torch.Generator().manual_seed(3)
+    for (b, h, w) in ((2, 64, 96), (1, 416, 416)):
+        x = torch.rand(b, 3, h, w, generator=g)
+        wt = torch.randn(64, 3, 7, 7, generator=g) * 0.1
+        scale, shift = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g) * 0.1
+        y = torch.empty(b, h // 2, w // 2, 64, dtype=torch.float16, device=DEV)
+        ops.call('yb_stem7x7_bn_relu_fwd', x.to(DEV), wt.to(DEV), scale.to(DEV), shift.to(DEV), y, b, h, w)
+        ref = torch.relu(torch.nn.functional.conv2d(x.double(), wt.double(), None, 2, 3) * scale.double()[None, :, None, None] + shift.double()[None, :, None, None])
+        assert rel_err(y.permute(0, 3, 1, 2), ref.float()) <= 6e-4               # one fp16 rounding of the output
+    for (b, h, w, c) in ((2, 32, 48, 64), (1, 13, 27, 8), (3, 208, 208, 64)):
+        x = torch.randn(b, h, w, c, generator=g).half().to(DEV)
+        oh, ow = (h + 1) // 2, (w + 1) // 2
+        y = torch.empty(b, oh, ow, c, dtype=torch.float16, device=DEV)
+        ops.call('yb_maxpool3x3_s2_f16', x, y, b, h, w, c)
+        ref = torch.nn.functional.max_pool2d(x.permute(0, 3, 1, 2).float(), 3, 2, 1).permute(0, 2, 3, 1)
+        assert torch.equal(y.float(), ref)
+        ops.call('yb_subsample2_f16', x, y, b, h, w, c)
+        assert torch.equal(y, x[:, ::2, ::2, :])
+    a = torch.randn(5, 13, 13, 512, generator=g).half().to(DEV)
+    r = torch.randn(5, 13, 13, 512, generator=g).half().to(DEV)
+    out = torch.empty_like(a)
+    ops.call('yb_add_relu_f16', a, r, out, a.numel())
+    assert torch.equal(out, torch.relu(a.float() + r.float()).half())
+    ops.call('yb_add_relu_f16', a, r, a, a.numel())                               # in place, as the blocks use it
+    assert torch.equal(a, out)
+    x = torch.randn(1, 64, 26, 26, generator=g)
+    wt = torch.randn(128, 64, 3, 3, generator=g)
+    s1 = torch.nn.functional.conv2d(x, wt, None, 1, 1)[:, :, ::2, ::2]
+    s2 = torch.nn.functional.conv2d(x, wt, None, 2, 1)
+    assert s1.shape == s2.shape and (s1 - s2).abs().max() <= 1e-4 * s2.abs().max()
+
+
+def test_resnet_plugin_vs_reference_golden(golden_dir):
+    """model.resnet.resnet18 / resnet50 on the B200 kernels vs the EXECUTED reference (tests/golden/make_golden_resnet.py): stem pool and
+    every block's output at 64x64, head feature at 64 and 416.  fp16 operands through 17 (resnet18) / 49 (resnet50) convs: <= 3e-3."""
+    import detect
+    import model
+    import model.resnet
+    import utils
+    g = np.load(os.path.join(golden_dir, 'resnet.npz'))
+    cfg = make_config(1)
+    anchors = O.anchors_yolo_voc()
+    rec = {}
+    for name in ('resnet18', 'resnet50'):
+        net = utils.parse_attr('model.resnet.' + name)(model.ConfigChannels(cfg), anchors, 20)
+        res = net.load_state_dict(O.make_resnet_state_dict(name, 0), strict=False)
+        assert not res.unexpected_keys and not res.missing_keys
+        net = net.to(DEV).eval()
+        f64 = net(O.synth_images(1, 64, 64, seed=10).to(DEV))
+        rec[name + '_feature64'] = rel_err(f64, torch.from_numpy(g[name + '_feature64']))
+        if name == 'resnet18':
+            f416 = net(O.synth_images(1, 416, 416, seed=0).to(DEV))
+            rec['resnet18_feature416'] = rel_err(f416, torch.from_numpy(g['resnet18_feature416']))
+            assert f416.shape == (1, 125, 13, 13)
+            # block by block at 64x64 through the model's own block runner
+            x = O.synth_images(1, 64, 64, seed=10).to(DEV)
+            scale, shift = net._fold('bn1', net.bn1)
+            stem = torch.empty(1, 32, 32, 64, dtype=torch.float16, device=DEV)
+            from b200 import ops as _ops
+            _ops.call('yb_stem7x7_bn_relu_fwd', x, net.conv1.weight.detach().contiguous(), scale, shift, stem, 1, 64, 64)
+            cur = torch.empty(1, 16, 16, 64, dtype=torch.float16, device=DEV)
+            _ops.call('yb_maxpool3x3_s2_f16', stem, cur, 1, 32, 32, 64)
+            worst = (rel_err(cur.permute(0, 3, 1, 2), torch.from_numpy(g['resnet18_act_maxpool'])), 'maxpool')
+            for lname in ('layer1', 'layer2', 'layer3', 'layer4'):
+                for bname, blk in getattr(net, lname).named_children():
+                    key = '%s.%s' % (lname, bname)
+                    cur = net._block(key, blk, cur)
+                    e = rel_err(cur.permute(0, 3, 1, 2), torch.from_numpy(g['resnet18_act_' + key]))
+                    worst = max(worst, (e, key))
+            rec['resnet18_worst_block'] = list(worst)
+            assert worst[0] <= 3e-3, worst
+            inference = model.Inference(cfg, net, anchors).eval()
+            pred = model._inference(inference, O.synth_images(3, 416, 416, seed=2).to(DEV))
+            assert len(detect.postprocess_batch(cfg, pred)) == 3
+    record('resnet_golden', rec)
+    assert all(v <= 3e-3 for k, v in rec.items() if 'feature' in k), rec
+
+
 def test_c5_mobilenet_batch32_vs_oracle():
     """BASELINE configs[4] at its real size: MobileNet backbone on 32 x 3 x 416 x 416, head feature vs the oracle (itself pinned to the
     reference's MobileNet by mobilenet.npz) and the detection chain on top.  This plugin runs fp16 operands only (no strict mode): 27

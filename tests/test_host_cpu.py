@@ -121,6 +121,30 @@ def test_mobilenet_plugin_surface():
     assert sd['layers.14.bias'].shape == (125,) and sd['layers.3.dw.conv.weight'].shape == (128, 1, 3, 3)
 
 
+def test_resnet_plugin_surface():
+    """model.resnet: constructors, torchvision-style state_dict keys, `scope` (reference model/resnet.py:144-158), loud failures."""
+    import model
+    import model.resnet
+    import utils
+    from oracle import yolo2_oracle as O
+    config = load_config()
+    for name, params in (('resnet18', None), ('resnet50', None)):
+        net = utils.parse_attr('model.resnet.' + name)(model.ConfigChannels(config), O.anchors_yolo_voc(), 20)
+        ref = O.make_resnet_state_dict(name, 0)
+        sd = net.state_dict()
+        assert set(ref) == {k for k in sd if not k.endswith('num_batches_tracked')}, name
+        assert all(tuple(sd[k].shape) == tuple(ref[k].shape) for k in ref)
+    net = model.resnet.resnet18(model.ConfigChannels(config), O.anchors_yolo_voc(), 20)
+    assert net.scope('layer1.0.conv1.weight') == 'layer1.0.1' and net.scope('layer2.0.bn2.bias') == 'layer2.0.2'
+    assert net.scope('layer2.0.downsample.0.weight') == 'layer2.0.downsample' and net.scope('conv.weight') == 'conv'
+    assert net.scope('conv1.weight') == '1' and net.scope('bn1.running_mean') == '1'
+    assert net.conv.weight.shape == (125, 512, 1, 1) and net.layer2[0].conv1.stride == (2, 2) and net.layer2[0].downsample is not None
+    with pytest.raises(RuntimeError):
+        net.eval()(torch.zeros(1, 3, 32, 32))       # CPU tensor: no fallback
+    with pytest.raises(NotImplementedError):
+        net.train()(torch.zeros(1, 3, 32, 32))
+
+
 # ------------------------------------------------------------------------------------------------
 # Darknet `.weights` importer (SURVEY 8f rank 1; reference convert_darknet_torch.py:37-57,93-113)
 # ------------------------------------------------------------------------------------------------

@@ -158,6 +158,26 @@ def test_mobilenet_oracle_matches_reference(golden_dir):
     assert sum(v.numel() for k, v in sd.items() if 'running' not in k) == 3335101
 
 
+def test_resnet_oracle_matches_reference_golden(golden_dir):
+    """oracle.resnet_forward (restating model/resnet.py:28-142) against outputs of the reference's own resnet18 (BasicBlock) and
+    resnet50 (Bottleneck) modules (tests/golden/make_golden_resnet.py): stem pool + every block at 64x64, the feature at 64 and 416."""
+    g = np.load(os.path.join(golden_dir, 'resnet.npz'))
+    sd = O.make_resnet_state_dict('resnet18', 0)
+    collect = {}
+    with torch.no_grad():
+        f64 = O.resnet_forward(sd, O.synth_images(1, 64, 64, seed=10), 'resnet18', collect=collect)
+        f416 = O.resnet_forward(sd, O.synth_images(1, 416, 416, seed=0), 'resnet18')
+        g64 = O.resnet_forward(O.make_resnet_state_dict('resnet50', 0), O.synth_images(1, 64, 64, seed=10), 'resnet50')
+    assert f64.shape == (1, 125, 2, 2) and f416.shape == (1, 125, 13, 13)
+    np.testing.assert_allclose(f64.numpy(), g['resnet18_feature64'], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(f416.numpy(), g['resnet18_feature416'], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(g64.numpy(), g['resnet50_feature64'], rtol=1e-4, atol=1e-5)
+    keys = [k for k in g.files if k.startswith('resnet18_act_')]
+    assert len(keys) == 9
+    for k in keys:
+        np.testing.assert_allclose(collect[k[len('resnet18_act_'):]].numpy(), g[k], rtol=1e-4, atol=1e-5, err_msg=k)
+
+
 def test_tiny_oracle_matches_reference_golden(golden_dir):
     """oracle.tiny_forward (restating model/yolo2.py:140-173) against outputs of the reference's own Tiny module
     (tests/golden/make_golden_tiny.py): every conv unit at 64x64 and the 416x416 feature map."""

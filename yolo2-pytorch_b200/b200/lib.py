@@ -63,6 +63,10 @@ SIGNATURES = {
     'yb_dwconv3x3_raw_fwd': [P, P, P, c_int, c_int, c_int, c_int, c_int, P],
     'yb_dwconv3x3_dgrad': [P, P, P, c_int, c_int, c_int, c_int, c_int, P],
     'yb_dwconv3x3_wgrad': [P, P, P, c_int, c_int, c_int, c_int, c_int, P],
+    'yb_stem7x7_bn_relu_fwd': [P, P, P, P, P, c_int, c_int, c_int, P],
+    'yb_maxpool3x3_s2_f16': [P, P, c_int, c_int, c_int, c_int, P],
+    'yb_subsample2_f16': [P, P, c_int, c_int, c_int, c_int, P],
+    'yb_add_relu_f16': [P, P, P, c_longlong, P],
     'yb_comm_version': [ctypes.POINTER(c_int)],
     'yb_comm_unique_id': [P],
     'yb_comm_init': [ctypes.POINTER(P), c_int, P, c_int],
