@@ -757,6 +757,65 @@ def test_conv0_training_pieces(ops):
     ops.call('yb_conv0_wgrad', x.to(DEV), dz.to(DEV), dw, 2, 64, 96)
     ref_dw = torch.nn.grad.conv2d_weight(x, (32, 3, 3, 3), dz.float().permute(0, 3, 1, 2), padding=1)
     assert rel_err(dw, ref_dw) <= 1e-3
+    # raw output with the batch statistics fused in (yb_conv0_raw_stats_fwd): the same z bit for bit, sums == yb_bn_stats of it; the
+    # second size gives every CTA several tiles (the statistics accumulate in registers across them) and accumulates on top of the first call
+    for bsz, hh, ww in ((2, 64, 96), (24, 416, 416)):
+        xs = torch.rand(bsz, 3, hh, ww, generator=gen).to(DEV)
+        z0 = torch.empty(bsz, hh, ww, 32, dtype=torch.float16, device=DEV)
+        z1 = torch.full((bsz, hh, ww, 32), float('nan'), dtype=torch.float16, device=DEV)
+        ops.call('yb_conv0_raw_fwd', xs, w.to(DEV), z0, bsz, hh, ww, 32)
+        sums = torch.zeros(64, dtype=torch.float64, device=DEV)
+        ref_sums = torch.zeros(64, dtype=torch.float64, device=DEV)
+        for _ in range(2):
+            ops.call('yb_conv0_raw_stats_fwd', xs, w.to(DEV), z1, sums, bsz, hh, ww, 32)
+            ops.call('yb_bn_stats', z0, 32, bsz * hh * ww, 32, ref_sums)
+        assert torch.equal(z0, z1)
+        zd = z0.double().reshape(-1, 32)
+        exact = torch.cat([zd.sum(0), (zd * zd).sum(0)]) * 2
+        assert ((sums - exact).abs() / exact.abs().clamp_min(1.0)).max().item() <= 1e-4          # fp32 partial sums per thread / CTA
+        assert ((ref_sums - exact).abs() / exact.abs().clamp_min(1.0)).max().item() <= 1e-4
+
+
+def test_conv0_wgrad_with_fused_bn_backward(ops):
+    """yb_conv0_wgrad_bn (dz formed in shared memory from z and the pooled gradient) against the two-kernel path it replaces:
+    yb_bn_act_bwd mode 1 -> dz in memory -> yb_conv0_wgrad.  Both round dz to fp16 before the tensor-core pass; only the order of the
+    final atomics differs."""
+    gen = torch.Generator().manual_seed(78)
+    for b, h, w in ((2, 64, 96), (5, 160, 160)):
+        x = torch.rand(b, 3, h, w, generator=gen).to(DEV)
+        z = (torch.randn(b, h, w, 32, generator=gen) * 0.7).half().to(DEV)
+        z[0, :2, :2, :8] = 0.25                                           # tied window: the first maximum takes the gradient
+        dap_buf = (torch.randn(b, h // 2, w // 2, 48, generator=gen) * 0.05).half().to(DEV)      # gradient at channel offset 8 of a wider buffer
+        mean = (torch.randn(32, generator=gen) * 0.1).to(DEV)
+        invstd = (torch.rand(32, generator=gen) + 0.8).to(DEV)
+        gamma = (torch.rand(32, generator=gen) + 0.5).to(DEV)
+        gamma[3] = -0.7                                                   # a negative scale reverses the order inside the window
+        beta = (torch.randn(32, generator=gen) * 0.2).to(DEV)
+        sums = torch.zeros(64, dtype=torch.float64, device=DEV)
+        args = (z, 32, mean, invstd, gamma, beta, 0.1, None, 0, 0, dap_buf, 48, 8, b, h, w, 32, 1, sums)
+        ops.call('yb_bn_act_bwd', 0, *args, None, 0, 1)
+        dz = torch.empty(b, h, w, 32, dtype=torch.float16, device=DEV)
+        ops.call('yb_bn_act_bwd', 1, *args, dz, 32, 1)
+        dw_ref = torch.empty(32, 3, 3, 3, dtype=torch.float32, device=DEV)
+        ops.call('yb_conv0_wgrad', x, dz, dw_ref, b, h, w)
+        dw = torch.full((32, 3, 3, 3), float('nan'), dtype=torch.float32, device=DEV)
+        ops.call('yb_conv0_wgrad_bn', x, z, dap_buf, 48, 8, mean, invstd, gamma, beta, 0.1, sums, dw, b, h, w)
+        assert rel_err(dw, dw_ref) <= 1e-5, (b, h, w, rel_err(dw, dw_ref))
+        # and against fp32 autograd of the whole unit tail: a = maxpool(leaky(bn(z))), loss = sum(a * g)
+        zr = z.float().permute(0, 3, 1, 2).cpu().requires_grad_(True)
+        m, v = zr.mean(dim=(0, 2, 3)), zr.var(dim=(0, 2, 3), unbiased=False)
+        # the kernels take (mean, invstd) as given: use the batch's own so that autograd's BN backward is the same function
+        mean_b, invstd_b = m.detach().to(DEV), (1.0 / torch.sqrt(v.detach() + 1e-5)).to(DEV)
+        a = torch.nn.functional.max_pool2d(torch.nn.functional.leaky_relu(
+            torch.nn.functional.batch_norm(zr, None, None, gamma.cpu(), beta.cpu(), True, 0.0, 1e-5), 0.1), 2)
+        gref = dap_buf[..., 8:40].float().permute(0, 3, 1, 2).cpu()
+        (a * gref).sum().backward()
+        dw_auto = torch.nn.grad.conv2d_weight(x.cpu(), (32, 3, 3, 3), zr.grad, padding=1)
+        sums.zero_()
+        args = (z, 32, mean_b, invstd_b, gamma, beta, 0.1, None, 0, 0, dap_buf, 48, 8, b, h, w, 32, 1, sums)
+        ops.call('yb_bn_act_bwd', 0, *args, None, 0, 1)
+        ops.call('yb_conv0_wgrad_bn', x, z, dap_buf, 48, 8, mean_b, invstd_b, gamma, beta, 0.1, sums, dw, b, h, w)
+        assert rel_l2(dw.cpu(), dw_auto) <= 5e-3, rel_l2(dw.cpu(), dw_auto)
 
 
 def test_training_step_vs_oracle():
@@ -1014,7 +1073,8 @@ def test_graphed_training_step_matches_eager():
             assert 0.5 <= (dg.norm() / de.norm()).item() <= 2.0, k
 
 
-@pytest.mark.parametrize('case', [(3, 26, 26, 64, 192, 3), (2, 13, 13, 256, 512, 1), (5, 10, 14, 128, 1024, 3), (64, 13, 13, 512, 1024, 3)])
+@pytest.mark.parametrize('case', [(3, 26, 26, 64, 192, 3), (2, 13, 13, 256, 512, 1), (5, 10, 14, 128, 1024, 3), (64, 13, 13, 512, 1024, 3),
+                                  (3, 32, 24, 32, 64, 3), (6, 208, 208, 32, 64, 3), (2, 48, 40, 32, 32, 3)])      # the last three: the Cin = 32 halo-tile kernel
 def test_conv_fused_batch_statistics(ops, case):
     """yb_conv_bn_act_stats_fwd: same z as the plain kernel, bit for bit, and per-channel sum / sum of squares of the
     stored fp16 values equal to a separate yb_bn_stats pass (float partial sums in a different order: 1e-5)."""
@@ -1123,6 +1183,30 @@ def test_mobilenet_plugin_vs_reference_golden(golden_dir):
     inference = model.Inference(cfg, net, O.anchors_yolo_voc()).eval()
     pred = model._inference(inference, O.synth_images(3, 416, 416, seed=2).to(DEV))
     assert len(detect.postprocess_batch(cfg, pred)) == 3
+
+
+def test_pack_weights_batch_matches_per_unit(ops):
+    """yb_pack_weights_batch (one launch for all units of a training step) == yb_pack_weight_f16 + yb_pack_weight_dgrad_f16 per unit, bit for bit,
+    including the zero-padded filters of the head and channel counts that do not fill a tile."""
+    from b200.train_engine import PackPlan
+    g = torch.Generator().manual_seed(5)
+    shapes = [(64, 32, 3, 0), (128, 64, 3, 0), (64, 128, 1, 0), (1024, 1280, 3, 0), (125, 1024, 1, 128), (40, 24, 3, 48), (72, 520, 1, 0), (256, 16, 3, 0)]
+    ws = [torch.randn(co, ci, k, k, generator=g).to(DEV) for co, ci, k, _ in shapes]
+    plan = PackPlan([('u%d' % i, w, True, True, cp) for i, (w, (_, _, _, cp)) in enumerate(zip(ws, shapes))], torch.device(DEV))
+    for t in list(plan.fwd.values()) + list(plan.dgrad.values()):
+        t.fill_(float('nan'))
+    plan.run()
+    for i, (w, (co, ci, k, cp)) in enumerate(zip(ws, shapes)):
+        ref_f = ops.pack_weight_f16(w, 0)
+        cpad = max(co, cp)
+        ref_d = torch.empty(ci, k, k, cpad, dtype=torch.float16, device=DEV)
+        ops.call('yb_pack_weight_dgrad_f16', w, ref_d, co, ci, k, cpad)
+        assert torch.equal(plan.fwd['u%d' % i], ref_f), shapes[i]
+        assert torch.equal(plan.dgrad['u%d' % i], ref_d), shapes[i]
+    # forward-only / dgrad-only entries
+    plan2 = PackPlan([('a', ws[0], True, False, 0), ('b', ws[1], False, True, 0)], torch.device(DEV))
+    plan2.run()
+    assert torch.equal(plan2.fwd['a'], ops.pack_weight_f16(ws[0], 0)) and 'a' not in plan2.dgrad and 'b' not in plan2.fwd
 
 
 def test_resnet_kernels_vs_torch(ops):

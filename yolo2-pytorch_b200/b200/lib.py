@@ -40,7 +40,9 @@ SIGNATURES = {
     'yb_region_loss_fwd': [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, P, P, P, P, P, P, P, P, P],
     'yb_region_loss_bwd': [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P],
     'yb_conv0_raw_fwd': [P, P, P, c_int, c_int, c_int, c_int, P],
+    'yb_conv0_raw_stats_fwd': [P, P, P, P, c_int, c_int, c_int, c_int, P],
     'yb_pack_weight_dgrad_f16': [P, P, c_int, c_int, c_int, c_int, P],
+    'yb_pack_weights_batch': [P, c_int, c_int, P],
     'yb_bn_stats': [P, c_longlong, c_longlong, c_int, P, P],
     'yb_bn_finalize': [P, c_longlong, c_int, c_float, c_float, P, P, P, P, P],
     'yb_bn_act_apply': [P, c_longlong, P, P, P, P, c_float, P, c_longlong, c_int, c_int, c_int, c_int, c_int, c_int, P],
@@ -50,6 +52,7 @@ SIGNATURES = {
     'yb_reorg_bwd_f16': [P, c_longlong, c_int, P, c_int, c_int, c_int, c_int, P],
     'yb_head_grad_prepare': [P, P, P, c_int, c_int, c_int, c_int, P],
     'yb_conv0_wgrad': [P, P, P, c_int, c_int, c_int, P],
+    'yb_conv0_wgrad_bn': [P, P, P, c_longlong, c_int, P, P, P, P, c_float, P, P, c_int, c_int, c_int, P],
     'yb_conv_wgrad': [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P],
     'yb_unpack_wgrad': [P, P, c_int, c_int, c_int, c_float, P],
     'yb_grad_guard': [P, c_longlong, P, c_int, P],

@@ -15,6 +15,7 @@ nn.DataParallel.
 """
 import os
 
+import numpy as np
 import torch
 
 from . import ddp as _ddp
@@ -33,6 +34,42 @@ class _NullCtx(object):
 
     def __exit__(self, *exc):
         return False
+
+
+class PackPlan(object):
+    """Every unit's forward (w16) and data-gradient (rotated, transposed) fp16 operand re-derived from the fp32 parameters by ONE launch
+    (yb_pack_weights_batch).  A training step must re-pack all of them -- the optimizer just changed the weights, and fused optimizers do not
+    advance torch's version counters -- which used to be two latency-bound launches per unit.  The output buffers are persistent (the unit
+    table holds their addresses), so the plan is rebuilt when a parameter moves."""
+    DTYPE = np.dtype([('w', '<u8'), ('f', '<u8'), ('d', '<u8'), ('cout', '<i4'), ('cin', '<i4'), ('k', '<i4'), ('cp', '<i4'), ('b0', '<i4'), ('cib', '<i4')])
+
+    def __init__(self, entries, device):
+        """entries: [(key, weight [Cout,Cin,k,k] fp32, want_fwd, want_dgrad, cout_pad)]"""
+        assert self.DTYPE.itemsize == 48
+        table = np.zeros(len(entries), dtype=self.DTYPE)
+        self.key = tuple(w.data_ptr() for _, w, _, _, _ in entries)
+        self.fwd, self.dgrad = {}, {}
+        blocks = 0
+        for i, (key, w, want_f, want_d, cp) in enumerate(entries):
+            cout, cin, k, _ = w.shape
+            cp = max(cout, cp)
+            if cin % 2 or cp % 2 or k not in (1, 3) or w.dtype != torch.float32 or not w.is_contiguous():
+                raise ValueError('PackPlan: unsupported weight %s %s' % (key, tuple(w.shape)))
+            f = torch.empty(cout, k, k, cin, dtype=torch.float16, device=device) if want_f else None
+            d = torch.empty(cin, k, k, cp, dtype=torch.float16, device=device) if want_d else None
+            cib = -(-cin // (32 if k == 3 else 256))
+            table[i] = (w.data_ptr(), 0 if f is None else f.data_ptr(), 0 if d is None else d.data_ptr(), cout, cin, k, cp, blocks, cib)
+            blocks += -(-cp // 64) * cib
+            if f is not None:
+                self.fwd[key] = f
+            if d is not None:
+                self.dgrad[key] = d
+        self.blocks = blocks
+        self.count = len(entries)
+        self.table = torch.from_numpy(table.view(np.uint8).copy()).to(device)
+
+    def run(self):
+        ops.call('yb_pack_weights_batch', self.table, self.count, self.blocks)
 
 
 class DarknetTrainer(object):
@@ -56,6 +93,7 @@ class DarknetTrainer(object):
         self.wgrad_stream = os.environ.get('YB_WGRAD_STREAM', '1') != '0'
         self._side_streams = {}
         self._side_busy = False
+        self._pack_plan = None
 
     # ---- helpers -------------------------------------------------------------------------------------
     def _emit(self, name, grads):
@@ -93,6 +131,33 @@ class DarknetTrainer(object):
         """Inverse loss scale, with the 1 / world of the data-parallel gradient average folded in."""
         return 1.0 / (self.grad_scale * (self.reducer.grad_divisor if self.reducer is not None else 1.0))
 
+    def _repack(self, device):
+        """All kernel operands that depend on the parameters, re-derived for this step: one batched pack launch for the fp16 weight
+        operands (forward + data gradient); the first layer reads its fp32 weights and the head its fp32 bias in place.  The eval-mode
+        BatchNorm fold is NOT refreshed here (training uses batch statistics); `Darknet.train(False)` invalidates it."""
+        eng = self.engine
+        units, keys = eng.all_units(), eng.unit_keys()
+        ptrs = tuple(u.conv.weight.data_ptr() for u in units[1:])
+        plan = self._pack_plan
+        if plan is None or plan.key != ptrs or plan.table.device != device:
+            entries = []
+            for u, key in zip(units[1:], keys[1:]):
+                cpad = (u.cout + 31) // 32 * 32 if u.bn is None else 0          # the head's filters are padded to the dz buffer's width
+                entries.append((key, u.conv.weight.detach(), True, True, cpad))
+            plan = self._pack_plan = PackPlan(entries, device)
+        plan.run()
+        units[0].w16 = units[0].conv.weight.detach()
+        for u, key in zip(units[1:], keys[1:]):
+            u.w16 = plan.fwd[key]
+            u._wver = None                      # the eval path re-checks (and may re-pack into its own buffer)
+            self.wd_cache[key] = plan.dgrad[key]
+        head = units[-1]
+        if head.bn is None:
+            one, _ = self._ones(head.cout, device)
+            head.scale = one
+            head.shift = head.conv.bias.detach() if head.conv.bias is not None else self._ones(head.cout, device)[1]
+            head._bver = None
+
     def _sums(self, key, channels, device):
         t = self.sums.get(key)
         if t is None or t.numel() != 2 * channels or t.device != device:
@@ -113,7 +178,8 @@ class DarknetTrainer(object):
         conv epilogue into the unit's double accumulators, so `_bn_forward` does not read z again."""
         one, zero = self._ones(u.cout, src.device)
         self._fused_stats = False
-        if key is not None and self.fuse_stats and not (u.cin == 32 and u.ksize == 3 and u.cout <= 64):
+        c32 = u.cin == 32 and u.ksize == 3 and u.cout <= 64          # the halo-tile kernel: fused statistics need exact 16 x 8 tiling
+        if key is not None and self.fuse_stats and not (c32 and (src.shape[1] % 16 or src.shape[2] % 8)):
             self._fused_stats = True
             return ops.conv_bn_act_stats(src, u.w16, one, zero, 1.0, self._sums(('f', key), u.cout, src.device), out=out)
         return ops.conv_bn_act(src, u.w16, one, zero, 1.0, out=out, **kw)
@@ -167,7 +233,7 @@ class DarknetTrainer(object):
         if eng.precision != 'fast':
             raise RuntimeError("Darknet (B200) training uses fp16 operands with fp32 accumulation; precision='strict' is an inference mode "
                                "(call dnn.engine.set_precision('fast') before train())")
-        eng.refresh(force=True)      # every step: do not trust parameter version counters (fused optimizers do not advance them)
+        self._repack(x.device)       # every step: do not trust parameter version counters (fused optimizers do not advance them)
         for u in eng.all_units()[:-1]:
             if u.bn is None:
                 raise NotImplementedError('training path requires batch_norm/enable = 1')
@@ -184,7 +250,12 @@ class DarknetTrainer(object):
         # layers1.0 (direct from the fp32 image)
         u0 = eng.units1[0]
         z = torch.empty(b, h, w, u0.cout, dtype=torch.float16, device=dev)
-        ops.call('yb_conv0_raw_fwd', x, u0.w16, z, b, h, w, u0.cout)
+        if self.fuse_stats and h % 32 == 0 and w % 16 == 0:
+            # batch statistics accumulated by the conv kernel's copy-out loop: z is not read again for them
+            ops.call('yb_conv0_raw_stats_fwd', x, u0.w16, z, self._sums(('f', 'layers1.0'), u0.cout, dev), b, h, w, u0.cout)
+            self._fused_stats = True
+        else:
+            ops.call('yb_conv0_raw_fwd', x, u0.w16, z, b, h, w, u0.cout)
         mean, invstd = self._bn_forward('layers1.0', u0, z, b * h * w)
         cur = self._apply(u0, z, mean, invstd, b, h, w, True)
         record('layers1.0', u0, None, z, mean, invstd, h, w, True)
@@ -238,6 +309,9 @@ class DarknetTrainer(object):
         cout, cin, k, _ = w.shape
         cp = max(cout, cout_pad)
         wd = self.wd_cache.get(key)
+        plan = self._pack_plan
+        if plan is not None and wd is not None and plan.dgrad.get(key) is wd and wd.shape == (cin, k, k, cp):
+            return wd                         # packed by this step's batched launch (_repack)
         if wd is None or wd.shape != (cin, k, k, cp) or wd.device != w.device:
             wd = torch.empty(cin, k, k, cp, dtype=torch.float16, device=w.device)
             self.wd_cache[key] = wd
@@ -364,9 +438,24 @@ class DarknetTrainer(object):
             g_da, g_dap = (None, g) if prev_pooled else (g, None)
         # layers1.0: weight gradient straight from the fp32 image
         s0 = saved.units['layers1.0']
-        dz0 = self._unit_backward('layers1.0', s0, b, grads, da=g_da, dap=g_dap)
         dw0 = self.arena.views['layers1.0.conv.weight']
-        ops.call('yb_conv0_wgrad', saved.x, dz0, dw0, b, saved.h, saved.w)
+        if g_da is None and g_dap is not None and saved.h % 8 == 0 and saved.w % 32 == 0 and os.environ.get('YB_CONV0_WGRAD_FUSED', '1') != '0':
+            # reduce pass of the BatchNorm backward, then the weight-gradient kernel forms dz itself (in shared memory, from z and the pooled
+            # gradient): the 2 x 708 MB (B = 64 @ 416) write + read of dz and one launch disappear
+            u0 = s0.u
+            sums = self._sums(('b', 'layers1.0'), u0.cout, dev)
+            bnw, bnb = u0.bn.weight.detach(), u0.bn.bias.detach()
+            ops.call('yb_bn_act_bwd', 0, s0.z, s0.z.shape[-1], s0.mean, s0.invstd, bnw, bnb, self.slope, None, 0, 0, g_dap, g_dap.shape[-1], 0,
+                     b, s0.h, s0.w, u0.cout, 1, sums, None, 0, 1)
+            ops.call('yb_conv0_wgrad_bn', saved.x, s0.z, g_dap, g_dap.shape[-1], 0, s0.mean, s0.invstd, bnw, bnb, self.slope, sums, dw0, b, saved.h, saved.w)
+            dgamma, dbeta = self.arena.views['layers1.0.bn.weight'], self.arena.views['layers1.0.bn.bias']
+            ops.call('yb_bn_param_grad', sums, u0.cout, dgamma, dbeta, 1, self._unscale)          # also clears the accumulators (after their last reader)
+            grads['layers1.0.bn.weight'], grads['layers1.0.bn.bias'] = dgamma, dbeta
+            self._emit('layers1.0.bn.weight', grads)
+            self._emit('layers1.0.bn.bias', grads)
+        else:
+            dz0 = self._unit_backward('layers1.0', s0, b, grads, da=g_da, dap=g_dap)
+            ops.call('yb_conv0_wgrad', saved.x, dz0, dw0, b, saved.h, saved.w)
         grads['layers1.0.conv.weight'] = dw0.mul_(self._unscale)
         self._emit('layers1.0.conv.weight', grads)
         self._join(dev)

@@ -68,9 +68,10 @@ int maxpool2x2_split(const void*, void*, int, int, int, int, int, int, int, int,
 int conv_ref_forward(const void*, const void*, const float*, const float*, float, void*, int, int, int, int, int, int, int, long long,
                      int, int, cudaStream_t);
 int pack_weight(const float*, void*, int, int, int, int, int, cudaStream_t);
+int pack_weights_batch(const void*, int, int, cudaStream_t);
 void conv_set_trace(void*);
 int bn_fold(const float*, const float*, const float*, const float*, float, float*, float*, int, cudaStream_t);
-int conv0_tc_forward(const void*, int, const float*, const float*, const float*, float, void*, int, int, int, int, int, cudaStream_t);
+int conv0_tc_forward(const void*, int, const float*, const float*, const float*, float, void*, int, int, int, int, int, double*, cudaStream_t);
 int maxpool2x2(const void*, void*, int, int, int, int, int, cudaStream_t);
 int maxpool2x2_s1(const void*, void*, int, int, int, int, int, cudaStream_t);
 int maxpool2x2_s1_bwd(const void*, const void*, void*, int, int, int, int, cudaStream_t);
@@ -94,6 +95,8 @@ int bn_param_grad(double*, int, float*, float*, int, float, cudaStream_t);
 int reorg_bwd(const void*, long long, int, void*, int, int, int, int, cudaStream_t);
 int head_grad_prepare(const float*, void*, float*, int, int, int, int, cudaStream_t);
 int conv0_wgrad(const float*, const void*, float*, int, int, int, cudaStream_t);
+int conv0_wgrad_bn(const float*, const void*, const void*, long long, int, const float*, const float*, const float*, const float*, float, const double*, float*, int, int, int,
+                   cudaStream_t);
 int resize_batch_u8(const void*, const long long*, const int*, void*, int, int, int, int, float*, float*, int, cudaStream_t);
 int totensor_u8(const void*, float*, int, int, int, cudaStream_t);
 int warp_affine_u8(const void*, int, int, void*, int, int, const double*, const int*, cudaStream_t);
@@ -150,12 +153,12 @@ int yb_bn_fold(const float* gamma, const float* beta, const float* running_mean,
 
 int yb_conv0_bn_leaky_pool_fwd(const float* x_nchw, const float* w_oihw, const float* scale, const float* shift, float slope,
                                void* y_nhwc_f16, int batch, int height, int width, int cout, yb_stream_t stream) {
-  return yb::conv0_tc_forward(x_nchw, 0, w_oihw, scale, shift, slope, y_nhwc_f16, batch, height, width, cout, 0, S(stream));
+  return yb::conv0_tc_forward(x_nchw, 0, w_oihw, scale, shift, slope, y_nhwc_f16, batch, height, width, cout, 0, nullptr, S(stream));
 }
 
 int yb_conv0_u8_bn_leaky_pool_fwd(const unsigned char* x_nhwc_u8, const float* w_oihw, const float* scale, const float* shift,
                                   float slope, void* y_nhwc_f16, int batch, int height, int width, int cout, yb_stream_t stream) {
-  return yb::conv0_tc_forward(x_nhwc_u8, 1, w_oihw, scale, shift, slope, y_nhwc_f16, batch, height, width, cout, 0, S(stream));
+  return yb::conv0_tc_forward(x_nhwc_u8, 1, w_oihw, scale, shift, slope, y_nhwc_f16, batch, height, width, cout, 0, nullptr, S(stream));
 }
 
 int yb_conv_bn_act_fwd(const void* x, const void* w, const float* scale, const float* shift, float slope, void* y, int batch,
@@ -263,7 +266,16 @@ int yb_region_loss_bwd(const float* grad_terms, const float* grad_bg, const floa
 
 int yb_conv0_raw_fwd(const float* x_nchw, const float* w_oihw, void* z_nhwc_f16, int batch, int height, int width, int cout,
                      yb_stream_t stream) {
-  return yb::conv0_tc_forward(x_nchw, 0, w_oihw, nullptr, nullptr, 1.f, z_nhwc_f16, batch, height, width, cout, 1, S(stream));
+  return yb::conv0_tc_forward(x_nchw, 0, w_oihw, nullptr, nullptr, 1.f, z_nhwc_f16, batch, height, width, cout, 1, nullptr, S(stream));
+}
+
+int yb_conv0_raw_stats_fwd(const float* x_nchw, const float* w_oihw, void* z_nhwc_f16, double* sums, int batch, int height, int width, int cout,
+                           yb_stream_t stream) {
+  return yb::conv0_tc_forward(x_nchw, 0, w_oihw, nullptr, nullptr, 1.f, z_nhwc_f16, batch, height, width, cout, 1, sums, S(stream));
+}
+
+int yb_pack_weights_batch(const yb_pack_unit* units_dev, int num_units, int total_blocks, yb_stream_t stream) {
+  return yb::pack_weights_batch(units_dev, num_units, total_blocks, S(stream));
 }
 
 int yb_pack_weight_dgrad_f16(const float* w_oihw, void* w_f16, int cout, int cin, int ksize, int cout_pad, yb_stream_t stream) {
@@ -308,6 +320,12 @@ int yb_head_grad_prepare(const float* dfeature, void* dz_nhwc_f16, float* dbias,
 
 int yb_conv0_wgrad(const float* x_nchw, const void* dz_nhwc_f16, float* dw_oihw, int batch, int height, int width, yb_stream_t stream) {
   return yb::conv0_wgrad(x_nchw, dz_nhwc_f16, dw_oihw, batch, height, width, S(stream));
+}
+
+int yb_conv0_wgrad_bn(const float* x_nchw, const void* z_nhwc_f16, const void* dap, long long ld_dap, int dap_off, const float* mean, const float* invstd,
+                      const float* gamma, const float* beta, float slope, const double* sums, float* dw_oihw, int batch, int height, int width,
+                      yb_stream_t stream) {
+  return yb::conv0_wgrad_bn(x_nchw, z_nhwc_f16, dap, ld_dap, dap_off, mean, invstd, gamma, beta, slope, sums, dw_oihw, batch, height, width, S(stream));
 }
 
 int yb_conv_wgrad(const void* x, const void* dz, float* dw_krsc, int batch, int height, int width, int cin, int cout, int ksize, int x_ld,

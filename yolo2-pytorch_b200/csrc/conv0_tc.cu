@@ -45,6 +45,7 @@ struct Conv0Params {
   int batch, height, width;
   int tiles_x, tiles_y, num_tiles;
   int raw;              // 1: write the raw conv output, unpooled fp16 NHWC [B,H,W,32] (training forward)
+  double* stats;        // raw form of conv0_k16_kernel: += sum z, sum z^2 per channel ([2][32]); may be null
   int* dbg;
 };
 
@@ -264,8 +265,17 @@ constexpr int kV2Copy = kV2PR * kV2Pitch;                       // 4896 B
 constexpr int kV2Pixels = kV2PR * kV2PC;                        // 612
 constexpr int kV2Iters = (kV2Pixels + 127) / 128;               // 5 pixels per thread
 
-template <bool kU8>
+// kRaw (training forward): the un-normalised conv output z goes out at full resolution.  Written 16 B per lane straight from the TMEM layout,
+// every store instruction touched 32 different 128-byte lines (the kernel ran at 2.2 TB/s, bound by L2 write transactions); instead the tile is
+// staged in shared memory (swizzled, conflict-free) and leaves as 512 contiguous bytes per warp instruction.  The copy-out loop hands every thread
+// the same 8 channels on every trip, so the BatchNorm batch statistics (sum z, sum z^2 of the fp16 values that are stored) accumulate in 16
+// registers over all of the CTA's tiles and are reduced once at the end (p.stats: double [2][32], as yb_bn_stats).
+constexpr int kV2StageBytes = kV2Rows * kV2Cols * kC0Out * 2;   // 32 KB
+
+template <bool kU8, bool kRaw>
 __global__ void __launch_bounds__(128, 4) conv0_k16_kernel(const Conv0Params p) {
+  __shared__ __align__(128) uint8_t stage[kRaw ? kV2StageBytes : 16];
+  __shared__ float s_stats[2 * kC0Out];
   __shared__ __align__(128) uint8_t patch_e[kV2Copy + 48];      // pixel (r, c) at (r * 18 + c) * 8: even columns 16 B aligned
   __shared__ __align__(128) uint8_t patch_o[kV2Copy + 48];      // the same pixels at + 8 B: odd columns 16 B aligned
   __shared__ __align__(128) uint8_t b_smem[3 * 1024];           // per filter row: [n / 8][k / 8][n % 8][k % 8] fp16 (32 x 16)
@@ -339,6 +349,10 @@ __global__ void __launch_bounds__(128, 4) conv0_k16_kernel(const Conv0Params p) 
   };
   float pre[kV2Iters][3];
   if (static_cast<int>(blockIdx.x) < p.num_tiles) prefetch(blockIdx.x, pre);
+  float st1[8], st2[8];                           // kRaw: statistics of channels (tid & 3) * 8 .. + 7
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { st1[e] = 0.f; st2[e] = 0.f; }
+  if (kRaw && tid < 2 * kC0Out) s_stats[tid] = 0.f;
 
   for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
     const int tx = tile % p.tiles_x;
@@ -390,11 +404,13 @@ __global__ void __launch_bounds__(128, 4) conv0_k16_kernel(const Conv0Params p) 
 #pragma unroll
       for (int j = 0; j < 4; ++j) tmem_ld_32x32b_x8(lane_addr + j * kC0Out + g * 8, v[j]);
       tmem_ld_wait();
-      if (p.raw) {
+      if constexpr (kRaw) {
+        // pixel (row, col) of the tile lives at slot col' = col / 2 + (col & 1) * 8 of its row (the eight lanes of a quarter-warp then fill
+        // eight consecutive 64-byte slots), 16-byte chunk g at g ^ ((col / 4) & 3)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int yy = ty * kV2Rows + 2 * wy + (j >> 1), xx = tx * kV2Cols + 2 * wx + (j & 1);
-          *reinterpret_cast<uint4*>(p.y + ((static_cast<long long>(img) * p.height + yy) * p.width + xx) * kC0Out + g * 8) =
+          const int row = 2 * wy + (j >> 1), slot = wx + (j & 1) * 8;
+          *reinterpret_cast<uint4*>(stage + (row * kV2Cols + slot) * (kC0Out * 2) + ((g ^ ((wx >> 1) & 3)) << 4)) =
               make_uint4(pack_h2(__uint_as_float(v[j][0]), __uint_as_float(v[j][1])), pack_h2(__uint_as_float(v[j][2]), __uint_as_float(v[j][3])),
                          pack_h2(__uint_as_float(v[j][4]), __uint_as_float(v[j][5])), pack_h2(__uint_as_float(v[j][6]), __uint_as_float(v[j][7])));
         }
@@ -416,6 +432,49 @@ __global__ void __launch_bounds__(128, 4) conv0_k16_kernel(const Conv0Params p) 
       *reinterpret_cast<uint4*>(dst + g * 8) = make_uint4(pack_h2(m[0], m[1]), pack_h2(m[2], m[3]), pack_h2(m[4], m[5]), pack_h2(m[6], m[7]));
     }
     tc_fence_before();
+    if constexpr (kRaw) {
+      __syncthreads();                              // the whole tile is staged
+      // 2048 chunks of 16 B: chunk c = i * 128 + tid -> row c / 64, (col, g) = c % 64 = tid % 64 on every trip
+      const int cr = tid & 63, col = cr >> 2, gq = cr & 3;
+      const int src_off = ((col >> 1) + (col & 1) * 8) * (kC0Out * 2) + ((gq ^ ((col >> 2) & 3)) << 4);
+      __half* dst = p.y + ((static_cast<long long>(img) * p.height + ty * kV2Rows) * p.width + tx * kV2Cols) * kC0Out + cr * 8;
+#pragma unroll 4
+      for (int i = 0; i < kV2Rows / 2; ++i) {
+        const int row = 2 * i + (tid >> 6);
+        const uint4 q = *reinterpret_cast<const uint4*>(stage + row * (kV2Cols * kC0Out * 2) + src_off);
+        *reinterpret_cast<uint4*>(dst + static_cast<long long>(row) * p.width * kC0Out) = q;
+        if (p.stats != nullptr) {
+          const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(h[e]);
+            st1[2 * e] += f.x; st2[2 * e] = fmaf(f.x, f.x, st2[2 * e]);
+            st1[2 * e + 1] += f.y; st2[2 * e + 1] = fmaf(f.y, f.y, st2[2 * e + 1]);
+          }
+        }
+      }
+      // the next iteration's __syncthreads (after the patch is written) orders this copy-out before the next tile's staging stores
+    }
+  }
+  if (kRaw && p.stats != nullptr) {
+    // lanes with equal (lane & 3) hold the same 8 channels
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+#pragma unroll
+      for (int sft = 4; sft <= 16; sft <<= 1) {
+        st1[e] += __shfl_xor_sync(0xffffffffu, st1[e], sft);
+        st2[e] += __shfl_xor_sync(0xffffffffu, st2[e], sft);
+      }
+    }
+    if ((tid & 31) < 4) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        atomicAdd(&s_stats[(tid & 3) * 8 + e], st1[e]);
+        atomicAdd(&s_stats[kC0Out + (tid & 3) * 8 + e], st2[e]);
+      }
+    }
+    __syncthreads();
+    if (tid < 2 * kC0Out) atomicAdd(p.stats + tid, static_cast<double>(s_stats[tid]));
   }
   tc_fence_before();
   __syncthreads();
@@ -426,7 +485,7 @@ __global__ void __launch_bounds__(128, 4) conv0_k16_kernel(const Conv0Params p) 
 }
 
 int conv0_tc_forward(const void* x, int x_is_u8, const float* w, const float* scale, const float* shift, float slope, void* y, int batch,
-                     int height, int width, int cout, int raw, cudaStream_t stream) {
+                     int height, int width, int cout, int raw, double* stats, cudaStream_t stream) {
   YB_REQUIRE(x && w && y && (raw || (scale && shift)), "conv0: null pointer");
   YB_REQUIRE(cout == kC0Out, "conv0: Cout=%d unsupported (32)", cout);
   YB_REQUIRE(batch > 0 && height > 0 && width > 0 && height % kT0Rows == 0 && width % kT0Cols == 0,
@@ -443,13 +502,21 @@ int conv0_tc_forward(const void* x, int x_is_u8, const float* w, const float* sc
   YB_REQUIRE(tiles < (1ll << 31), "conv0: too many tiles");
   p.num_tiles = static_cast<int>(tiles);
   p.raw = raw;
+  p.stats = stats;
+  YB_REQUIRE(stats == nullptr || (raw && v2 && !x_is_u8), "conv0: fused statistics need the raw fp32-input form on a 32 x 16-tileable image");
   if (raw) { p.scale = w; p.shift = w; }   // unused in raw mode, must be readable
   p.dbg = debug_word_device();
   const int max_ctas = sm_count() * 4;
   const int grid = p.num_tiles < max_ctas ? p.num_tiles : max_ctas;
   if (v2) {
-    if (x_is_u8) conv0_k16_kernel<true><<<grid, 128, 0, stream>>>(p);
-    else conv0_k16_kernel<false><<<grid, 128, 0, stream>>>(p);
+    if (x_is_u8) {
+      YB_REQUIRE(!raw, "conv0: the uint8 input form has no raw output");
+      conv0_k16_kernel<true, false><<<grid, 128, 0, stream>>>(p);
+    } else if (raw) {
+      conv0_k16_kernel<false, true><<<grid, 128, 0, stream>>>(p);
+    } else {
+      conv0_k16_kernel<false, false><<<grid, 128, 0, stream>>>(p);
+    }
     return check_launch("conv0_k16_kernel");
   }
   if (x_is_u8) conv0_tc_kernel<true><<<grid, 128, 0, stream>>>(p);

@@ -853,6 +853,7 @@ struct C32Params {
   int skip;
   int* dbg;
   unsigned long long* trace;
+  double* stats;  // training forward: += per-channel sum / sum of squares of the stored values ([2][cout]); needs exact tiling, no pool
 };
 
 struct C32Cfg {
@@ -869,7 +870,7 @@ struct C32Cfg {
   static constexpr int kGroups = 3;                               // epilogue groups of four warps (tools/conv_ablate.py: the per-tile epilogue chain, not the MMA, bounds this kernel)
   static constexpr int kEpiThreads = kGroups * 128;
   static constexpr int kThreads = 64 + kEpiThreads;
-  static constexpr int kSmemBytes = 1024 + kBBytes + 2 * kGroups * kOutBytes + kStages * kHalo + 2 * BN * 4 + 256;
+  static constexpr int kSmemBytes = 1024 + kBBytes + 2 * kGroups * kOutBytes + kStages * kHalo + 2 * BN * 4 + 256 + 2 * BN * 4 /*stats*/;
 };
 
 __global__ void __launch_bounds__(C32Cfg::kThreads, 1)
@@ -892,6 +893,7 @@ conv_c32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   const uint32_t bar_tempty = bar_tfull + 8 * Cfg::kAccStages;
   const uint32_t bar_w = bar_tempty + 8 * Cfg::kAccStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 2 * Cfg::kAccStages + 1);
+  float* ep_stats = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);      // [2][BN], accumulated over all of this CTA's tiles
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -974,6 +976,7 @@ conv_c32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     for (int i = et; i < BN; i += Cfg::kEpiThreads) {
       ep_scale[i] = (i < p.cout) ? __ldg(p.scale + i) : 0.f;
       ep_shift[i] = (i < p.cout) ? __ldg(p.shift + i) : 0.f;
+      ep_stats[i] = 0.f; ep_stats[BN + i] = 0.f;
     }
     asm volatile("bar.sync 8, %0;" :: "n"(Cfg::kEpiThreads) : "memory");
     const int m = q * 32 + lane;            // tile-local pixel: row m >> 3, column m & 7
@@ -1016,6 +1019,28 @@ conv_c32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           f[j4 * 4 + 0] = x0 > 0.f ? x0 : x0 * p.slope; f[j4 * 4 + 1] = x1 > 0.f ? x1 : x1 * p.slope;
           f[j4 * 4 + 2] = x2 > 0.f ? x2 : x2 * p.slope; f[j4 * 4 + 3] = x3 > 0.f ? x3 : x3 * p.slope;
         }
+        if (p.stats != nullptr) {
+          // column sums over this warp's 32 pixels by recursive halving (as conv_igemm_kernel): lane l ends up with channel half * 32 + l
+          float a1[32], a2[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float r = __half2float(__float2half_rn(f[j]));          // statistics of the value that is stored
+            a1[j] = r; a2[j] = r * r;
+          }
+#pragma unroll
+          for (int sft = 16; sft >= 1; sft >>= 1) {
+            const bool up = (lane & sft) != 0;
+#pragma unroll
+            for (int j = 0; j < sft; ++j) {
+              const float k1 = up ? a1[j + sft] : a1[j], g1 = up ? a1[j] : a1[j + sft];
+              const float k2 = up ? a2[j + sft] : a2[j], g2 = up ? a2[j] : a2[j + sft];
+              a1[j] = k1 + __shfl_xor_sync(0xffffffffu, g1, sft);
+              a2[j] = k2 + __shfl_xor_sync(0xffffffffu, g2, sft);
+            }
+          }
+          atomicAdd(&ep_stats[half * 32 + lane], a1[0]);
+          atomicAdd(&ep_stats[BN + half * 32 + lane], a2[0]);
+        }
         if (p.pool) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -1049,6 +1074,13 @@ conv_c32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       if (et == 0) { YB_TRACE(2, tr); ++tr; }
     }
     if (gt == 0) tma_store_wait<0>();
+    if (p.stats != nullptr) {
+      asm volatile("bar.sync 8, %0;" :: "n"(Cfg::kEpiThreads) : "memory");       // every group has added its last tile
+      for (int i = et; i < p.cout; i += Cfg::kEpiThreads) {
+        atomicAdd(p.stats + i, static_cast<double>(ep_stats[i]));
+        atomicAdd(p.stats + p.cout + i, static_cast<double>(ep_stats[BN + i]));
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -1148,7 +1180,8 @@ static int dispatch_conv(int bn, int mt, const CUtensorMap& ta, const CUtensorMa
 }
 
 static int conv_c32_forward(const void* x, const void* w, const float* scale, const float* shift, float slope, void* y, int batch,
-                            int height, int width, int cout, int x_ld, long long y_ld, int y_ch_off, int pool, int flags, cudaStream_t stream) {
+                            int height, int width, int cout, int x_ld, long long y_ld, int y_ch_off, int pool, int flags, double* stats,
+                            cudaStream_t stream) {
   using Cfg = C32Cfg;
   EncodeTiledFn enc_tiled;
   EncodeIm2colFn enc_im2col;
@@ -1168,6 +1201,9 @@ static int conv_c32_forward(const void* x, const void* w, const float* scale, co
   p.skip = (flags >> 24) & 0xF;
   p.dbg = debug_word_device();
   p.trace = g_conv_trace;
+  p.stats = stats;
+  YB_REQUIRE(stats == nullptr || (!pool && height % Cfg::TH == 0 && width % Cfg::TW == 0),
+             "conv: fused statistics on the Cin = 32 kernel need H %% 16 == 0, W %% 8 == 0 and no fused pool");
   alignas(64) CUtensorMap tx, tw, ty;
   CUresult cr;
   {
@@ -1219,7 +1255,7 @@ int conv_igemm_forward(const void* x, const void* w, const float* scale, const f
   YB_REQUIRE(a_channels <= cin && a_channels % 32 == 0 && cin - a_channels <= a_channels, "conv: a_channels=%d does not fit cin=%d", a_channels, cin);
   YB_REQUIRE(lo_ch_off < 0 || (out_mode == 0 && stats == nullptr && lo_ch_off % 8 == 0 && lo_ch_off >= y_ch_off + cout && lo_ch_off + cout <= y_ld),
              "conv: lo_ch_off=%d (needs fp16 NHWC output with room for a second Cout-wide slice)", lo_ch_off);
-  YB_REQUIRE(stats == nullptr || (out_mode == 0 && !(cin == 32 && ksize == 3 && cout <= 64)), "conv: fused statistics need the generic fp16 NHWC kernel");
+  YB_REQUIRE(stats == nullptr || out_mode == 0, "conv: fused statistics need the fp16 NHWC output");
   YB_REQUIRE(ksize == 1 || ksize == 3, "conv: ksize %d unsupported (1 or 3)", ksize);
   YB_REQUIRE(batch > 0 && height > 0 && width > 0, "conv: bad shape");
   YB_REQUIRE(cin % 32 == 0, "conv: Cin=%d must be a multiple of 32 (layer 0 uses yb_conv0_*)", cin);
@@ -1235,7 +1271,7 @@ int conv_igemm_forward(const void* x, const void* w, const float* scale, const f
   const int pool = (flags >> 4) & 1;        // YB_CONV_POOL2X2
   // 3x3, Cin = 32, Cout <= 64 (layers1.2): halo-tile kernel unless a test asks for one of the im2col kernels
   if (!split && cin == 32 && ksize == 3 && cout <= 64 && out_mode == 0 && ((flags >> 28) & 1) == 0 && ((flags >> 5) & 1) == 0 && ((flags >> 8) & 0xFFFF) == 0)
-    return conv_c32_forward(x, w, scale, shift, slope, y, batch, height, width, cout, x_ld, y_ld, y_ch_off, pool, flags, stream);
+    return conv_c32_forward(x, w, scale, shift, slope, y, batch, height, width, cout, x_ld, y_ld, y_ch_off, pool, flags, stats, stream);
   if (pool) return fail(YB_ERR_UNSUPPORTED, "conv: YB_CONV_POOL2X2 is only implemented for the Cin = 32 3x3 layer");
   const int bk = (cin % 64 == 0 && a_channels % 64 == 0) ? 64 : 32;     // K-blocks never straddle the wrap point
   // tile shape: flags may force BLOCK_N (bits 8..17) and the number of M-subtiles (bits 20..21);

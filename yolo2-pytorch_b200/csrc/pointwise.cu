@@ -64,6 +64,73 @@ int pack_weight(const float* w, void* out, int cout, int cin, int k, int mode, i
   return check_launch("pack_weight_kernel");
 }
 
+// Both training operands of MANY units in one launch (yb_pack_weights_batch): every block converts one 64-filter x (32 channels x 9 taps | 256
+// channels) tile of one unit -- found from the unit table's running block offsets -- reads the fp32 OIHW rows coalesced ONCE, and writes the
+// forward operand out_f[co][tap][ci] and the data-gradient operand out_d[ci][k*k-1-tap][co] (rotated, filters zero-padded to cout_pad) as
+// 4-byte pairs along their contiguous dimension.  Replaces 2 launches per unit (44 per Darknet-19 step, most of them latency-bound).
+struct PackUnit {
+  const float* w;
+  __half* out_f;      // may be null
+  __half* out_d;      // may be null
+  int cout, cin, k, cout_pad, block0, ci_blocks;
+};
+constexpr int kPackCo = 64, kPackPitch = 290;      // halves per staged filter row (288 + 2: odd word pitch)
+
+__global__ void __launch_bounds__(256) pack_weights_batch_kernel(const PackUnit* __restrict__ units, int num_units) {
+  __shared__ __half tile[kPackCo * kPackPitch];
+  __shared__ int s_unit;
+  if (threadIdx.x == 0) {
+    int u = 0;
+    while (u + 1 < num_units && static_cast<int>(blockIdx.x) >= units[u + 1].block0) ++u;
+    s_unit = u;
+  }
+  __syncthreads();
+  const PackUnit pu = units[s_unit];
+  const int k2 = pu.k * pu.k;
+  const int chunk = pu.k == 3 ? 32 : 256;                         // input channels per tile (<= 288 staged columns)
+  const int local = static_cast<int>(blockIdx.x) - pu.block0;
+  const int co0 = (local / pu.ci_blocks) * kPackCo, ci0 = (local % pu.ci_blocks) * chunk;
+  const int nci = pu.cin - ci0 < chunk ? pu.cin - ci0 : chunk;     // even (cin % 2 == 0 is required)
+  const int ncols = nci * k2;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int r = warp; r < kPackCo; r += 8) {
+    const int co = co0 + r;
+    const float* src = pu.w + (static_cast<long long>(co) * pu.cin + ci0) * k2;
+    for (int c = lane; c < ncols; c += 32) tile[r * kPackPitch + c] = __float2half_rn(co < pu.cout ? __ldg(src + c) : 0.f);
+  }
+  __syncthreads();
+  if (pu.out_f != nullptr) {
+    const int half_ci = nci >> 1;
+    const int items = kPackCo * k2 * half_ci;
+    for (int i = tid; i < items; i += 256) {
+      const int cp = i % half_ci, rt = i / half_ci;
+      const int tap = rt % k2, r = rt / k2;
+      const int co = co0 + r;
+      if (co >= pu.cout) break;                                     // rows ascend with i
+      const __half2 v = __halves2half2(tile[r * kPackPitch + (2 * cp) * k2 + tap], tile[r * kPackPitch + (2 * cp + 1) * k2 + tap]);
+      *reinterpret_cast<__half2*>(pu.out_f + (static_cast<long long>(co) * k2 + tap) * pu.cin + ci0 + 2 * cp) = v;
+    }
+  }
+  if (pu.out_d != nullptr) {
+    const int items = ncols * (kPackCo / 2);
+    for (int i = tid; i < items; i += 256) {
+      const int cp = i & (kPackCo / 2 - 1), col = i / (kPackCo / 2);
+      const int co = co0 + 2 * cp;
+      if (co >= pu.cout_pad) continue;
+      const int ci = col / k2, tap = col - ci * k2;
+      const __half2 v = __halves2half2(tile[(2 * cp) * kPackPitch + col], tile[(2 * cp + 1) * kPackPitch + col]);
+      *reinterpret_cast<__half2*>(pu.out_d + (static_cast<long long>(ci0 + ci) * k2 + (k2 - 1 - tap)) * pu.cout_pad + co) = v;
+    }
+  }
+}
+
+int pack_weights_batch(const void* units_dev, int num_units, int total_blocks, cudaStream_t stream) {
+  YB_REQUIRE(units_dev && num_units > 0 && total_blocks > 0, "pack_weights_batch: bad argument");
+  static_assert(sizeof(PackUnit) == 48, "PackUnit must match yb_pack_unit");
+  pack_weights_batch_kernel<<<total_blocks, 256, 0, stream>>>(static_cast<const PackUnit*>(units_dev), num_units);
+  return check_launch("pack_weights_batch_kernel");
+}
+
 // Split-precision B operand (strict mode, see ConvParams::a_wrap in conv_igemm.cu): out[co][tap][s*Cin + ci] for s in [0, segments),
 // segment s holding w_hi = fp16(w) or, where bit s of lo_mask is set, w_lo = fp16(w - fp32(w_hi)).  Same tiling as mode 0.
 __global__ void __launch_bounds__(128) pack_weight_split_kernel(const float* __restrict__ w, __half* __restrict__ out, int cin, int k, int segments,

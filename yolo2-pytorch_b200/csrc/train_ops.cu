@@ -561,14 +561,44 @@ struct W0Smem {
   __align__(16) __half dzs[2][kW0Rows * kW0Cols][kW0DzStride];
   float s_dw[32 * 32];            // [tap (padded)][co]
 };
+// fused form: dz is never in memory.  The staged tile holds the raw conv output z; the gradient arriving through the unit's 2x2 max-pool
+// (one 64-byte row per window) is staged next to it and the BatchNorm + leaky + pool backward (bn_act_bwd_kernel<1, 1, 0>'s arithmetic)
+// turns z into dz in place, in shared memory, before the tensor-core pass.
+struct W0SmemFused {
+  W0Smem base;
+  __align__(16) __half dap[2][(kW0Rows / 2) * (kW0Cols / 2)][32];
+  float k[6][32];                 // sc, sh, xa, xb, k1, k2 per channel
+};
+struct W0Fuse {
+  const __half* z;                // [B,H,W,32] raw conv output of the forward pass
+  const __half* dap; long long ld_dap; int dap_off;     // [B,H/2,W/2,*] gradient of the pooled activation
+  const float *mean, *invstd, *gamma, *beta;
+  float slope;
+  const double* sums;             // pass-1 sums of this unit (sum dy, sum dy * xhat)
+};
 
+template <bool kFused>
 __global__ void __launch_bounds__(256) conv0_wgrad_kernel(const float* __restrict__ x, const __half* __restrict__ dz, float* __restrict__ dw, int batch,
-                                                          int height, int width, int tiles_x, int tiles_y, int num_tiles) {
+                                                          int height, int width, int tiles_x, int tiles_y, int num_tiles, const W0Fuse fz) {
   extern __shared__ __align__(16) uint8_t w0_raw[];
   W0Smem& sm = *reinterpret_cast<W0Smem*>(w0_raw);
+  W0SmemFused& smf = *reinterpret_cast<W0SmemFused*>(w0_raw);       // only touched when kFused
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   for (int i = tid; i < 32 * 32; i += 256) sm.s_dw[i] = 0.f;
+  if (kFused) {
+    if (tid < 32) {
+      const float inv_rows = 1.f / static_cast<float>(static_cast<long long>(batch) * height * width);
+      const float istd = __ldg(fz.invstd + tid), sc = __ldg(fz.gamma + tid) * istd, mu = __ldg(fz.mean + tid);
+      smf.k[0][tid] = sc;
+      smf.k[1][tid] = __ldg(fz.beta + tid) - mu * sc;
+      smf.k[2][tid] = istd;
+      smf.k[3][tid] = -mu * istd;
+      smf.k[4][tid] = sc * (static_cast<float>(fz.sums[tid]) * inv_rows);
+      smf.k[5][tid] = sc * (static_cast<float>(fz.sums[32 + tid]) * inv_rows);
+    }
+    dz = fz.z;                     // the staged tile starts as z
+  }
   float acc[2][4][4];
 #pragma unroll
   for (int a = 0; a < 2; ++a)
@@ -612,6 +642,12 @@ __global__ void __launch_bounds__(256) conv0_wgrad_kernel(const float* __restric
       const int py = pix / kW0Cols, pxx = pix % kW0Cols;
       cp_async_16(&sm.dzs[buf][pix][part * 8], dz + ((static_cast<long long>(img) * height + y0 + py) * width + x0 + pxx) * 32 + part * 8);
     }
+    if (kFused) {                                                    // one 16-byte piece per thread: 64 windows x 4
+      const int win = tid >> 2, part = tid & 3;
+      const int wy = win / (kW0Cols / 2), wx = win % (kW0Cols / 2);
+      cp_async_16(&smf.dap[buf][win][part * 8],
+                  fz.dap + ((static_cast<long long>(img) * (height >> 1) + (y0 >> 1) + wy) * (width >> 1) + (x0 >> 1) + wx) * fz.ld_dap + fz.dap_off + part * 8);
+    }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
@@ -626,6 +662,41 @@ __global__ void __launch_bounds__(256) conv0_wgrad_kernel(const float* __restric
       asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
+    if (kFused) {
+      // thread = 8 channels (cg) of one pool window: z -> dz in place (first maximum takes the pooled gradient, as torch routes it)
+      const int win = tid >> 2, cg = tid & 3;
+      const int wy = win / (kW0Cols / 2), wx = win % (kW0Cols / 2);
+      float zf[4][8], gp[8];
+      __half* zp[4];
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        zp[w] = &sm.dzs[buf][(2 * wy + (w >> 1)) * kW0Cols + 2 * wx + (w & 1)][cg * 8];
+        h8_to_f(*reinterpret_cast<const uint4*>(zp[w]), zf[w]);
+      }
+      h8_to_f(*reinterpret_cast<const uint4*>(&smf.dap[buf][win][cg * 8]), gp);
+      float out[4][8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = cg * 8 + i;
+        const float sc = smf.k[0][c], sh = smf.k[1][c], xa = smf.k[2][c], xb = smf.k[3][c], k1 = smf.k[4][c], k2 = smf.k[5][c];
+        float besty = fmaf(zf[0][i], sc, sh);
+        int arg = 0;
+#pragma unroll
+        for (int w = 1; w < 4; ++w) {
+          const float y = fmaf(zf[w][i], sc, sh);
+          if (y > besty) { besty = y; arg = w; }
+        }
+        const float dyb = besty > 0.f ? gp[i] : gp[i] * fz.slope;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const float base = -fmaf(k2, fmaf(zf[w][i], xa, xb), k1);
+          out[w][i] = arg == w ? fmaf(sc, dyb, base) : base;
+        }
+      }
+#pragma unroll
+      for (int w = 0; w < 4; ++w) *reinterpret_cast<uint4*>(zp[w]) = f_to_h8(out[w]);
+      __syncthreads();
+    }
     const float* pflat = &sm.patch[buf][0][0][0];
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
@@ -680,23 +751,47 @@ __global__ void __launch_bounds__(256) conv0_wgrad_kernel(const float* __restric
   }
 }
 
-int conv0_wgrad(const float* x, const void* dz, float* dw, int batch, int height, int width, cudaStream_t stream) {
-  YB_REQUIRE(x && dz && dw && batch > 0 && height % kW0Rows == 0 && width % kW0Cols == 0, "conv0_wgrad: H %% 8 == 0 and W %% 32 == 0 required");
+static int conv0_wgrad_launch(const float* x, const void* dz, float* dw, int batch, int height, int width, const W0Fuse* fz, cudaStream_t stream) {
+  YB_REQUIRE(x && dw && batch > 0 && height % kW0Rows == 0 && width % kW0Cols == 0, "conv0_wgrad: H %% 8 == 0 and W %% 32 == 0 required");
   YB_CUDA(cudaMemsetAsync(dw, 0, 27 * 32 * sizeof(float), stream));
   const int tiles_x = width / kW0Cols, tiles_y = height / kW0Rows;
   const long long tiles = static_cast<long long>(tiles_x) * tiles_y * batch;
-  static int resident = 0;                       // persistent blocks: exactly what fits (a partial second wave would double the time)
-  const int smem = static_cast<int>(sizeof(W0Smem));
-  if (resident == 0) {
-    YB_CUDA(cudaFuncSetAttribute(conv0_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    YB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, conv0_wgrad_kernel, 256, smem));
-    if (resident < 1) resident = 1;
+  static int resident[2] = {0, 0};               // persistent blocks: exactly what fits (a partial second wave would double the time)
+  const int fused = fz != nullptr;
+  const int smem = static_cast<int>(fused ? sizeof(W0SmemFused) : sizeof(W0Smem));
+  if (resident[fused] == 0) {
+    if (fused) {
+      YB_CUDA(cudaFuncSetAttribute(conv0_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      YB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident[1], conv0_wgrad_kernel<true>, 256, smem));
+    } else {
+      YB_CUDA(cudaFuncSetAttribute(conv0_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      YB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident[0], conv0_wgrad_kernel<false>, 256, smem));
+    }
+    if (resident[fused] < 1) resident[fused] = 1;
   }
-  const int cap = sm_count() * resident;
+  const int cap = sm_count() * resident[fused];
   const int grid = tiles < cap ? static_cast<int>(tiles) : cap;
-  conv0_wgrad_kernel<<<grid, 256, smem, stream>>>(x, reinterpret_cast<const __half*>(dz), dw, batch, height, width, tiles_x, tiles_y,
-                                               static_cast<int>(tiles));
+  if (fused)
+    conv0_wgrad_kernel<true><<<grid, 256, smem, stream>>>(x, nullptr, dw, batch, height, width, tiles_x, tiles_y, static_cast<int>(tiles), *fz);
+  else
+    conv0_wgrad_kernel<false><<<grid, 256, smem, stream>>>(x, reinterpret_cast<const __half*>(dz), dw, batch, height, width, tiles_x, tiles_y,
+                                                          static_cast<int>(tiles), W0Fuse{});
   return check_launch("conv0_wgrad_kernel");
+}
+
+int conv0_wgrad(const float* x, const void* dz, float* dw, int batch, int height, int width, cudaStream_t stream) {
+  YB_REQUIRE(dz, "conv0_wgrad: dz missing");
+  return conv0_wgrad_launch(x, dz, dw, batch, height, width, nullptr, stream);
+}
+
+// Weight gradient of the first layer with the BatchNorm + leaky + 2x2 max-pool backward of that layer fused in (second pass: `sums` already
+// holds sum dy, sum dy * xhat from bn_act_bwd mode 0): reads z and the pooled gradient, never writes dz (no data gradient is needed for the image).
+int conv0_wgrad_bn(const float* x, const void* z, const void* dap, long long ld_dap, int dap_off, const float* mean, const float* invstd,
+                   const float* gamma, const float* beta, float slope, const double* sums, float* dw, int batch, int height, int width,
+                   cudaStream_t stream) {
+  YB_REQUIRE(z && dap && mean && invstd && gamma && beta && sums && ld_dap >= 32 && ld_dap % 8 == 0 && dap_off % 8 == 0, "conv0_wgrad_bn: bad argument");
+  W0Fuse fz{reinterpret_cast<const __half*>(z), reinterpret_cast<const __half*>(dap), ld_dap, dap_off, mean, invstd, gamma, beta, slope, sums};
+  return conv0_wgrad_launch(x, nullptr, dw, batch, height, width, &fz, stream);
 }
 
 // ------------------------------------------------------------------------------------------------
