@@ -489,6 +489,29 @@ def mobilenet_record(args, device, peaks):
             t, fl, by, n = agg[kind]
             out['depthwise' if kind == 'dw' else 'first_conv'] = dict(launches=n // reps, us=t * 1e3, alg_bytes=by, achieved_gbs=by / t / 1e6,
                                                                         frac_of_hbm_peak=by / t / 1e6 / peaks['hbm'])
+    # strict precision ([hi | lo] activations, split-precision pointwise convs; 1e-3 contract, tests/test_gpu_parity.py): cost of the mode
+    try:
+        f_fast = dnn(xs[0]).clone()
+        dnn.set_precision('strict')
+        f_strict = dnn(xs[0]).clone()
+        torch.cuda.synchronize()
+        gs = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gs):
+            chain(xs[1])
+        for _ in range(3):
+            gs.replay()
+        s.record()
+        for _ in range(steps):
+            gs.replay()
+        e.record()
+        torch.cuda.synchronize()
+        ms_s = s.elapsed_time(e) / steps
+        out['strict'] = dict(value=B / (ms_s / 1e3), ms_per_step=ms_s, cost_vs_fast=ms_s / ms,
+                             fast_vs_strict_feature_rel_err=float(((f_fast - f_strict).abs().max() / f_strict.abs().max()).item()))
+    except Exception as ex:     # the headline record must not depend on the optional mode
+        out['strict'] = dict(error='%s: %s' % (type(ex).__name__, ex))
+    finally:
+        dnn.set_precision('fast')
     return out
 
 

@@ -62,6 +62,8 @@ SIGNATURES = {
     'yb_totensor_u8': [P, P, c_int, c_int, c_int, P],
     'yb_eval_match': [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_float, c_float, P, P],
     'yb_mb_conv0_raw_fwd': [P, P, P, c_int, c_int, c_int, P],
+    'yb_mb_conv0_split_fwd': [P, P, P, P, P, c_int, c_int, c_int, P],
+    'yb_dwconv3x3_split_fwd': [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P],
     'yb_mb_conv0_wgrad': [P, P, P, c_int, c_int, c_int, P],
     'yb_dwconv3x3_raw_fwd': [P, P, P, c_int, c_int, c_int, c_int, c_int, P],
     'yb_dwconv3x3_dgrad': [P, P, P, c_int, c_int, c_int, c_int, c_int, P],

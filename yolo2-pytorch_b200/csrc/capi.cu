@@ -117,7 +117,8 @@ int comm_init(void**, int, const void*, int);
 int comm_destroy(void*);
 int allreduce_bucket(void*, void*, long long, int, cudaStream_t);
 int broadcast_buffer(void*, void*, long long, int, int, cudaStream_t);
-int mb_conv0(const float*, const float*, const float*, const float*, void*, int, int, int, int, cudaStream_t);
+int mb_conv0(const float*, const float*, const float*, const float*, void*, int, int, int, int, int, cudaStream_t);
+int dwconv3x3_split(const void*, const float*, const float*, const float*, void*, int, int, int, int, int, cudaStream_t);
 int dwconv3x3(const void*, const float*, const float*, const float*, void*, int, int, int, int, int, int, cudaStream_t);
 int dw_dgrad(const void*, const float*, void*, int, int, int, int, int, cudaStream_t);
 int dw_wgrad(const void*, const void*, float*, int, int, int, int, int, cudaStream_t);
@@ -369,11 +370,21 @@ int yb_eval_match(const float* det_yx_min, const float* det_yx_max, const int* d
 
 int yb_mb_conv0_bn_relu_fwd(const float* x_nchw, const float* w_oihw, const float* scale, const float* shift, void* y_nhwc_f16, int batch,
                             int height, int width, yb_stream_t stream) {
-  return yb::mb_conv0(x_nchw, w_oihw, scale, shift, y_nhwc_f16, batch, height, width, 0, S(stream));
+  return yb::mb_conv0(x_nchw, w_oihw, scale, shift, y_nhwc_f16, batch, height, width, 0, 0, S(stream));
+}
+
+int yb_mb_conv0_split_fwd(const float* x_nchw, const float* w_oihw, const float* scale, const float* shift, void* y_hi_lo, int batch, int height, int width,
+                          yb_stream_t stream) {
+  return yb::mb_conv0(x_nchw, w_oihw, scale, shift, y_hi_lo, batch, height, width, 0, 1, S(stream));
+}
+
+int yb_dwconv3x3_split_fwd(const void* x_hi_lo, const float* w_c9, const float* scale, const float* shift, void* y_hi_lo, int batch, int height, int width,
+                           int channels, int stride, yb_stream_t stream) {
+  return yb::dwconv3x3_split(x_hi_lo, w_c9, scale, shift, y_hi_lo, batch, height, width, channels, stride, S(stream));
 }
 
 int yb_mb_conv0_raw_fwd(const float* x_nchw, const float* w_oihw, void* z_nhwc_f16, int batch, int height, int width, yb_stream_t stream) {
-  return yb::mb_conv0(x_nchw, w_oihw, nullptr, nullptr, z_nhwc_f16, batch, height, width, 1, S(stream));
+  return yb::mb_conv0(x_nchw, w_oihw, nullptr, nullptr, z_nhwc_f16, batch, height, width, 1, 0, S(stream));
 }
 
 int yb_mb_conv0_wgrad(const float* x_nchw, const void* dz_nhwc_f16, float* dw_oihw, int batch, int height, int width, yb_stream_t stream) {

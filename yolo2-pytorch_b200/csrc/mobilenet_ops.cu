@@ -11,7 +11,8 @@
 namespace yb {
 
 __global__ void __launch_bounds__(256) mb_conv0_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ scale,
-                                                       const float* __restrict__ shift, __half* __restrict__ y, int batch, int height, int width, int raw) {
+                                                       const float* __restrict__ shift, __half* __restrict__ y, int batch, int height, int width, int raw,
+                                                       int split) {
   __shared__ __align__(16) float ws[27][32];
   __shared__ float sc[32], sh[32];
   for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) ws[i / 32][i % 32] = w[(i % 32) * 27 + i / 32];
@@ -46,25 +47,33 @@ __global__ void __launch_bounds__(256) mb_conv0_kernel(const float* __restrict__
         }
       }
     }
-  uint4* dst = reinterpret_cast<uint4*>(y + idx * 32);
+  // split (strict precision): the pixel holds [hi 32 | lo 32], lo = fp16(v - fp32(hi)): the next layer reads hi + lo
+  uint4* dst = reinterpret_cast<uint4*>(y + idx * (split ? 64 : 32));
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    uint4 pk;
+    uint4 pk, pl;
     __half2* h = reinterpret_cast<__half2*>(&pk);
+    __half2* hl = reinterpret_cast<__half2*>(&pl);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int c = q * 8 + 2 * e;
       const float lo = raw ? -INFINITY : 0.f;          // raw (training forward): the conv output itself, BatchNorm / ReLU come later
-      h[e] = __floats2half2_rn(fmaxf(acc[c] * sc[c] + sh[c], lo), fmaxf(acc[c + 1] * sc[c + 1] + sh[c + 1], lo));
+      const float v0 = fmaxf(acc[c] * sc[c] + sh[c], lo), v1 = fmaxf(acc[c + 1] * sc[c + 1] + sh[c + 1], lo);
+      h[e] = __floats2half2_rn(v0, v1);
+      const float2 r = __half22float2(h[e]);
+      hl[e] = __floats2half2_rn(v0 - r.x, v1 - r.y);
     }
     dst[q] = pk;
+    if (split) dst[4 + q] = pl;
   }
 }
 
-int mb_conv0(const float* x, const float* w, const float* scale, const float* shift, void* y, int batch, int height, int width, int raw, cudaStream_t stream) {
-  YB_REQUIRE(x && w && (raw || (scale && shift)) && y && batch > 0 && height % 2 == 0 && width % 2 == 0, "mb_conv0: bad argument");
+int mb_conv0(const float* x, const float* w, const float* scale, const float* shift, void* y, int batch, int height, int width, int raw, int split,
+             cudaStream_t stream) {
+  YB_REQUIRE(x && w && (raw || (scale && shift)) && y && batch > 0 && height % 2 == 0 && width % 2 == 0 && !(raw && split), "mb_conv0: bad argument");
   const long long total = static_cast<long long>(batch) * (height / 2) * (width / 2);
-  mb_conv0_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(x, w, raw ? w : scale, raw ? w : shift, reinterpret_cast<__half*>(y), batch, height, width, raw);
+  mb_conv0_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(x, w, raw ? w : scale, raw ? w : shift, reinterpret_cast<__half*>(y), batch, height, width, raw,
+                                                                                 split);
   return check_launch("mb_conv0_kernel");
 }
 
@@ -190,6 +199,72 @@ int dwconv3x3(const void* x, const float* w, const float* scale, const float* sh
     else dwconv3x3_kernel<2, 4><<<grid, 128, 0, stream>>>(xp, w, scale, shift, yp, batch, height, width, channels, raw);
   }
   return check_launch("dwconv3x3_kernel");
+}
+
+// Strict-precision form (the plugin's `precision = strict`): activations travel as [hi | lo] fp16 pairs (x: [B,H,W,2C], y: [B,OH,OW,2C]), the
+// depthwise sum runs on hi + lo in fp32 and the result is split again, so a depthwise layer adds no fp16 rounding of its own.
+// One thread = 8 channels of one output pixel (18 loads); this mode trades speed for the 1e-3 contract.
+__global__ void __launch_bounds__(128) dwconv3x3_split_kernel(const __half* __restrict__ x, const float* __restrict__ w, const float* __restrict__ scale,
+                                                              const float* __restrict__ shift, __half* __restrict__ y, int batch, int height, int width,
+                                                              int channels, int stride) {
+  const int c8 = channels >> 3;
+  const int oh = height / stride, ow = width / stride;
+  const long long total = static_cast<long long>(batch) * oh * ow * c8;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cg = static_cast<int>(idx % c8);
+  long long t = idx / c8;
+  const int px = static_cast<int>(t % ow); t /= ow;
+  const int py = static_cast<int>(t % oh);
+  const long long img = t / oh;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  const float* wp = w + static_cast<long long>(cg) * 72;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int iy = py * stride - 1 + r;
+    if (iy < 0 || iy >= height) continue;
+#pragma unroll
+    for (int s2 = 0; s2 < 3; ++s2) {
+      const int ix = px * stride - 1 + s2;
+      if (ix < 0 || ix >= width) continue;
+      const __half* src = x + ((img * height + iy) * width + ix) * (2 * channels) + cg * 8;
+      const uint4 qh = __ldg(reinterpret_cast<const uint4*>(src)), ql = __ldg(reinterpret_cast<const uint4*>(src + channels));
+      const __half2* hh = reinterpret_cast<const __half2*>(&qh);
+      const __half2* hl = reinterpret_cast<const __half2*>(&ql);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 a = __half22float2(hh[e]), b = __half22float2(hl[e]);
+        acc[2 * e] = fmaf(a.x + b.x, __ldg(wp + (2 * e) * 9 + r * 3 + s2), acc[2 * e]);
+        acc[2 * e + 1] = fmaf(a.y + b.y, __ldg(wp + (2 * e + 1) * 9 + r * 3 + s2), acc[2 * e + 1]);
+      }
+    }
+  }
+  uint4 pk, pl;
+  __half2* ho = reinterpret_cast<__half2*>(&pk);
+  __half2* lo = reinterpret_cast<__half2*>(&pl);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int c = cg * 8 + 2 * e;
+    const float v0 = fmaxf(acc[2 * e] * __ldg(scale + c) + __ldg(shift + c), 0.f), v1 = fmaxf(acc[2 * e + 1] * __ldg(scale + c + 1) + __ldg(shift + c + 1), 0.f);
+    ho[e] = __floats2half2_rn(v0, v1);
+    const float2 rr = __half22float2(ho[e]);
+    lo[e] = __floats2half2_rn(v0 - rr.x, v1 - rr.y);
+  }
+  __half* dst = y + ((img * oh + py) * ow + px) * (2 * channels) + cg * 8;
+  *reinterpret_cast<uint4*>(dst) = pk;
+  *reinterpret_cast<uint4*>(dst + channels) = pl;
+}
+
+int dwconv3x3_split(const void* x, const float* w, const float* scale, const float* shift, void* y, int batch, int height, int width, int channels, int stride,
+                    cudaStream_t stream) {
+  YB_REQUIRE(x && w && scale && shift && y && batch > 0 && channels % 8 == 0 && (stride == 1 || stride == 2) && height % stride == 0 && width % stride == 0,
+             "dwconv3x3_split: bad argument");
+  const long long total = static_cast<long long>(batch) * (height / stride) * (width / stride) * (channels / 8);
+  dwconv3x3_split_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 0, stream>>>(reinterpret_cast<const __half*>(x), w, scale, shift,
+                                                                                        reinterpret_cast<__half*>(y), batch, height, width, channels, stride);
+  return check_launch("dwconv3x3_split_kernel");
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -8,7 +8,13 @@ contract x[B,3,H,W] fp32 -> [B, A*(5+C), H/32, W/32] fp32 (:84-85).  Modules onl
   13 x conv_unit      -> yb_dwconv3x3_bn_relu_fwd (depthwise, HBM-bound) + tcgen05 1x1 conv with fused BN + ReLU
   nn.Conv2d(1024, A*(5+C), 1) with bias -> tcgen05 1x1 conv writing fp32 NCHW.
 BatchNorm uses the PyTorch-default momentum 0.1 (unlike model.yolo2's 0.01) and the activation is ReLU (:28-29).
+
+Two inference precisions, as for Darknet (`set_precision`, `[b200] precision` in the INI, YB_PRECISION): `fast` (fp16 operands, 1.4e-3 from
+the fp32 reference after 27 layers) and `strict`: activations travel as [hi | lo] fp16 pairs, the pointwise convs and the head run the
+split-precision tcgen05 kernel (operands [a_hi | a_lo | a_hi] x [w_hi | w_hi | w_lo] in one fp32 accumulator), the first conv and the depthwise
+convs compute in fp32 on hi + lo -- within 1e-3 of the reference.
 """
+import os
 import collections
 
 import torch
@@ -70,6 +76,20 @@ class MobileNet(nn.Module):
                 nn.init.zeros_(m.bias)
         self._cache = {}
         self._trainer = None
+        config = getattr(config_channels, 'config', None)
+        precision = os.environ.get('YB_PRECISION')
+        if precision is None and config is not None and config.has_option('b200', 'precision'):
+            precision = config.get('b200', 'precision')
+        self.precision = 'fast'
+        self.set_precision(precision or 'fast')
+
+    def set_precision(self, precision):
+        if precision not in ('fast', 'strict'):
+            raise ValueError("precision must be 'fast' or 'strict', got %r" % (precision,))
+        if precision != self.precision:
+            self._cache = {}
+        self.precision = precision
+        return self
 
     @property
     def trainer(self):
@@ -101,6 +121,43 @@ class MobileNet(nn.Module):
             self._cache[key] = hit
         return hit[1]
 
+    def _packed_split(self, key, w):
+        ver = (w.data_ptr(), w._version)
+        hit = self._cache.get(key)
+        if hit is None or hit[0] != ver:
+            hit = (ver, _ops.pack_weight_split_f16(w.detach().contiguous(), True, True))
+            self._cache[key] = hit
+        return hit[1]
+
+    def _forward_strict(self, x):
+        b, c, h, w = x.shape
+        dev = x.device
+        first = self.layers[0]
+        scale, shift = self._fold('bn0', first.bn)
+        ch = first.conv.weight.shape[0]
+        cur = torch.empty(b, h // 2, w // 2, 2 * ch, dtype=torch.float16, device=dev)            # [hi | lo]
+        _ops.call('yb_mb_conv0_split_fwd', x, first.conv.weight.detach().contiguous(), scale, shift, cur, b, h, w)
+        hh, ww = h // 2, w // 2
+        for i, unit in enumerate(list(self.layers)[1:-1], 1):
+            dw, pw = unit.dw, unit.pw
+            stride = dw.conv.stride[0]
+            scale, shift = self._fold('dw%d' % i, dw.bn)
+            out = torch.empty(b, hh // stride, ww // stride, 2 * ch, dtype=torch.float16, device=dev)
+            _ops.call('yb_dwconv3x3_split_fwd', cur, dw.conv.weight.detach().contiguous().view(ch, 9), scale, shift, out, b, hh, ww, ch, stride)
+            hh, ww = hh // stride, ww // stride
+            scale, shift = self._fold('pw%d' % i, pw.bn)
+            cout = pw.conv.weight.shape[0]
+            cur = torch.empty(b, hh, ww, 2 * cout, dtype=torch.float16, device=dev)
+            _ops.conv_bn_act_split(out, self._packed_split('pws%d' % i, pw.conv.weight), scale, shift, 0.0, cur, a_channels=2 * ch, lo_ch_off=cout)
+            ch = cout
+        head = self.layers[-1]
+        cout = head.weight.shape[0]
+        ones = torch.ones(cout, dtype=torch.float32, device=dev)
+        feature = torch.empty(b, cout, hh, ww, dtype=torch.float32, device=dev)
+        _ops.conv_bn_act_split(cur, self._packed_split('heads', head.weight), ones, head.bias.detach().float().contiguous(), 1.0, feature,
+                               a_channels=2 * ch, out_mode=_ops.OUT_F32_NCHW)
+        return feature
+
     def forward(self, x):
         if self.training:
             # batch-statistics BatchNorm + autograd through the explicit backward chain (b200.train_engine.MobileNetTrainer)
@@ -113,10 +170,12 @@ class MobileNet(nn.Module):
             raise ValueError('MobileNet expects [B,3,H,W] with H, W multiples of 32')
         x = x.contiguous().float()
         first = self.layers[0]
-        scale, shift = self._fold('bn0', first.bn)
-        cur = torch.empty(b, h // 2, w // 2, first.conv.weight.shape[0], dtype=torch.float16, device=x.device)
         if first.conv.weight.shape[0] != 32:
             raise ValueError('MobileNet (B200): the first layer must have 32 output channels')
+        if self.precision == 'strict':
+            return self._forward_strict(x)
+        scale, shift = self._fold('bn0', first.bn)
+        cur = torch.empty(b, h // 2, w // 2, first.conv.weight.shape[0], dtype=torch.float16, device=x.device)
         _ops.call('yb_mb_conv0_bn_relu_fwd', x, first.conv.weight.detach().contiguous(), scale, shift, cur, b, h, w)
         hh, ww = h // 2, w // 2
         for i, unit in enumerate(list(self.layers)[1:-1], 1):
