@@ -125,7 +125,7 @@ __device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
 // kPair = true runs two CTAs of a (2,1,1) cluster as one cta_group::2 unit: every MMA is M = 256 (128 rows
 // from each CTA), each CTA stages only HALF of the weight tile (N/2 rows) and the tensor cores read the other
 // half from the peer SM, so the per-SM operand feed drops again by 25-33%.
-template <int BN, int BK, int MT, bool kPair>
+template <int BN, int BK, int MT, bool kPair, int EW = 4>
 struct ConvCfg {
   static constexpr int kSwizzle = BK * 2;                       // bytes per smem row
   static constexpr int kASubBytes = BM * BK * 2;
@@ -133,24 +133,28 @@ struct ConvCfg {
   static constexpr int kBRows = kPair ? BN / 2 : BN;            // weight rows staged by this CTA
   static constexpr int kBBytes = kBRows * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (196608 / kStageBytes) > 8 ? 8 : (196608 / kStageBytes);
+  static constexpr int kEpiWarps = EW;                          // 4, or 8 = two warps per TMEM lane quarter taking alternate 64-column chunks
+  static constexpr int kThreads = 64 + 32 * EW;
+  static constexpr int kOperandBudget = 196608 - (EW == 8 ? BM * 128 : 0);
+  static constexpr int kStages = (kOperandBudget / kStageBytes) > 8 ? 8 : (kOperandBudget / kStageBytes);
   static constexpr int kAccCols = MT * BN;                      // TMEM columns of one accumulator stage
   static constexpr int kAccStages = (2 * kAccCols <= 512) ? 2 : 1;
   static constexpr int kTmemCols = kAccStages * kAccCols;       // power of two in [64, 512]
   static constexpr int kRowsPerCta = BM * MT;
   static constexpr bool kMergedA = (MT == 2 && !kPair);        // A tile fetched by one 256-pixel TMA box
   static constexpr int kRowsPerTile = kRowsPerCta * (kPair ? 2 : 1);
-  static constexpr int kOutBytes = BM * 128;                   // TMA-store staging: 128 rows x 64 channels fp16
+  static constexpr int kOutBytes = (EW / 4) * BM * 128;         // TMA-store staging: one 32-row x 64-channel fp16 slice (4 KB) per epilogue warp
   static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 /*align slack*/ + 2 * 2 * BN * 4 /*scale/shift x2*/ + 2 * BN * 4 /*stats*/ + 256 /*barriers*/;
   static_assert(kSmemBytes <= 232448, "shared memory budget");
   static_assert(kAccCols <= 512, "accumulator does not fit TMEM");
 };
 
-template <int BN, int BK, int MT, bool kPair>
-__global__ void __launch_bounds__(kNumThreads, 1)
+template <int BN, int BK, int MT, bool kPair, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const __grid_constant__ CUtensorMap tmap_y, const ConvParams p) {
-  using Cfg = ConvCfg<BN, BK, MT, kPair>;
+  using Cfg = ConvCfg<BN, BK, MT, kPair, EW>;
+  constexpr int kEpiThreads = 32 * EW;          // shadows the file-scope constant of the 4-warp form
   constexpr int kAccStages = Cfg::kAccStages;
   constexpr int kStages = Cfg::kStages;
   constexpr bool kMergedA = Cfg::kMergedA;
@@ -185,7 +189,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_tfull + 8 * i, 1);
-      mbar_init(bar_tempty + 8 * i, kPair ? 8 : 4);
+      mbar_init(bar_tempty + 8 * i, (kPair ? 2 : 1) * EW);
     }
     fence_mbar_init();
     fence_proxy_async_smem();
@@ -326,7 +330,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;                    // TMEM lane quadrant this warp may read
-    const int et = threadIdx.x - 64;           // 0..127
+    const int eh = (warp - 2) >> 2;            // EW = 8: which of the quadrant's two warps (they take alternate 64- / 32-column chunks)
+    const int et = threadIdx.x - 64;           // 0 .. 32 * EW - 1
     int acc = 0;
     uint32_t acc_phase = 0;
     int buf = 0;
@@ -373,7 +378,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           }
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" :: "n"(32 * EW) : "memory");
       mbar_wait(bar_tfull + 8 * acc, acc_phase, p.dbg, 0x400 | acc);
       tc_fence_after();
       if (sk_dump) {
@@ -385,6 +390,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll 1
           for (int cc = 0; cc < BN / 32; ++cc) {
             if (n0 + cc * 32 >= p.cout) break;
+            if (EW == 8 && (((t * (BN / 32) + cc) & 1) != eh)) continue;
             uint32_t v[32];
             tmem_ld_32x32b_x32(taddr + cc * 32, v);
             tmem_ld_wait();
@@ -396,7 +402,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         }
         tc_fence_before();
         __threadfence();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" :: "n"(32 * EW) : "memory");
         if (et == 0) st_release_gpu(p.flags + blockIdx.x, 1u);
         if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
         if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
@@ -415,6 +421,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll 1
           for (int c2 = 0; c2 < BN / 64; ++c2) {
             if (n0 + c2 * 64 >= p.cout) break;
+            if (EW == 8 && (((t * (BN / 64) + c2) & 1) != eh)) continue;      // the quadrant's other warp takes this chunk
             uint4 pk[8];
             // both 32-column halves in flight before the single wait (a TMEM load is a few hundred cycles of latency)
             uint32_t vv[2][32];
@@ -485,14 +492,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             if (lane == 0) tma_store_wait_read<0>();
             __syncwarp();
             {
-              const uint32_t slice = smem_o + q * 4096 + lane * 128;
+              const uint32_t slice = smem_o + (eh * 4 + q) * 4096 + lane * 128;
 #pragma unroll
               for (int c = 0; c < 8; ++c) st_shared_v4(slice + ((c ^ (lane & 7)) << 4), pk[c]);
             }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0 && !(p.skip & 8)) {
-              tma_store_2d(&tmap_y, smem_o + q * 4096, n0 + c2 * 64, m_cta + t * BM + q * 32);      // rows >= M and channels >= Cout are clipped by the tensor map
+              tma_store_2d(&tmap_y, smem_o + (eh * 4 + q) * 4096, n0 + c2 * 64, m_cta + t * BM + q * 32);      // rows >= M and channels >= Cout are clipped by the tensor map
               tma_store_commit();
             }
           }
@@ -500,6 +507,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         }
 #pragma unroll 1
         for (int cc = 0; cc < BN / 32; ++cc) {
+          if (EW == 8 && (((t * (BN / 32) + cc) & 1) != eh)) continue;
           uint32_t v[32];
           tmem_ld_32x32b_x32(taddr + cc * 32, v);
           tmem_ld_wait();
@@ -603,18 +611,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       if (p.stats != nullptr) {
         // this tile's column sums -> the global double accumulators (the bar.sync at the top of the next tile orders the
         // re-zeroing of ep_stats after these reads)
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" :: "n"(32 * EW) : "memory");
         for (int i = et; i < BN; i += kEpiThreads) {
           if (n0 + i < p.cout) {
             atomicAdd(p.stats + n0 + i, static_cast<double>(ep_stats[i]));
             atomicAdd(p.stats + p.cout + n0 + i, static_cast<double>(ep_stats[BN + i]));
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" :: "n"(32 * EW) : "memory");
       }
       if (sk_collect) {
         // every reader is done with the partials: hand the slots back (the next writer is a later launch)
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" :: "n"(32 * EW) : "memory");
         for (int j = sk_lo + et; j < static_cast<int>(blockIdx.x); j += kEpiThreads) p.flags[j] = 0u;
       }
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
@@ -1125,12 +1133,12 @@ static int get_encoders(EncodeTiledFn* tiled, EncodeIm2colFn* im2col) {
 
 int get_tensor_map_encoders(EncodeTiledFn* tiled, EncodeIm2colFn* im2col) { return get_encoders(tiled, im2col); }
 
-template <int BN, int BK, int MT, bool kPair>
+template <int BN, int BK, int MT, bool kPair, int EW = 4>
 static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty, const ConvParams& p, cudaStream_t stream) {
-  using Cfg = ConvCfg<BN, BK, MT, kPair>;
+  using Cfg = ConvCfg<BN, BK, MT, kPair, EW>;
   static bool attr_set = false;
   if (!attr_set) {
-    YB_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, BK, MT, kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    YB_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, BK, MT, kPair, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
   const int tiles = p.m_tiles * p.n_tiles;
@@ -1159,16 +1167,35 @@ static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   } else {
     cfg.gridDim = dim3(tiles < sm_count() ? tiles : sm_count());
   }
-  cfg.blockDim = dim3(kNumThreads);
+  cfg.blockDim = dim3(Cfg::kThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
   cfg.attrs = attr; cfg.numAttrs = nattr;
-  YB_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BN, BK, MT, kPair>, ta, tb, ty, p));
+  YB_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BN, BK, MT, kPair, EW>, ta, tb, ty, p));
   return check_launch("conv_igemm_kernel");
+}
+
+// Eight epilogue warps (two per TMEM lane quarter, alternate 64-column chunks, own staging slices) for BLOCK_N <= 128, non-pair, non-stream-K
+// launches: built to test whether the per-tile epilogue chain bounds the 104^2 / 52^2 / 1x1 layers.  Measured on B200
+// (profiles/r02_epi_warps_ab.md): one batch in flight 25.77 k -> 25.97 k img/s, two lanes 33.67 k -> 33.52 k -- no gain, so the four-warp
+// form stays the default and YB_CONV_EPI_WARPS=8 selects this one.
+static int epi_warps_default() {
+  static const int v = getenv("YB_CONV_EPI_WARPS") ? atoi(getenv("YB_CONV_EPI_WARPS")) : 4;
+  return v == 8 ? 8 : 4;
 }
 
 template <int BK, bool kPair>
 static int dispatch_conv(int bn, int mt, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty, const ConvParams& p, cudaStream_t stream) {
+  if constexpr (!kPair) {
+    if (bn <= 128 && !p.streamk && epi_warps_default() == 8) {
+      if (mt == 1) {
+        if (bn == 64) return launch_conv<64, BK, 1, false, 8>(ta, tb, ty, p, stream);
+        return launch_conv<128, BK, 1, false, 8>(ta, tb, ty, p, stream);
+      }
+      if (bn == 64) return launch_conv<64, BK, 2, false, 8>(ta, tb, ty, p, stream);
+      return launch_conv<128, BK, 2, false, 8>(ta, tb, ty, p, stream);
+    }
+  }
   if (mt == 1) {
     if (bn == 64) return launch_conv<64, BK, 1, kPair>(ta, tb, ty, p, stream);
     if (bn == 128) return launch_conv<128, BK, 1, kPair>(ta, tb, ty, p, stream);
