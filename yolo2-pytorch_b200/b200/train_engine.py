@@ -94,6 +94,13 @@ class DarknetTrainer(object):
         self._side_streams = {}
         self._side_busy = False
         self._pack_plan = None
+        self._tracked = []
+
+    def _bump_tracked(self):
+        """`num_batches_tracked += 1` of every BatchNorm of the step as ONE multi-tensor kernel instead of one tiny launch per layer."""
+        if self._tracked:
+            torch._foreach_add_(self._tracked, 1)
+            self._tracked = []
 
     # ---- helpers -------------------------------------------------------------------------------------
     def _emit(self, name, grads):
@@ -196,7 +203,7 @@ class DarknetTrainer(object):
         self._fused_stats = False
         ops.call('yb_bn_finalize', sums, rows, c, float(bn.eps), float(bn.momentum), bn.running_mean, bn.running_var, mean, invstd)
         if bn.num_batches_tracked is not None:
-            bn.num_batches_tracked += 1
+            self._tracked.append(bn.num_batches_tracked)      # incremented together at the end of the forward pass (_bump_tracked)
         u._bver = None      # running stats changed behind torch's version counter: re-fold on the next eval forward
         return mean, invstd
 
@@ -225,6 +232,7 @@ class DarknetTrainer(object):
 
     # ---- forward -------------------------------------------------------------------------------------
     def forward(self, x):
+        self._tracked = []
         eng = self.engine
         if not x.is_cuda:
             raise RuntimeError('Darknet (B200) training: input must be a CUDA tensor')
@@ -300,6 +308,7 @@ class DarknetTrainer(object):
         record('layers3.0', u30, cat, z, mean, invstd, h32, w32, False)
         feature = ops.conv_bn_act(a30, u31.w16, u31.scale, u31.shift, 1.0, out_mode=ops.OUT_F32_NCHW)
         saved.a30, saved.cat, saved.x1, saved.h16, saved.w16, saved.h32, saved.w32 = a30, cat, x1, hh, ww, h32, w32
+        self._bump_tracked()
         return feature, saved
 
     # ---- backward ------------------------------------------------------------------------------------
@@ -498,6 +507,7 @@ class TinyTrainer(DarknetTrainer):
         return t
 
     def forward(self, x):
+        self._tracked = []
         if not x.is_cuda:
             raise RuntimeError('Tiny (B200) training: input must be a CUDA tensor')
         b, _, h, w = x.shape
@@ -558,6 +568,7 @@ class TinyTrainer(DarknetTrainer):
         key_h, u_h, _ = plan[-1]
         feature = ops.conv_bn_act(cur, u_h.w16, u_h.scale, u_h.shift, 1.0, out_mode=ops.OUT_F32_NCHW)
         saved.a_last, saved.hh, saved.ww, saved.head = cur, hh, ww, (key_h, u_h)
+        self._bump_tracked()
         return feature, saved
 
     def backward(self, saved, dfeature, dnn=None):
@@ -683,6 +694,7 @@ class MobileNetTrainer(DarknetTrainer):
         return names + ['layers.0.bn.weight', 'layers.0.bn.bias', 'layers.0.conv.weight']
 
     def forward(self, x):
+        self._tracked = []
         if not x.is_cuda:
             raise RuntimeError('MobileNet (B200) training: input must be a CUDA tensor')
         b, _, h, w = x.shape
@@ -731,6 +743,7 @@ class MobileNetTrainer(DarknetTrainer):
         ones = torch.ones(cout, dtype=torch.float32, device=dev)
         feature = ops.conv_bn_act(cur, w16, ones, head.bias.detach().float().contiguous(), 1.0, out_mode=ops.OUT_F32_NCHW)
         saved.a_last, saved.hh, saved.ww = cur, hh, ww
+        self._bump_tracked()
         return feature, saved
 
     def backward(self, saved, dfeature, dnn=None):
