@@ -578,7 +578,7 @@ struct W0Fuse {
 };
 
 template <bool kFused>
-__global__ void __launch_bounds__(256) conv0_wgrad_kernel(const float* __restrict__ x, const __half* __restrict__ dz, float* __restrict__ dw, int batch,
+__global__ void __launch_bounds__(256, kFused ? 3 : 1) conv0_wgrad_kernel(const float* __restrict__ x, const __half* __restrict__ dz, float* __restrict__ dw, int batch,
                                                           int height, int width, int tiles_x, int tiles_y, int num_tiles, const W0Fuse fz) {
   extern __shared__ __align__(16) uint8_t w0_raw[];
   W0Smem& sm = *reinterpret_cast<W0Smem*>(w0_raw);
@@ -674,27 +674,34 @@ __global__ void __launch_bounds__(256) conv0_wgrad_kernel(const float* __restric
         h8_to_f(*reinterpret_cast<const uint4*>(zp[w]), zf[w]);
       }
       h8_to_f(*reinterpret_cast<const uint4*>(&smf.dap[buf][win][cg * 8]), gp);
-      float out[4][8];
+      // per channel: which pixel of the window holds the maximum (2 bits each), and the routed gradient times sc (kept in gp)
+      uint32_t argbits = 0u;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int c = cg * 8 + i;
-        const float sc = smf.k[0][c], sh = smf.k[1][c], xa = smf.k[2][c], xb = smf.k[3][c], k1 = smf.k[4][c], k2 = smf.k[5][c];
+        const float sc = smf.k[0][c], sh = smf.k[1][c];
         float besty = fmaf(zf[0][i], sc, sh);
-        int arg = 0;
+        uint32_t arg = 0u;
 #pragma unroll
         for (int w = 1; w < 4; ++w) {
           const float y = fmaf(zf[w][i], sc, sh);
-          if (y > besty) { besty = y; arg = w; }
+          if (y > besty) { besty = y; arg = static_cast<uint32_t>(w); }
         }
-        const float dyb = besty > 0.f ? gp[i] : gp[i] * fz.slope;
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-          const float base = -fmaf(k2, fmaf(zf[w][i], xa, xb), k1);
-          out[w][i] = arg == w ? fmaf(sc, dyb, base) : base;
-        }
+        argbits |= arg << (2 * i);
+        gp[i] = sc * (besty > 0.f ? gp[i] : gp[i] * fz.slope);
       }
+      // one pixel at a time (keeps the live registers low: this kernel wants three blocks per SM)
 #pragma unroll
-      for (int w = 0; w < 4; ++w) *reinterpret_cast<uint4*>(zp[w]) = f_to_h8(out[w]);
+      for (int w = 0; w < 4; ++w) {
+        float out[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int c = cg * 8 + i;
+          const float base = -fmaf(smf.k[5][c], fmaf(zf[w][i], smf.k[2][c], smf.k[3][c]), smf.k[4][c]);
+          out[i] = ((argbits >> (2 * i)) & 3u) == static_cast<uint32_t>(w) ? gp[i] + base : base;
+        }
+        *reinterpret_cast<uint4*>(zp[w]) = f_to_h8(out);
+      }
       __syncthreads();
     }
     const float* pflat = &sm.patch[buf][0][0][0];
