@@ -153,7 +153,7 @@ class DarknetTrainer(object):
                 entries.append((key, u.conv.weight.detach(), True, True, cpad))
             plan = self._pack_plan = PackPlan(entries, device)
         plan.run()
-        units[0].w16 = units[0].conv.weight.detach()
+        units[0].w16 = units[0].conv.weight.detach().contiguous()
         for u, key in zip(units[1:], keys[1:]):
             u.w16 = plan.fwd[key]
             u._wver = None                      # the eval path re-checks (and may re-pack into its own buffer)
