@@ -121,6 +121,32 @@ def test_mobilenet_plugin_surface():
     assert sd['layers.14.bias'].shape == (125,) and sd['layers.3.dw.conv.weight'].shape == (128, 1, 3, 3)
 
 
+def test_pack_unit_table_matches_the_header_struct():
+    """b200.train_engine.PackPlan builds the device table of yb_pack_weights_batch with numpy: field order, sizes and the 48-byte stride
+    must be those of `yb_pack_unit` in include/yolo2_b200.h (3 pointers + 6 ints on LP64)."""
+    import re
+    from b200.train_engine import PackPlan
+    header = open(os.path.join(ROOT, 'include', 'yolo2_b200.h')).read()
+    body = re.search(r'typedef struct yb_pack_unit \{(.*?)\} yb_pack_unit;', header, re.S).group(1)
+    fields = []
+    for decl in body.split(';'):
+        decl = decl.strip()
+        if not decl:
+            continue
+        ctype, names = decl.rsplit(' ', 1) if ',' not in decl else (decl.split(' ', 1)[0], decl.split(' ', 1)[1])
+        for name in names.split(','):
+            name = name.strip()
+            fields.append(('ptr' if '*' in ctype or '*' in name else ctype.strip(), name.lstrip('*')))
+    assert [k for k, _ in fields] == ['ptr'] * 3 + ['int'] * 6, fields
+    dt = PackPlan.DTYPE
+    assert dt.itemsize == 48 and len(dt.names) == len(fields)
+    assert [dt.fields[n][1] for n in dt.names] == [0, 8, 16, 24, 28, 32, 36, 40, 44]
+    assert [dt.fields[n][0].itemsize for n in dt.names] == [8, 8, 8, 4, 4, 4, 4, 4, 4]
+    # logical order: weight, forward operand, data-gradient operand, cout, cin, ksize, cout_pad, block0, ci_blocks
+    assert [n for _, n in fields] == ['w_oihw', 'out_fwd', 'out_dgrad', 'cout', 'cin', 'ksize', 'cout_pad', 'block0', 'ci_blocks']
+    assert dt.names == ('w', 'f', 'd', 'cout', 'cin', 'k', 'cp', 'b0', 'cib')
+
+
 def test_resnet_plugin_surface():
     """model.resnet: constructors, torchvision-style state_dict keys, `scope` (reference model/resnet.py:144-158), loud failures."""
     import model
