@@ -1,5 +1,6 @@
 """CPU tests (no GPU): the C-ABI library builds/loads and exports every symbol include/*.h declares;
 the host-side mirror of the reference's plugin/config surface behaves like the reference."""
+import collections
 import configparser
 import ctypes
 import os
@@ -145,6 +146,39 @@ def test_pack_unit_table_matches_the_header_struct():
     # logical order: weight, forward operand, data-gradient operand, cout, cin, ksize, cout_pad, block0, ci_blocks
     assert [n for _, n in fields] == ['w_oihw', 'out_fwd', 'out_dgrad', 'cout', 'cin', 'ksize', 'cout_pad', 'block0', 'ci_blocks']
     assert dt.names == ('w', 'f', 'd', 'cout', 'cin', 'k', 'cp', 'b0', 'cib')
+
+
+def test_checkpoint_directory_round_trip_and_torch031_compat(tmp_path):
+    """utils.train: the reference's model-directory format (`<step>.pth` = OrderedDict of CPU tensors + `<step>.epoch`, utils/train.py:51-126),
+    Saver's keep-N tidy, load_model's latest-step rule, and loading a torch-0.3.1-style state_dict (no num_batches_tracked) into the plugin."""
+    import model
+    import model.yolo2
+    import utils.train
+    from oracle import yolo2_oracle as O
+    config = load_config()
+    dnn = model.yolo2.Darknet(model.ConfigChannels(config), O.anchors_yolo_voc(), 20)
+    saver = utils.train.Saver(str(tmp_path), keep=2, logger=None)
+    for step, epoch in ((10, 0), (200, 1), (3000, None)):
+        saver(utils.train.state_dict_cpu(dnn), step, epoch)
+    assert sorted(os.listdir(str(tmp_path))) == ['200.epoch', '200.pth', '3000.pth']
+    path, step, epoch = utils.train.load_model(str(tmp_path), logger=None)
+    assert (os.path.basename(path), step, epoch) == ('3000.pth', 3000, None)
+    assert utils.train.load_model(str(tmp_path), 200, logger=None)[1:] == (200, 1)
+    sd, step, epoch = utils.train.load_checkpoint(str(tmp_path), logger=None)
+    assert step == 3000 and set(sd) == set(dnn.state_dict())
+    # channel-pruned / checkpoint-shaped construction as the reference does it (detect.py:95): ConfigChannels(config, state_dict)
+    old = collections.OrderedDict((k, v) for k, v in O.make_state_dict(0).items())           # torch 0.3.1 style: no num_batches_tracked
+    assert not any(k.endswith('num_batches_tracked') for k in old)
+    dnn2 = model.yolo2.Darknet(model.ConfigChannels(config, old), O.anchors_yolo_voc(), 20)
+    utils.train.load_state_dict(dnn2, old)
+    assert torch.equal(dnn2.state_dict()['layers2.3.conv.weight'], old['layers2.3.conv.weight'])
+    bad = collections.OrderedDict(old)
+    bad.pop('layers1.4.bn.running_var')
+    with pytest.raises(RuntimeError):
+        utils.train.load_state_dict(dnn2, bad)
+    assert utils.train.load_sizes(config)[:1] and all(len(hw) == 2 for hw in utils.train.load_sizes(config))
+    t = utils.train.Timer(3600, first=True)
+    assert t() is True and t() is False and utils.train.Timer(3600, first=False)() is False
 
 
 def test_resnet_plugin_surface():
